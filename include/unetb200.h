@@ -1,0 +1,151 @@
+/* libunetb200 -- C ABI of the B200-native U-Net hot path.
+ *
+ * The reference (usnistgov/semantic-segmentation-unet) has no FFI of its own: UNet/model.py calls TensorFlow/Keras
+ * directly.  Each entry point below therefore replaces the *library kernel* TensorFlow would dispatch for one op of
+ * the reference graph; the citation after each declaration is the reference call site (file:line under
+ * /root/reference) whose arithmetic it implements.  A maintainer binds them with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 (UB_OK) or a negative UB_ERR_*; ub_last_error() holds a thread-local message;
+ *     nothing throws or aborts.
+ *   - all pointers are caller-owned DEVICE memory (except where noted), valid until `stream` reaches the op.
+ *     Launches are asynchronous on `stream`; no hidden synchronisation or allocation.
+ *   - activations are NHWC.  dtype: UB_BF16 (product path) or UB_F32 (fp32 check mode).
+ *   - conv weights (fp32 master and bf16 shadow) are packed [Cout][tap = 3*dy+dx][Cin]; deconv weights
+ *     [(2*a+b)*Cout + co][Cin]; "dgrad packs" are the transposes produced by ub_transpose_pack.
+ *   - "partial" buffers hold per-block partial sums: UB_STATS_ROWS rows; the entry point zero-fills them first.
+ */
+#ifndef UNETB200_H_
+#define UNETB200_H_
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB_VERSION 100
+#define UB_OK 0
+#define UB_ERR_INVALID_ARG (-1)
+#define UB_ERR_UNSUPPORTED_SHAPE (-2)
+#define UB_ERR_CUDA (-3)
+#define UB_ERR_NCCL (-4)
+
+#define UB_BF16 0
+#define UB_F32 1
+
+#define UB_STATS_ROWS 592   /* 148 SMs x 4: rows of every "partial" buffer */
+#define UB_MAX_CLASSES 8    /* number_classes supported by the head kernels */
+#define UB_ZSCORE_BLOCKS 256
+
+const char* ub_last_error(void);
+int ub_version(void);
+int ub_device_sm_count(void);
+
+/* ---- tensor-core implicit GEMMs (bf16 storage, fp32 accumulate in TMEM) -------------------------------------- */
+
+/* Conv2D(3x3, same, relu) forward over concat(x0, x1) -- UNet/model.py:30-35 (+ :57 concat).  stats (nullable):
+ * partial[UB_STATS_ROWS][2][Cout] sum / sum-of-squares of the activated output for the BatchNorm of model.py:36. */
+int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, void* out,
+                   float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream);
+/* Gradient w.r.t. the conv input (tape.gradient, UNet/model.py:219).  w_t = ub_transpose_pack(w, flip=1).
+ * Channels [0,C0) go to dx0 and [C0,C0+C1) to dx1 (gradient of the concat; C1 == 0 or C1 == C0). */
+int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H,
+                     int W, cudaStream_t stream);
+/* Gradient w.r.t. the conv kernel: dw fp32 [Cout][9][C0+C1] -- UNet/model.py:219. */
+long long ub_conv3x3_wgrad_workspace_bytes(int C0, int C1, int Cout, int N, int H, int W);
+int ub_conv3x3_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, void* workspace,
+                     long long workspace_bytes, int N, int H, int W, cudaStream_t stream);
+/* Conv2DTranspose(2x2, stride 2, same, no activation) -- UNet/model.py:41-46.  x [N,h,w,Cin] -> out [N,2h,2w,Cout];
+ * stats: partial[UB_STATS_ROWS][2][4*Cout] (finalise with groups = 4). */
+int ub_deconv2x2_fwd(const void* x, int Cin, const void* w, const float* bias, void* out, float* stats, int N, int h,
+                     int w_in, int Cout, cudaStream_t stream);
+int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int w_in,
+                       cudaStream_t stream);
+long long ub_deconv2x2_wgrad_workspace_bytes(int Cin, int Cout, int N, int h, int w_in);
+int ub_deconv2x2_wgrad(const void* x, int Cin, const void* dz, int Cout, float* dw, void* workspace,
+                       long long workspace_bytes, int N, int h, int w_in, cudaStream_t stream);
+
+/* ---- first layer (Cin <= 4) and class head --------------------------------------------------------------------- */
+
+/* Conv2D(3x3, same, relu) on the fp32 NCHW network input -- UNet/model.py:88.  w fp32 [64][9][Cin]. */
+int ub_conv_first_fwd(const float* x_nchw, const float* w, const float* bias, void* out, float* partial, int N, int H, int W,
+                      int Cin, int dtype, cudaStream_t stream);
+/* partial scratch: UB_STATS_ROWS * Cin * 9 * 64 floats */
+int ub_conv_first_wgrad(const float* x_nchw, const void* dz, float* dw, float* partial, int N, int H, int W, int Cin, int dtype,
+                        cudaStream_t stream);
+/* 1x1 Conv2D(relu) 64 -> K classes -- UNet/model.py:136.  a_out fp32 [P][K]; partial [UB_STATS_ROWS][2][K]. */
+int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, float* partial, long long P, int K, int dtype,
+                cudaStream_t stream);
+/* BatchNorm -> Softmax -> CategoricalCrossentropy + CategoricalAccuracy -- UNet/model.py:136-142, :211-215, :225-226.
+ * labels: uint8 class index per pixel (nullable: inference); class_w nullable (all ones = reference behaviour);
+ * dlogits = (softmax - onehot) * class_w[label] * inv_denom; partial[UB_STATS_ROWS][2] = {sum CE, #correct}. */
+int ub_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 const unsigned char* labels, const float* class_w, float inv_denom, float* softmax_out, float* dlogits,
+                 float* partial, long long P, int K, cudaStream_t stream);
+/* one-hot int32 [P][K] (the reference's label tensor, UNet/imagereader.py:302-312) -> uint8 index */
+int ub_onehot_to_index(const int* onehot, unsigned char* idx, long long P, int K, cudaStream_t stream);
+int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const float* rstd, float* partial, long long P, int K,
+                       cudaStream_t stream);
+/* partial: UB_STATS_ROWS rows of {dW[K][64], db[K]} */
+int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
+                      const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K,
+                      int dtype, cudaStream_t stream);
+/* Inference epilogue: argmax of the head written into the tile's zone of the mask -- UNet/inference.py:105-129. */
+int ub_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int h, int w_tile,
+                   int cy0, int cy1, int cx0, int cx1, int* mask, long long mask_ld, int dst_y, int dst_x, float* softmax_out,
+                   int dtype, cudaStream_t stream);
+
+/* ---- BatchNormalization(axis=1), eps 1e-3, momentum 0.99 -- UNet/model.py:36, :47 ------------------------------ */
+int ub_bn_stats(const void* a, float* partial, long long M, int C, int dtype, cudaStream_t stream);
+int ub_bn_finalize(const float* partial, int ncols, int groups, long long count, float* mean, float* rstd, float* moving_mean,
+                   float* moving_var, float momentum, float eps, cudaStream_t stream);
+int ub_bn_apply(const void* a, void* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                const unsigned char* drop_mask, long long M, int C, int dtype, cudaStream_t stream);
+/* BN apply (+Dropout, model.py:62) fused with MaxPool2D(2) (model.py:52): writes y, pooled and the argmax slot. */
+int ub_bn_apply_pool(const void* a, void* y, void* pooled, unsigned char* idx, const float* mean, const float* rstd,
+                     const float* gamma, const float* beta, const unsigned char* drop_mask, int N, int H, int W, int C, int dtype,
+                     cudaStream_t stream);
+int ub_bn_bwd_reduce(const void* dy, const void* a, const float* mean, const float* rstd, float* partial, long long M, int C,
+                     int dtype, cudaStream_t stream);
+int ub_bn_bwd_apply(const void* dy, const void* a, const float* mean, const float* rstd, const float* gamma, const float* dbeta,
+                    const float* dgamma, void* dz, float* partial, long long M, int C, int relu, int dtype, cudaStream_t stream);
+int ub_reduce_rows(const float* partial, int rows, int ncols, float* out, float scale, cudaStream_t stream);
+
+/* ---- pool / dropout backward ----------------------------------------------------------------------------------- */
+/* dy = maxpool_bwd(dpool, idx) + dskip (skip fan-out, model.py:91/:132 ...), optional dropout backward */
+int ub_maxpool2x2_bwd_add(const void* dpool, const unsigned char* idx, const void* dskip, const unsigned char* drop_mask, void* dy,
+                          int N, int H, int W, int C, int dtype, cudaStream_t stream);
+int ub_dropout_bwd(const void* in, const unsigned char* mask, void* out, long long n, int dtype, cudaStream_t stream);
+/* Philox4x32-10 Bernoulli(0.5) keep mask, one byte per element */
+int ub_dropout_mask(unsigned char* mask, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t stream);
+
+/* ---- optimizer / packing / input ------------------------------------------------------------------------------- */
+/* Keras Adam (UNet/model.py:79, :223): theta -= lr_t * m / (sqrt(v) + eps); optional bf16 shadow copy of theta */
+int ub_adam(float* param, const float* grad, float* m, float* v, void* bf16_shadow, long long n, float lr_t, float beta1,
+            float beta2, float eps, float grad_scale, cudaStream_t stream);
+/* dst[c][t'][r] = src(r,t,c) (t' = T-1-t when flip): builds the dgrad weight packs.
+ * src_layout 0: src [R][T][C] (conv [Cout][tap][Cin]); 1: src [T][R][C] (deconv [(2a+b)][Cout][Cin]) */
+int ub_transpose_pack(const float* src, void* dst, int R, int T, int C, int flip, int src_layout, int dst_dtype,
+                      cudaStream_t stream);
+int ub_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+/* zscore_normalize (UNet/imagereader.py:33-66) per plane; src_dtype 0 = u8, 1 = u16, 2 = f32;
+ * scratch: planes * UB_ZSCORE_BLOCKS * 2 doubles */
+int ub_zscore(const void* src, int src_dtype, float* dst, double* scratch, int planes, long long plane, cudaStream_t stream);
+
+/* ---- fp32 check mode (CUDA cores, fp32 storage) ----------------------------------------------------------------- */
+int ub_check_conv3x3(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias, float* out0, int Co0,
+                     float* out1, int Co1, int N, int H, int W, int relu, cudaStream_t stream);
+int ub_check_conv3x3_wgrad(const float* x0, int C0, const float* x1, int C1, const float* dz, int Cout, float* dw, int N, int H,
+                           int W, cudaStream_t stream);
+int ub_check_deconv2x2_fwd(const float* x, const float* w, const float* bias, float* out, int N, int h, int w_in, int Cin, int Cout,
+                           cudaStream_t stream);
+int ub_check_deconv2x2_dgrad(const float* dz, const float* w, float* dx, int N, int h, int w_in, int Cin, int Cout,
+                             cudaStream_t stream);
+int ub_check_deconv2x2_wgrad(const float* x, const float* dz, float* dw, int N, int h, int w_in, int Cin, int Cout,
+                             cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNETB200_H_ */

@@ -1,0 +1,656 @@
+// HBM-bound kernels of the U-Net step (sm_100a): BatchNorm statistics / apply / backward, 2x2 max-pool with argmax,
+// dropout, skip-gradient merge, Adam, weight repacking, dropout-mask generation, z-score normalisation.
+// All activations are NHWC; T = __nv_bfloat16 (product path) or float (fp32 check mode).  Every thread moves 8
+// consecutive channels (128-bit accesses for bf16); per-channel reductions are thread-private over a grid-stride
+// pixel loop, then one shared-memory tree per block, then one partial row per block (deterministic, no atomics).
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+template <typename T>
+struct V8;
+template <>
+struct V8<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]);
+    u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]);
+    u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <>
+struct V8<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+};
+
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) { V8<float>::load(p, f); }
+
+// value as it will be read back from storage of type T
+template <typename T>
+__device__ __forceinline__ float storage_round(float v);
+template <>
+__device__ __forceinline__ float storage_round<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
+template <>
+__device__ __forceinline__ float storage_round<float>(float v) { return v; }
+
+// Block-level finish of per-channel partials.  Thread t owns channel group g = t % G (8 channels) and pixel lane
+// t / G.  Writes row `blockIdx.x` of partial[rows][NCOMP][C].
+template <int NCOMP>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NCOMP][8], int C, float* __restrict__ partial, size_t row_stride = 0) {
+  if (row_stride == 0) row_stride = (size_t)NCOMP * C;
+  __shared__ float red[TPB * 8];
+  const int G = C >> 3;
+  const int PL = TPB / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+#pragma unroll
+  for (int comp = 0; comp < NCOMP; ++comp) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * C + g * 8 + i] = acc[comp][i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += TPB) {
+      float t = 0.f;
+      for (int l = 0; l < PL; ++l) t += red[l * C + c];
+      partial[(size_t)blockIdx.x * row_stride + (size_t)comp * C + c] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ BN statistics (standalone)
+template <typename T>
+__global__ void __launch_bounds__(TPB) bn_stats_kernel(const T* __restrict__ a, float* __restrict__ partial, long long M, int C) {
+  const int G = C >> 3, PL = TPB / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  float acc[2][8] = {};
+  for (long long px = (long long)blockIdx.x * PL + pl; px < M; px += (long long)gridDim.x * PL) {
+    float f[8];
+    V8<T>::load(a + px * C + g * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += f[i];
+      acc[1][i] += f[i] * f[i];
+    }
+  }
+  block_channel_reduce<2>(acc, C, partial);
+}
+
+// partial[rows][2][ncols]; channel c gathers columns g*C + c for g < groups.  Biased variance normalises (training),
+// the unbiased one feeds the moving average.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int ncols, int groups, double count,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ moving_mean,
+                                   float* __restrict__ moving_var, float momentum, float eps) {
+  const int C = ncols / groups;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int r = 0; r < rows; ++r)
+    for (int g = 0; g < groups; ++g) {
+      s += (double)partial[((size_t)r * 2 + 0) * ncols + g * C + c];
+      q += (double)partial[((size_t)r * 2 + 1) * ncols + g * C + c];
+    }
+  const double mu = s / count;
+  double var = q / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (moving_mean) {
+    const double unb = count > 1.0 ? var * (count / (count - 1.0)) : var;
+    moving_mean[c] = momentum * moving_mean[c] + (1.f - momentum) * (float)mu;
+    moving_var[c] = momentum * moving_var[c] + (1.f - momentum) * (float)unb;
+  }
+}
+
+// out[c] = scale * sum_rows partial[r][c]
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, int ncols, float* __restrict__ out, float scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  double s = 0.0;
+  for (int r = 0; r < rows; ++r) s += (double)partial[(size_t)r * ncols + c];
+  out[c] = (float)(s * (double)scale);
+}
+
+// ------------------------------------------------------------------ BN apply (+dropout) (+2x2 max-pool)
+// y = a*scale + shift with scale = gamma*rstd, shift = beta - mean*scale; optional inverted dropout (x2 on keep).
+template <typename T>
+__global__ void __launch_bounds__(TPB) bn_apply_kernel(const T* __restrict__ a, T* __restrict__ y, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const uint8_t* __restrict__ drop_mask,
+                                                       long long total8, int C) {
+  const int G = C >> 3;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total8; i += (long long)gridDim.x * TPB) {
+    const int c0 = (int)(i % G) * 8;
+    float f[8], mu[8], rs[8], ga[8], be[8];
+    V8<T>::load(a + i * 8, f);
+    load8f(mean + c0, mu); load8f(rstd + c0, rs); load8f(gamma + c0, ga); load8f(beta + c0, be);
+    uint2 dm = make_uint2(0x01010101u, 0x01010101u);
+    if (drop_mask) dm = __ldg(reinterpret_cast<const uint2*>(drop_mask + i * 8));
+    const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sc = ga[k] * rs[k];
+      float v = (f[k] - mu[k]) * sc + be[k];
+      if (drop_mask) v = dmb[k] ? 2.f * v : 0.f;
+      f[k] = v;
+    }
+    V8<T>::store(y + i * 8, f);
+  }
+}
+
+// One thread = one 2x2 window x 8 channels: writes the 4 normalised pixels, the pooled max and its slot (2*dy+dx,
+// first max wins, matching argmax tie-breaking of the oracle).
+template <typename T>
+__global__ void __launch_bounds__(TPB) bn_apply_pool_kernel(const T* __restrict__ a, T* __restrict__ y, T* __restrict__ pooled,
+                                                            uint8_t* __restrict__ idx, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const uint8_t* __restrict__ drop_mask,
+                                                            int N, int H, int W, int C) {
+  const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const int c0 = g * 8;
+    float mu[8], rs[8], ga[8], be[8], best[8];
+    int slot[8];
+    load8f(mean + c0, mu); load8f(rstd + c0, rs); load8f(gamma + c0, ga); load8f(beta + c0, be);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const long long off = (((long long)n * H + 2 * ho + (s >> 1)) * W + 2 * wo + (s & 1)) * C + c0;
+      float f[8];
+      V8<T>::load(a + off, f);
+      uint2 dm = make_uint2(0x01010101u, 0x01010101u);
+      if (drop_mask) dm = __ldg(reinterpret_cast<const uint2*>(drop_mask + off));
+      const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dm);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = (f[k] - mu[k]) * (ga[k] * rs[k]) + be[k];
+        if (drop_mask) v = dmb[k] ? 2.f * v : 0.f;
+        f[k] = v;
+      }
+      V8<T>::store(y + off, f);
+      // compare what the consumer will read (storage precision), so the saved slot agrees with a re-computed pool
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float r = storage_round<T>(f[k]);
+        if (s == 0 || r > best[k]) {
+          best[k] = r;
+          slot[k] = s;
+        }
+      }
+    }
+    const long long po = (((long long)n * Ho + ho) * Wo + wo) * C + c0;
+    V8<T>::store(pooled + po, best);
+    uint2 pk;
+    pk.x = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
+    pk.y = slot[4] | (slot[5] << 8) | (slot[6] << 16) | (slot[7] << 24);
+    *reinterpret_cast<uint2*>(idx + po) = pk;
+  }
+}
+
+// dy[n,h,w,c] = (slot matches ? dpool : 0) + dskip   (skip fan-out sum), optional dropout backward
+template <typename T>
+__global__ void __launch_bounds__(TPB) pool_bwd_add_kernel(const T* __restrict__ dpool, const uint8_t* __restrict__ idx,
+                                                           const T* __restrict__ dskip, const uint8_t* __restrict__ drop_mask,
+                                                           T* __restrict__ dy, int N, int H, int W, int C) {
+  const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int g = (int)(i % G);
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const int c0 = g * 8;
+    const long long po = (((long long)n * Ho + ho) * Wo + wo) * C + c0;
+    float dp[8];
+    V8<T>::load(dpool + po, dp);
+    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + po));
+    const uint8_t* sl = reinterpret_cast<const uint8_t*>(&pk);
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const long long off = (((long long)n * H + 2 * ho + (s >> 1)) * W + 2 * wo + (s & 1)) * C + c0;
+      float f[8];
+      if (dskip) V8<T>::load(dskip + off, f);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = 0.f;
+      }
+      uint2 dm = make_uint2(0x01010101u, 0x01010101u);
+      if (drop_mask) dm = __ldg(reinterpret_cast<const uint2*>(drop_mask + off));
+      const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dm);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = f[k] + (sl[k] == s ? dp[k] : 0.f);
+        if (drop_mask) v = dmb[k] ? 2.f * v : 0.f;
+        f[k] = v;
+      }
+      V8<T>::store(dy + off, f);
+    }
+  }
+}
+
+// out = in * (mask ? 2 : 0)   (dropout backward where no pool follows: the bottleneck)
+template <typename T>
+__global__ void __launch_bounds__(TPB) dropout_scale_kernel(const T* __restrict__ in, const uint8_t* __restrict__ mask, T* __restrict__ out,
+                                                            long long total8) {
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total8; i += (long long)gridDim.x * TPB) {
+    float f[8];
+    V8<T>::load(in + i * 8, f);
+    const uint2 dm = __ldg(reinterpret_cast<const uint2*>(mask + i * 8));
+    const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = dmb[k] ? 2.f * f[k] : 0.f;
+    V8<T>::store(out + i * 8, f);
+  }
+}
+
+// ------------------------------------------------------------------ BN backward
+// pass 1: partial[row][0][c] = sum dy, partial[row][1][c] = sum dy * xhat
+template <typename T>
+__global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ partial, long long M, int C) {
+  const int G = C >> 3, PL = TPB / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  float mu[8], rs[8];
+  load8f(mean + g * 8, mu);
+  load8f(rstd + g * 8, rs);
+  float acc[2][8] = {};
+  for (long long px = (long long)blockIdx.x * PL + pl; px < M; px += (long long)gridDim.x * PL) {
+    float d[8], f[8];
+    V8<T>::load(dy + px * C + g * 8, d);
+    V8<T>::load(a + px * C + g * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += d[i];
+      acc[1][i] += d[i] * (f[i] - mu[i]) * rs[i];
+    }
+  }
+  block_channel_reduce<2>(acc, C, partial);
+}
+
+// pass 2: dz = gamma*rstd*(dy - dbeta/M - xhat*dgamma/M) * [a > 0 if relu];  partial[row][0][c] = sum dz (bias gradient)
+template <typename T>
+__global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                           T* __restrict__ dz, float* __restrict__ partial, long long M, int C, int relu) {
+  const int G = C >> 3, PL = TPB / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  float mu[8], rs[8], ga[8], db[8], dg[8];
+  load8f(mean + g * 8, mu); load8f(rstd + g * 8, rs); load8f(gamma + g * 8, ga);
+  load8f(dbeta + g * 8, db); load8f(dgamma + g * 8, dg);
+  const float invM = 1.f / (float)M;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ga[i] *= rs[i];
+    db[i] *= invM;
+    dg[i] *= invM;
+  }
+  float acc[1][8] = {};
+  for (long long px = (long long)blockIdx.x * PL + pl; px < M; px += (long long)gridDim.x * PL) {
+    float d[8], f[8];
+    V8<T>::load(dy + px * C + g * 8, d);
+    V8<T>::load(a + px * C + g * 8, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (f[i] - mu[i]) * rs[i];
+      float v = ga[i] * (d[i] - db[i] - xh * dg[i]);
+      if (relu && !(f[i] > 0.f)) v = 0.f;
+      d[i] = v;
+    }
+    V8<T>::store(dz + px * C + g * 8, d);
+    // accumulate what the consumers (wgrad / dgrad) will read
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[0][i] += storage_round<T>(d[i]);
+  }
+  block_channel_reduce<1>(acc, C, partial);
+}
+
+// ------------------------------------------------------------------ Adam (Keras formula)
+__global__ void __launch_bounds__(TPB) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                   __nv_bfloat16* __restrict__ shadow, long long n, float lr_t, float b1, float b2, float eps,
+                                                   float gscale) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n4; i += (long long)gridDim.x * TPB) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* pa = &pp.x; const float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = ga[k] * gscale;
+      ma[k] = b1 * ma[k] + (1.f - b1) * gk;
+      va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+      pa[k] -= lr_t * ma[k] / (sqrtf(va[k]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) {
+      uint2 s;
+      s.x = pack_bf16x2(pp.x, pp.y);
+      s.y = pack_bf16x2(pp.z, pp.w);
+      reinterpret_cast<uint2*>(shadow)[i] = s;
+    }
+  }
+  // tail (n not a multiple of 4)
+  const long long i = n4 * 4 + (long long)blockIdx.x * TPB + threadIdx.x;
+  if (blockIdx.x == 0 && i < n) {
+    const float gk = g[i] * gscale;
+    m[i] = b1 * m[i] + (1.f - b1) * gk;
+    v[i] = b2 * v[i] + (1.f - b2) * gk * gk;
+    p[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+    if (shadow) shadow[i] = __float2bfloat16(p[i]);
+  }
+}
+
+// dst[c][t'][r] = src(r, t, c), t' = flip ? T-1-t : t;  dst (bf16 or fp32) is [C][T][R].
+// src_layout 0: src fp32 [R][T][C] (conv kernels [Cout][tap][Cin]); 1: src fp32 [T][R][C] (deconv kernels [(ab)][Cout][Cin])
+template <typename TO>
+__global__ void transpose_pack_kernel(const float* __restrict__ src, TO* __restrict__ dst, int R, int T, int C, int flip, int src_layout) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    const size_t si = src_layout ? ((size_t)t * R + r) * C + c : ((size_t)r * T + t) * C + c;
+    tile[j][threadIdx.x] = (r < R && c < C) ? src[si] : 0.f;
+  }
+  __syncthreads();
+  const int tt = flip ? T - 1 - t : t;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < C) dst[((size_t)c * T + tt) * R + r] = (TO)tile[threadIdx.x][j];
+  }
+}
+
+__global__ void __launch_bounds__(TPB) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) dst[i] = __float2bfloat16(src[i]);
+}
+
+// ------------------------------------------------------------------ dropout mask (Philox4x32-10, keep prob 0.5)
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// one thread -> 16 mask bytes (128 random bits would give 128 masks; we spend 8 bits per element for simplicity)
+__global__ void __launch_bounds__(TPB) dropout_mask_kernel(uint8_t* __restrict__ mask, long long n16, unsigned long long seed,
+                                                           unsigned long long offset) {
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n16; i += (long long)gridDim.x * TPB) {
+    const unsigned long long ctr = offset + (unsigned long long)i;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint4 out;
+    uint32_t* o = &out.x;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) o[w] = (c[w] & 0x01010101u);   // bit 0 of each byte: Bernoulli(0.5)
+    reinterpret_cast<uint4*>(mask)[i] = out;
+  }
+}
+
+// ------------------------------------------------------------------ z-score (UNet/imagereader.py:33-66)
+// stats: per (image, channel) plane sum and sum of squares in fp64; input u8 / u16 / f32 planes (NCHW).
+template <typename TI>
+__global__ void __launch_bounds__(TPB) zscore_stats_kernel(const TI* __restrict__ x, double* __restrict__ sums, long long plane) {
+  const TI* xp = x + (long long)blockIdx.y * plane;
+  double s = 0.0, q = 0.0;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < plane; i += (long long)gridDim.x * TPB) {
+    const double v = (double)(float)xp[i];
+    s += v;
+    q += v * v;
+  }
+  __shared__ double sh[2][TPB / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = s;
+    sh[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < TPB / 32; ++w) {
+      ts += sh[0][w];
+      tq += sh[1][w];
+    }
+    // [plane][block][2] partials; summed in fixed order by the apply kernel
+    sums[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 0] = ts;
+    sums[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 1] = tq;
+  }
+}
+template <typename TI>
+__global__ void __launch_bounds__(TPB) zscore_apply_kernel(const TI* __restrict__ x, float* __restrict__ y, const double* __restrict__ sums,
+                                                           int nblk, long long plane) {
+  __shared__ float s_mu, s_inv;
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+      ts += sums[((size_t)blockIdx.y * nblk + b) * 2 + 0];
+      tq += sums[((size_t)blockIdx.y * nblk + b) * 2 + 1];
+    }
+    const double mu = ts / (double)plane;
+    double var = tq / (double)plane - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float sd = (float)sqrt(var);
+    s_mu = (float)mu;
+    s_inv = (sd <= 1.0f) ? 1.0f : sd;          // std <= 1 -> subtract the mean only (divide by 1)
+  }
+  __syncthreads();
+  const TI* xp = x + (long long)blockIdx.y * plane;
+  float* yp = y + (long long)blockIdx.y * plane;
+  const float mu = s_mu, inv = s_inv;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < plane; i += (long long)gridDim.x * TPB)
+    yp[i] = ((float)xp[i] - mu) / inv;
+}
+
+inline int grid_for(long long work_items, int per_block, int cap) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+bool channels_ok(int C) { return C >= 64 && C <= 2048 && (C & (C - 1)) == 0; }
+
+}  // namespace
+
+#define UB_DISPATCH_T(dtype, ...)                                   \
+  do {                                                              \
+    if ((dtype) == UB_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((dtype) == UB_F32) { using T = float; __VA_ARGS__; }   \
+    else { ub_set_error("bad dtype %d", (int)(dtype)); return UB_ERR_INVALID_ARG; } \
+  } while (0)
+
+extern "C" {
+
+int ub_bn_stats(const void* a, float* partial, long long M, int C, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(a && partial && M > 0, "bn_stats: bad args");
+  UB_CHECK_SHAPE(channels_ok(C), "bn_stats: C=%d must be a power of two in [64,2048]", C);
+  UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * C, stream));
+  const int PL = TPB / (C >> 3);
+  const int grid = grid_for(M, PL * 4, UB_STATS_ROWS);
+  UB_DISPATCH_T(dtype, (bn_stats_kernel<T><<<grid, TPB, 0, stream>>>((const T*)a, partial, M, C)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_finalize(const float* partial, int ncols, int groups, long long count, float* mean, float* rstd, float* moving_mean,
+                   float* moving_var, float momentum, float eps, cudaStream_t stream) {
+  UB_CHECK_ARG(partial && mean && rstd && groups > 0 && ncols % groups == 0 && count > 0, "bn_finalize: bad args");
+  const int C = ncols / groups;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, UB_STATS_ROWS, ncols, groups, (double)count, mean, rstd, moving_mean,
+                                                         moving_var, momentum, eps);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_reduce_rows(const float* partial, int rows, int ncols, float* out, float scale, cudaStream_t stream) {
+  UB_CHECK_ARG(partial && out && rows > 0 && ncols > 0, "reduce_rows: bad args");
+  reduce_rows_kernel<<<(ncols + 127) / 128, 128, 0, stream>>>(partial, rows, ncols, out, scale);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_apply(const void* a, void* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                const unsigned char* drop_mask, long long M, int C, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(a && y && mean && rstd && gamma && beta && M > 0, "bn_apply: bad args");
+  UB_CHECK_SHAPE(C % 8 == 0, "bn_apply: C %% 8");
+  const long long total8 = M * (C / 8);
+  const int grid = grid_for(total8, TPB, ub_num_sms() * 16);
+  UB_DISPATCH_T(dtype, (bn_apply_kernel<T><<<grid, TPB, 0, stream>>>((const T*)a, (T*)y, mean, rstd, gamma, beta, drop_mask, total8, C)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_apply_pool(const void* a, void* y, void* pooled, unsigned char* idx, const float* mean, const float* rstd,
+                     const float* gamma, const float* beta, const unsigned char* drop_mask, int N, int H, int W, int C, int dtype,
+                     cudaStream_t stream) {
+  UB_CHECK_ARG(a && y && pooled && idx && mean && rstd && gamma && beta, "bn_apply_pool: bad args");
+  UB_CHECK_SHAPE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "bn_apply_pool: C %% 8, even H/W");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  const int grid = grid_for(total, TPB, ub_num_sms() * 16);
+  UB_DISPATCH_T(dtype, (bn_apply_pool_kernel<T><<<grid, TPB, 0, stream>>>((const T*)a, (T*)y, (T*)pooled, idx, mean, rstd, gamma, beta,
+                                                                         drop_mask, N, H, W, C)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_maxpool2x2_bwd_add(const void* dpool, const unsigned char* idx, const void* dskip, const unsigned char* drop_mask, void* dy,
+                          int N, int H, int W, int C, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(dpool && idx && dy, "maxpool2x2_bwd_add: bad args");
+  UB_CHECK_SHAPE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_bwd_add: C %% 8, even H/W");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  const int grid = grid_for(total, TPB, ub_num_sms() * 16);
+  UB_DISPATCH_T(dtype, (pool_bwd_add_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dpool, idx, (const T*)dskip, drop_mask, (T*)dy, N, H, W, C)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_dropout_bwd(const void* in, const unsigned char* mask, void* out, long long n, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(in && mask && out && n % 8 == 0, "dropout_bwd: bad args");
+  const int grid = grid_for(n / 8, TPB, ub_num_sms() * 16);
+  UB_DISPATCH_T(dtype, (dropout_scale_kernel<T><<<grid, TPB, 0, stream>>>((const T*)in, mask, (T*)out, n / 8)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_bwd_reduce(const void* dy, const void* a, const float* mean, const float* rstd, float* partial, long long M, int C, int dtype,
+                     cudaStream_t stream) {
+  UB_CHECK_ARG(dy && a && mean && rstd && partial && M > 0, "bn_bwd_reduce: bad args");
+  UB_CHECK_SHAPE(channels_ok(C), "bn_bwd_reduce: C=%d must be a power of two in [64,2048]", C);
+  UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * C, stream));
+  const int PL = TPB / (C >> 3);
+  const int grid = grid_for(M, PL * 4, UB_STATS_ROWS);
+  UB_DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dy, (const T*)a, mean, rstd, partial, M, C)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_bwd_apply(const void* dy, const void* a, const float* mean, const float* rstd, const float* gamma, const float* dbeta,
+                    const float* dgamma, void* dz, float* partial, long long M, int C, int relu, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(dy && a && mean && rstd && gamma && dbeta && dgamma && dz && partial && M > 0, "bn_bwd_apply: bad args");
+  UB_CHECK_SHAPE(channels_ok(C), "bn_bwd_apply: C=%d must be a power of two in [64,2048]", C);
+  UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * C, stream));
+  const int PL = TPB / (C >> 3);
+  const int grid = grid_for(M, PL * 4, UB_STATS_ROWS);
+  UB_DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dy, (const T*)a, mean, rstd, gamma, dbeta, dgamma, (T*)dz,
+                                                                        partial, M, C, relu)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_adam(float* param, const float* grad, float* m, float* v, void* bf16_shadow, long long n, float lr_t, float beta1, float beta2,
+            float eps, float grad_scale, cudaStream_t stream) {
+  UB_CHECK_ARG(param && grad && m && v && n > 0, "adam: bad args");
+  const int grid = grid_for(n / 4 + 1, TPB, ub_num_sms() * 8);
+  adam_kernel<<<grid, TPB, 0, stream>>>(param, grad, m, v, (__nv_bfloat16*)bf16_shadow, n, lr_t, beta1, beta2, eps, grad_scale);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_transpose_pack(const float* src, void* dst, int R, int T, int C, int flip, int src_layout, int dst_dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(src && dst && R > 0 && T > 0 && C > 0, "transpose_pack: bad args");
+  dim3 grid((C + 31) / 32, (R + 31) / 32, T), block(32, 8);
+  if (dst_dtype == UB_BF16) transpose_pack_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(src, (__nv_bfloat16*)dst, R, T, C, flip, src_layout);
+  else if (dst_dtype == UB_F32) transpose_pack_kernel<float><<<grid, block, 0, stream>>>(src, (float*)dst, R, T, C, flip, src_layout);
+  else { ub_set_error("transpose_pack: bad dtype"); return UB_ERR_INVALID_ARG; }
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+  UB_CHECK_ARG(src && dst && n > 0, "cast_bf16: bad args");
+  cast_bf16_kernel<<<grid_for(n, TPB, ub_num_sms() * 8), TPB, 0, stream>>>(src, (__nv_bfloat16*)dst, n);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_dropout_mask(unsigned char* mask, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
+  UB_CHECK_ARG(mask && n > 0 && n % 16 == 0, "dropout_mask: n must be a multiple of 16");
+  dropout_mask_kernel<<<grid_for(n / 16, TPB, ub_num_sms() * 8), TPB, 0, stream>>>(mask, n / 16, seed, offset);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+// src planes [planes][plane] of src_dtype (0 = u8, 1 = u16, 2 = f32) -> dst fp32, each plane z-scored on its own.
+// scratch: at least planes * UB_ZSCORE_BLOCKS * 2 doubles.
+int ub_zscore(const void* src, int src_dtype, float* dst, double* scratch, int planes, long long plane, cudaStream_t stream) {
+  UB_CHECK_ARG(src && dst && scratch && planes > 0 && plane > 0, "zscore: bad args");
+  const int nblk = grid_for(plane, TPB * 8, UB_ZSCORE_BLOCKS);
+  dim3 grid(nblk, planes);
+  dim3 agrid(grid_for(plane, TPB * 4, 4096), planes);
+  if (src_dtype == 0) {
+    zscore_stats_kernel<uint8_t><<<grid, TPB, 0, stream>>>((const uint8_t*)src, scratch, plane);
+    zscore_apply_kernel<uint8_t><<<agrid, TPB, 0, stream>>>((const uint8_t*)src, dst, scratch, nblk, plane);
+  } else if (src_dtype == 1) {
+    zscore_stats_kernel<uint16_t><<<grid, TPB, 0, stream>>>((const uint16_t*)src, scratch, plane);
+    zscore_apply_kernel<uint16_t><<<agrid, TPB, 0, stream>>>((const uint16_t*)src, dst, scratch, nblk, plane);
+  } else if (src_dtype == 2) {
+    zscore_stats_kernel<float><<<grid, TPB, 0, stream>>>((const float*)src, scratch, plane);
+    zscore_apply_kernel<float><<<agrid, TPB, 0, stream>>>((const float*)src, dst, scratch, nblk, plane);
+  } else {
+    ub_set_error("zscore: bad src dtype %d", src_dtype);
+    return UB_ERR_INVALID_ARG;
+  }
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,589 @@
+// First layer (Cin <= 4, not a tensor-core problem) and the class head of the U-Net (sm_100a, HBM-bound).
+//
+//   conv_first : relu(conv3x3_same(x_nchw_fp32, W) + b) -> NHWC 64 channels (+BN stat partials)   UNet/model.py:88
+//   head_fwd   : relu(conv1x1(x, W) + b), 64 -> K classes, fp32 [P][K] (+BN stat partials)          UNet/model.py:136
+//   head_loss  : BN -> softmax -> cross-entropy, argmax, accuracy count, dL/dlogits                 UNet/model.py:139-142, 211-215
+//   head_bwd   : BN backward + ReLU mask + 1x1 dgrad / wgrad / bias grad
+//   head_argmax: inference epilogue -- BN(moving stats folded) -> argmax written straight into the tile's zone of the
+//                output mask (UNet/inference.py:105-129), optional softmax for the model-call contract
+// Thread mapping for the 64-channel tensors: 8 threads per pixel x 8 channels each (128-bit bf16 accesses, a warp
+// covers 4 pixels = 512 contiguous bytes); class-dimension reductions use warp shuffles.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+constexpr int KMAX = UB_MAX_CLASSES;
+
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+template <>
+__device__ __forceinline__ void st8<float>(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// sum `v` over all threads of the block; result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* sh /*[TPB/32]*/) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < TPB / 32; ++w) t += sh[w];
+  return t;
+}
+
+// ------------------------------------------------------------------ first conv
+// x: fp32 NCHW [N][CIN][H][W]; w: fp32 [64][9][CIN]; out: NHWC [P][64]; partial: [rows][2][64]
+template <typename T, int CIN>
+__global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                             T* __restrict__ out, float* __restrict__ partial, int N, int H, int W) {
+  __shared__ float ws[9 * CIN][64];
+  __shared__ float red[TPB * 8];
+  for (int i = threadIdx.x; i < 64 * 9 * CIN; i += TPB) {
+    const int co = i / (9 * CIN), k = i % (9 * CIN);
+    ws[k][co] = w[i];
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = bias[sub * 8 + i];
+  float acc_s[8] = {}, acc_q[8] = {};
+  const long long P = (long long)N * H * W;
+  const long long plane = (long long)H * W;
+  for (long long px = (long long)blockIdx.x * 32 + pl; px < P; px += (long long)gridDim.x * 32) {
+    const int n = (int)(px / plane);
+    const int rem = (int)(px - (long long)n * plane);
+    const int h = rem / W, wv = rem % W;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = b[i];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = wv + t % 3 - 1;
+      const bool in = (hh >= 0) && (hh < H) && (ww >= 0) && (ww < W);
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float xv = in ? __ldg(x + ((long long)n * CIN + ci) * plane + (long long)hh * W + ww) : 0.f;
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[t * CIN + ci][sub * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[t * CIN + ci][sub * 8 + 4]);
+        o[0] += xv * w0.x; o[1] += xv * w0.y; o[2] += xv * w0.z; o[3] += xv * w0.w;
+        o[4] += xv * w1.x; o[5] += xv * w1.y; o[6] += xv * w1.z; o[7] += xv * w1.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i] = fmaxf(o[i], 0.f);
+      acc_s[i] += o[i];
+      acc_q[i] += o[i] * o[i];
+    }
+    st8<T>(out + px * 64 + sub * 8, o);
+  }
+  if (partial) {
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[pl * 64 + sub * 8 + i] = comp ? acc_q[i] : acc_s[i];
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        float t = 0.f;
+        for (int l = 0; l < 32; ++l) t += red[l * 64 + threadIdx.x];
+        partial[((size_t)blockIdx.x * 2 + comp) * 64 + threadIdx.x] = t;
+      }
+    }
+  }
+}
+
+// dW partial[row][ci][tap][64] = sum_p dz[p][co] * x[p + tap][ci]   (blockIdx.y = ci)
+template <typename T>
+__global__ void __launch_bounds__(TPB) conv_first_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dz, float* __restrict__ partial,
+                                                               int N, int H, int W, int CIN) {
+  __shared__ float red[TPB * 8];
+  const int ci = blockIdx.y;
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float acc[9][8] = {};
+  const long long P = (long long)N * H * W;
+  const long long plane = (long long)H * W;
+  for (long long px = (long long)blockIdx.x * 32 + pl; px < P; px += (long long)gridDim.x * 32) {
+    const int n = (int)(px / plane);
+    const int rem = (int)(px - (long long)n * plane);
+    const int h = rem / W, wv = rem % W;
+    float d[8];
+    ld8<T>(dz + px * 64 + sub * 8, d);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hh = h + t / 3 - 1, ww = wv + t % 3 - 1;
+      const bool in = (hh >= 0) && (hh < H) && (ww >= 0) && (ww < W);
+      const float xv = in ? __ldg(x + ((long long)n * CIN + ci) * plane + (long long)hh * W + ww) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[t][i] += xv * d[i];
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * 64 + sub * 8 + i] = acc[t][i];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float s = 0.f;
+      for (int l = 0; l < 32; ++l) s += red[l * 64 + threadIdx.x];
+      partial[(((size_t)blockIdx.x * CIN + ci) * 9 + t) * 64 + threadIdx.x] = s;
+    }
+  }
+}
+// dw[co][tap][ci] = sum_rows partial[row][ci][tap][co]
+__global__ void conv_first_wgrad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ dw, int rows, int CIN) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 9 * CIN) return;
+  const int co = i / (9 * CIN), r = i % (9 * CIN), t = r / CIN, ci = r % CIN;
+  double s = 0.0;
+  for (int row = 0; row < rows; ++row) s += (double)partial[(((size_t)row * CIN + ci) * 9 + t) * 64 + co];
+  dw[i] = (float)s;
+}
+
+// ------------------------------------------------------------------ head forward: a[P][K] = relu(x[P][64] . w[K][64] + b)
+template <typename T>
+__global__ void __launch_bounds__(TPB) head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ a_out, float* __restrict__ partial, long long P, int K) {
+  __shared__ float sh[TPB / 32];
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float wr[KMAX][8];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wr[k][i] = (k < K) ? w[k * 64 + sub * 8 + i] : 0.f;
+  float s[KMAX] = {}, q[KMAX] = {};
+  const long long iters = (P + 31) / 32;
+  for (long long it = blockIdx.x; it < iters; it += gridDim.x) {
+    const long long px = it * 32 + pl;
+    const bool ok = px < P;
+    float f[8] = {};
+    if (ok) ld8<T>(x + px * 64 + sub * 8, f);
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d += wr[k][i] * f[i];
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        const float a = fmaxf(d + b[k], 0.f);
+        if (ok && sub == (k & 7)) {
+          a_out[px * K + k] = a;
+          s[k] += a;
+          q[k] += a * a;
+        }
+      }
+    }
+  }
+  if (partial) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        const float ts = block_sum(s[k], sh);
+        const float tq = block_sum(q[k], sh);
+        if (threadIdx.x == 0) {
+          partial[((size_t)blockIdx.x * 2 + 0) * K + k] = ts;
+          partial[((size_t)blockIdx.x * 2 + 1) * K + k] = tq;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ head loss
+// per pixel: y = BN(a); p = softmax(y); ce = -log p[label]; partial[row] = {sum ce * cw[label], #correct}
+// dlogits = (p - onehot) * cw[label] * inv_denom ; optional softmax output
+__global__ void __launch_bounds__(TPB) head_loss_kernel(const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const uint8_t* __restrict__ labels, const float* __restrict__ class_w, float inv_denom,
+                                                        float* __restrict__ softmax_out, float* __restrict__ dlogits, float* __restrict__ partial,
+                                                        long long P, int K) {
+  __shared__ float sh[TPB / 32];
+  float sc[KMAX], sf[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    sc[k] = (k < K) ? gamma[k] * rstd[k] : 0.f;
+    sf[k] = (k < K) ? beta[k] - mean[k] * sc[k] : 0.f;
+  }
+  float loss = 0.f, correct = 0.f;
+  for (long long px = (long long)blockIdx.x * TPB + threadIdx.x; px < P; px += (long long)gridDim.x * TPB) {
+    float y[KMAX];
+    float mx = -INFINITY;
+    int am = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        y[k] = a[px * K + k] * sc[k] + sf[k];
+        if (y[k] > mx) {
+          mx = y[k];
+          am = k;
+        }
+      }
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        y[k] = __expf(y[k] - mx);
+        se += y[k];
+      }
+    const float inv = 1.f / se;
+    const int lab = labels ? (int)labels[px] : 0;
+    const float cw = class_w ? class_w[lab] : 1.f;
+    float pl = 1.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        const float p = y[k] * inv;
+        if (k == lab) pl = p;
+        if (softmax_out) softmax_out[px * K + k] = p;
+        if (dlogits) dlogits[px * K + k] = (p - (k == lab ? 1.f : 0.f)) * cw * inv_denom;
+      }
+    if (labels) {
+      loss += -__logf(fmaxf(pl, 1e-37f)) * cw;
+      correct += (am == lab) ? 1.f : 0.f;
+    }
+  }
+  if (partial) {
+    const float tl = block_sum(loss, sh);
+    const float tc = block_sum(correct, sh);
+    if (threadIdx.x == 0) {
+      partial[(size_t)blockIdx.x * 2 + 0] = tl;
+      partial[(size_t)blockIdx.x * 2 + 1] = tc;
+    }
+  }
+}
+
+// one-hot int32 [P][K] -> uint8 class index (argmax, first max): the reference's label contract (imagereader.py:302-312)
+__global__ void __launch_bounds__(TPB) onehot_to_index_kernel(const int* __restrict__ onehot, uint8_t* __restrict__ idx, long long P, int K) {
+  for (long long px = (long long)blockIdx.x * TPB + threadIdx.x; px < P; px += (long long)gridDim.x * TPB) {
+    int best = onehot[px * K], am = 0;
+    for (int k = 1; k < K; ++k) {
+      const int v = onehot[px * K + k];
+      if (v > best) {
+        best = v;
+        am = k;
+      }
+    }
+    idx[px] = (uint8_t)am;
+  }
+}
+
+// ------------------------------------------------------------------ head backward
+// pass 1: partial[row][0][k] = sum dy_k ; partial[row][1][k] = sum dy_k * xhat_k
+__global__ void __launch_bounds__(TPB) head_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ a, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, float* __restrict__ partial, long long P, int K) {
+  __shared__ float sh[TPB / 32];
+  float s[KMAX] = {}, q[KMAX] = {};
+  for (long long px = (long long)blockIdx.x * TPB + threadIdx.x; px < P; px += (long long)gridDim.x * TPB) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        const float d = dy[px * K + k];
+        s[k] += d;
+        q[k] += d * (a[px * K + k] - mean[k]) * rstd[k];
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) {
+      const float ts = block_sum(s[k], sh);
+      const float tq = block_sum(q[k], sh);
+      if (threadIdx.x == 0) {
+        partial[((size_t)blockIdx.x * 2 + 0) * K + k] = ts;
+        partial[((size_t)blockIdx.x * 2 + 1) * K + k] = tq;
+      }
+    }
+}
+
+// pass 2: dz_k = gamma_k rstd_k (dy_k - dbeta_k/P - xhat_k dgamma_k/P) [a_k > 0]
+//         dx[p][c] = sum_k w[k][c] dz_k   ;   partial[row] = { dW[k][c] (K*64), db[k] (K) }
+template <typename T>
+__global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ a, const T* __restrict__ x,
+                                                             const float* __restrict__ w, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                             const float* __restrict__ dbeta, const float* __restrict__ dgamma,
+                                                             T* __restrict__ dx, float* __restrict__ partial, long long P, int K) {
+  __shared__ float red[TPB / 32][KMAX * 64 + KMAX];
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float wr[KMAX][8], accw[KMAX][8] = {}, accb[KMAX] = {};
+  float g_rs[KMAX], mu[KMAX], rs[KMAX], db[KMAX], dg[KMAX];
+  const float invP = 1.f / (float)P;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wr[k][i] = (k < K) ? w[k * 64 + sub * 8 + i] : 0.f;
+    mu[k] = (k < K) ? mean[k] : 0.f;
+    rs[k] = (k < K) ? rstd[k] : 0.f;
+    g_rs[k] = (k < K) ? gamma[k] * rs[k] : 0.f;
+    db[k] = (k < K) ? dbeta[k] * invP : 0.f;
+    dg[k] = (k < K) ? dgamma[k] * invP : 0.f;
+  }
+  const long long iters = (P + 31) / 32;
+  for (long long it = blockIdx.x; it < iters; it += gridDim.x) {
+    const long long px = it * 32 + pl;
+    if (px < P) {
+      float f[8], o[8] = {};
+      ld8<T>(x + px * 64 + sub * 8, f);
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+          const float av = a[px * K + k];
+          const float xh = (av - mu[k]) * rs[k];
+          float dz = g_rs[k] * (dy[px * K + k] - db[k] - xh * dg[k]);
+          if (!(av > 0.f)) dz = 0.f;
+          if (sub == 0) accb[k] += dz;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i] += wr[k][i] * dz;
+            accw[k][i] += dz * f[i];
+          }
+        }
+      if (dx) st8<T>(dx + px * 64 + sub * 8, o);
+    }
+  }
+  // reduce over the 4 pixels of each warp (lanes with equal sub), then over warps through smem
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (k < K) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = accw[k][i];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 8) red[warp][k * 64 + sub * 8 + i] = v;
+      }
+      float vb = accb[k];
+      vb = warp_sum(vb);
+      if (lane == 0) red[warp][K * 64 + k] = vb;
+    }
+  __syncthreads();
+  const int ncomp = K * 64 + K;
+  for (int i = threadIdx.x; i < ncomp; i += TPB) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < TPB / 32; ++wv) t += red[wv][i];
+    partial[(size_t)blockIdx.x * ncomp + i] = t;
+  }
+}
+
+// ------------------------------------------------------------------ inference epilogue
+// logits_k = relu(x . w_k + b_k) * scale_k + shift_k (BN moving stats folded); argmax (first max) -> mask zone.
+// Tile pixel (ty, tx) of an h x w tile is written iff it lies in the crop box [cy0,cy1) x [cx0,cx1); destination is
+// mask[(dst_y + ty - cy0) * mask_ld + dst_x + tx - cx0].
+template <typename T>
+__global__ void __launch_bounds__(TPB) head_argmax_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                          const float* __restrict__ scale, const float* __restrict__ shift, int K, int h, int wd,
+                                                          int cy0, int cy1, int cx0, int cx1, int* __restrict__ mask, long long mask_ld, int dst_y,
+                                                          int dst_x, float* __restrict__ softmax_out) {
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float wr[KMAX][8];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wr[k][i] = (k < K) ? w[k * 64 + sub * 8 + i] : 0.f;
+  const long long P = (long long)h * wd;
+  const long long iters = (P + 31) / 32;
+  for (long long it = blockIdx.x; it < iters; it += gridDim.x) {
+    const long long px = it * 32 + pl;
+    const bool ok = px < P;
+    float f[8] = {};
+    if (ok) ld8<T>(x + px * 64 + sub * 8, f);
+    float y[KMAX];
+    float mx = -INFINITY;
+    int am = 0;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) {
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d += wr[k][i] * f[i];
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        y[k] = fmaxf(d + b[k], 0.f) * scale[k] + shift[k];
+        if (y[k] > mx) {
+          mx = y[k];
+          am = k;
+        }
+      }
+    if (ok && sub == 0) {
+      const int ty = (int)(px / wd), tx = (int)(px % wd);
+      if (mask && ty >= cy0 && ty < cy1 && tx >= cx0 && tx < cx1)
+        mask[(long long)(dst_y + ty - cy0) * mask_ld + dst_x + tx - cx0] = am;
+      if (softmax_out) {
+        float se = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) {
+            y[k] = __expf(y[k] - mx);
+            se += y[k];
+          }
+        const float inv = 1.f / se;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) softmax_out[px * K + k] = y[k] * inv;
+      }
+    }
+  }
+}
+
+inline int grid_for(long long work_items, int per_block, int cap) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace
+
+#define UB_DISPATCH_T(dtype, ...)                                   \
+  do {                                                              \
+    if ((dtype) == UB_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else if ((dtype) == UB_F32) { using T = float; __VA_ARGS__; }   \
+    else { ub_set_error("bad dtype %d", (int)(dtype)); return UB_ERR_INVALID_ARG; } \
+  } while (0)
+
+#define UB_DISPATCH_CIN(cin, ...)                                   \
+  do {                                                              \
+    if ((cin) == 1) { constexpr int CIN = 1; __VA_ARGS__; }         \
+    else if ((cin) == 2) { constexpr int CIN = 2; __VA_ARGS__; }    \
+    else if ((cin) == 3) { constexpr int CIN = 3; __VA_ARGS__; }    \
+    else { constexpr int CIN = 4; __VA_ARGS__; }                    \
+  } while (0)
+
+extern "C" {
+
+int ub_conv_first_fwd(const float* x_nchw, const float* w, const float* bias, void* out, float* partial, int N, int H, int W, int Cin,
+                      int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(x_nchw && w && bias && out, "conv_first_fwd: null pointer");
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_fwd: Cin=%d must be in [1,4]", Cin);
+  const long long P = (long long)N * H * W;
+  const int grid = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * 64, stream));
+  UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, (T*)out, partial, N, H, W))));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+// partial scratch: UB_STATS_ROWS * Cin * 9 * 64 floats
+int ub_conv_first_wgrad(const float* x_nchw, const void* dz, float* dw, float* partial, int N, int H, int W, int Cin, int dtype,
+                        cudaStream_t stream) {
+  UB_CHECK_ARG(x_nchw && dz && dw && partial, "conv_first_wgrad: null pointer");
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_wgrad: Cin=%d must be in [1,4]", Cin);
+  const long long P = (long long)N * H * W;
+  const int rows = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  dim3 grid(rows, Cin);
+  UB_DISPATCH_T(dtype, (conv_first_wgrad_kernel<T><<<grid, TPB, 0, stream>>>(x_nchw, (const T*)dz, partial, N, H, W, Cin)));
+  UB_LAUNCH_CHECK();
+  conv_first_wgrad_finalize_kernel<<<(64 * 9 * Cin + 127) / 128, 128, 0, stream>>>(partial, dw, rows, Cin);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, float* partial, long long P, int K, int dtype,
+                cudaStream_t stream) {
+  UB_CHECK_ARG(x && w && b && a_out && P > 0, "head_fwd: bad args");
+  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_fwd: number_classes=%d exceeds UB_MAX_CLASSES=%d", K, KMAX);
+  const int grid = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * K, stream));
+  UB_DISPATCH_T(dtype, (head_fwd_kernel<T><<<grid, TPB, 0, stream>>>((const T*)x, w, b, a_out, partial, P, K)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const unsigned char* labels,
+                 const float* class_w, float inv_denom, float* softmax_out, float* dlogits, float* partial, long long P, int K,
+                 cudaStream_t stream) {
+  UB_CHECK_ARG(a && mean && rstd && gamma && beta && P > 0, "head_loss: bad args");
+  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_loss: number_classes=%d exceeds UB_MAX_CLASSES=%d", K, KMAX);
+  const int grid = grid_for(P, TPB * 4, UB_STATS_ROWS);
+  if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2, stream));
+  head_loss_kernel<<<grid, TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, softmax_out, dlogits, partial, P, K);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_onehot_to_index(const int* onehot, unsigned char* idx, long long P, int K, cudaStream_t stream) {
+  UB_CHECK_ARG(onehot && idx && P > 0 && K >= 1 && K <= 255, "onehot_to_index: bad args");
+  onehot_to_index_kernel<<<grid_for(P, TPB, ub_num_sms() * 8), TPB, 0, stream>>>(onehot, idx, P, K);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const float* rstd, float* partial, long long P, int K,
+                       cudaStream_t stream) {
+  UB_CHECK_ARG(dy && a && mean && rstd && partial && P > 0, "head_bwd_reduce: bad args");
+  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_bwd_reduce: K");
+  const int grid = grid_for(P, TPB * 4, UB_STATS_ROWS);
+  UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * K, stream));
+  head_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>(dy, a, mean, rstd, partial, P, K);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+// partial: UB_STATS_ROWS * (K*64 + K) floats; row layout {dW[K][64], db[K]}
+int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
+                      const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K, int dtype,
+                      cudaStream_t stream) {
+  UB_CHECK_ARG(dy && a && x && w && mean && rstd && gamma && dbeta && dgamma && partial && P > 0, "head_bwd_apply: bad args");
+  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_bwd_apply: K");
+  const int grid = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * (K * 64 + K), stream));
+  UB_DISPATCH_T(dtype, (head_bwd_apply_kernel<T><<<grid, TPB, 0, stream>>>(dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx,
+                                                                          partial, P, K)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int h, int wd, int cy0,
+                   int cy1, int cx0, int cx1, int* mask, long long mask_ld, int dst_y, int dst_x, float* softmax_out, int dtype,
+                   cudaStream_t stream) {
+  UB_CHECK_ARG(x && w && b && scale && shift && (mask || softmax_out), "head_argmax: bad args");
+  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_argmax: K");
+  const long long P = (long long)h * wd;
+  const int grid = grid_for(P, 32 * 4, ub_num_sms() * 8);
+  UB_DISPATCH_T(dtype, (head_argmax_kernel<T><<<grid, TPB, 0, stream>>>((const T*)x, w, b, scale, shift, K, h, wd, cy0, cy1, cx0, cx1, mask,
+                                                                       mask_ld, dst_y, dst_x, softmax_out)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,472 @@
+// Implicit-GEMM on tcgen05/TMEM fed by TMA  (sm_100a).
+//
+//   D[pixel, col] = sum_{tap, src, c}  A_src[pixel + shift(tap), c] * Wt[col, (tap, src, c)]
+//
+// One kernel family serves four reference ops (all NHWC bf16, fp32 accumulate):
+//   conv3x3 forward  (UNet/model.py:30-35)   9 taps, 1-2 concatenated sources (skip first, model.py:57), bias+ReLU,
+//                                            per-channel sum / sum-of-squares partials for the following BatchNorm
+//   conv3x3 dgrad    (autodiff of the above) same kernel with 180-degree-rotated, transposed weights; the output
+//                                            channel range may be split over two tensors (gradient of a concat)
+//   deconv2x2 forward (UNet/model.py:41-46)  1 tap, N = 4*Cout columns scattered through 4 strided output views
+//   deconv2x2 dgrad                          4 strided source views, 1 tap
+//
+// M tile = 128 pixels = an 8x16 (h x w) patch of one image; the 'same' zero padding and ragged image edges come
+// from TMA out-of-bounds zero fill / store clipping.  K is walked in 64-channel blocks (one 128-byte swizzle row).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_W = 16;
+constexpr int TILE_H = 8;
+constexpr int BLOCK_M = 128;
+constexpr int A_BYTES = BLOCK_M * 128;  // 128 pixels x 64 bf16
+
+struct IgemmFwdParams {
+  CUtensorMap a_map[4];
+  CUtensorMap b_map;
+  CUtensorMap o_map[4];
+  int nsrc;
+  int cblk[4];       // 64-channel blocks per source
+  int ntaps;
+  int tap_dh[9];
+  int tap_dw[9];
+  int kb_per_tap;    // sum(cblk)
+  int num_kb;        // ntaps * kb_per_tap
+  int H, W;          // pixel space of the A sources
+  int tiles_w, tiles_h;
+  int n_tiles, total_tiles;
+  int blocks_per_omap;
+  const float* bias;  // may be null
+  int bias_mod;       // bias index = column % bias_mod
+  int relu;
+  float* stats;       // [UB_STATS_ROWS][2][ncols] or null
+  int ncols;
+};
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = (BLOCK_N / 64) * A_BYTES;
+  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
+  static constexpr int OFF_STAT = OFF_OUT + OUT_BYTES;          // float[4][2][BLOCK_N]
+  static constexpr int OFF_BIAS = OFF_STAT + 4 * 2 * BLOCK_N * 4;  // float[BLOCK_N]
+  static constexpr int OFF_BAR = OFF_BIAS + BLOCK_N * 4;        // full[S], empty[S], tfull[2], tempty[2]
+  static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
+  static constexpr int TOTAL = OFF_TMEM + 16 + 1024;            // + alignment slack
+};
+
+// Column sums over the 32 lanes of a warp for 32 columns held per lane: lane l returns sum_rows v[l].
+__device__ __forceinline__ float col_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant__ IgemmFwdParams p) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* out_stage = smem + L::OFF_OUT;
+  float* stat_smem = reinterpret_cast<float*>(smem + L::OFF_STAT);
+  float* bias_smem = reinterpret_cast<float*>(smem + L::OFF_BIAS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&p.a_map[i]);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.o_map[0]);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int img = m_tile / tiles_per_img;
+        const int rem = m_tile - img * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * TILE_H;
+        const int w0 = (rem % p.tiles_w) * TILE_W;
+        int kb = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+          for (int src = 0; src < p.nsrc; ++src) {
+            for (int cb = 0; cb < p.cblk[src]; ++cb, ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* sa = smem + stage * L::STAGE_BYTES;
+              mbar_expect_tx(&full[stage], L::STAGE_BYTES);
+              tma_load_4d(sa, &p.a_map[src], &full[stage], cb * 64, w0 + dw, h0 + dh, img);
+              tma_load_2d(sa + A_BYTES, &p.b_map, &full[stage], kb * 64, n_tile * BLOCK_N);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 bytes) per 64-channel block
+            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(&empty[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (4 warps, one TMEM lane quadrant each) =================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int et = threadIdx.x - 64;          // 0..127
+    const bool store_thread = (et == 0);
+    const uint32_t row_smem = smem_u32(out_stage) + row * 128;
+    const int rsw = row & 7;
+    constexpr int NCHUNK = BLOCK_N / 32;
+    float acc_sum[NCHUNK], acc_sq[NCHUNK];
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) acc_sum[c] = acc_sq[c] = 0.f;
+    int as = 0;
+    uint32_t aphase = 0;
+    int last_n_tile = -1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * TILE_H;
+      const int w0 = (rem % p.tiles_w) * TILE_W;
+      const bool valid = (h0 + row / TILE_W < p.H) && (w0 + row % TILE_W < p.W);
+
+      // staging buffer must have been drained by the previous tile's TMA store; refresh the bias slice
+      if (store_thread) tma_store_wait_read0();
+      if (n_tile != last_n_tile) {
+        for (int c = et; c < BLOCK_N; c += 128)
+          bias_smem[c] = p.bias ? p.bias[(n_tile * BLOCK_N + c) % p.bias_mod] : 0.f;
+        last_n_tile = n_tile;
+      }
+      named_bar_sync(1, 128);
+
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll
+      for (int chunk = 0; chunk < NCHUNK; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) + bias_smem[chunk * 32 + j];
+          f[j] = p.relu ? fmaxf(x, 0.f) : x;
+        }
+        const uint32_t blk = row_smem + (chunk >> 1) * A_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c16 = (chunk & 1) * 4 + q;
+          st_shared_v4(blk + ((c16 ^ rsw) << 4), pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                       pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+        }
+        if (p.stats) {
+          float s[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = valid ? f[j] : 0.f;
+            s[j] = f[j] * f[j];
+          }
+          acc_sum[chunk] += col_reduce32(f, lane);
+          acc_sq[chunk] += col_reduce32(s, lane);
+        }
+      }
+      // accumulator stage drained -> MMA warp may reuse it
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      // staged tile -> global through TMA (clipped at the image edge)
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (store_thread) {
+#pragma unroll
+        for (int b = 0; b < BLOCK_N / 64; ++b) {
+          const int j = n_tile * (BLOCK_N / 64) + b;
+          const int map = j / p.blocks_per_omap;
+          const int c0 = (j - map * p.blocks_per_omap) * 64;
+          tma_store_4d(&p.o_map[map], out_stage + b * A_BYTES, c0, w0, h0, img);
+        }
+        tma_store_commit();
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (store_thread) tma_store_wait_all0();
+    if (p.stats) {
+      // per-CTA partials: host guarantees gridDim.x % n_tiles == 0, so this CTA's n_tile never changes
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        stat_smem[(quad * 2 + 0) * BLOCK_N + c * 32 + lane] = acc_sum[c];
+        stat_smem[(quad * 2 + 1) * BLOCK_N + c * 32 + lane] = acc_sq[c];
+      }
+      named_bar_sync(1, 128);
+      const int n_tile = blockIdx.x % p.n_tiles;
+      const int srow = blockIdx.x / p.n_tiles;
+      for (int i = et; i < 2 * BLOCK_N; i += 128) {
+        const int which = i / BLOCK_N, c = i % BLOCK_N;
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t += stat_smem[(q * 2 + which) * BLOCK_N + c];
+        p.stats[((size_t)srow * 2 + which) * p.ncols + n_tile * BLOCK_N + c] = t;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct IgemmFwdLaunch {
+  IgemmFwdParams p;
+  int n_img;
+  int ncols;
+};
+
+template <int BLOCK_N, int STAGES>
+int launch_t(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  static_assert(L::TOTAL <= 232448, "smem budget");
+  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_done = true;
+  }
+  p.n_tiles = p.ncols / BLOCK_N;
+  p.tiles_w = (p.W + TILE_W - 1) / TILE_W;
+  p.tiles_h = (p.H + TILE_H - 1) / TILE_H;
+  const long long m_tiles = (long long)n_img * p.tiles_w * p.tiles_h;
+  const long long total = m_tiles * p.n_tiles;
+  UB_CHECK_SHAPE(total > 0 && total < (1ll << 31), "igemm: tile count out of range");
+  p.total_tiles = (int)total;
+  int sms = ub_num_sms();
+  int grid = (sms / p.n_tiles) * p.n_tiles;
+  if (grid <= 0) grid = p.n_tiles;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  UB_CHECK_SHAPE(grid / p.n_tiles <= UB_STATS_ROWS, "igemm: stats rows");
+  if (p.stats) UB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  kern<<<grid, 192, L::TOTAL, stream>>>(p);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int launch(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
+  p.kb_per_tap = 0;
+  for (int i = 0; i < p.nsrc; ++i) p.kb_per_tap += p.cblk[i];
+  p.num_kb = p.kb_per_tap * p.ntaps;
+  UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.num_kb > 0, "igemm: columns must be a multiple of 64");
+  if (p.ncols % 256 == 0) return launch_t<256, 3>(p, n_img, stream);
+  if (p.ncols % 128 == 0) return launch_t<128, 5>(p, n_img, stream);
+  return launch_t<64, 8>(p, n_img, stream);
+}
+
+void set_taps3x3(IgemmFwdParams& p) {
+  p.ntaps = 9;
+  for (int t = 0; t < 9; ++t) {
+    p.tap_dh[t] = t / 3 - 1;
+    p.tap_dw[t] = t % 3 - 1;
+  }
+}
+
+int dense_map(CUtensorMap* m, const void* base, int C, int W, int H, int N) {
+  return ub_tmap_act4d(m, base, C, W, H, N, (long long)C * 2, (long long)W * C * 2, (long long)H * W * C * 2, TILE_W, TILE_H);
+}
+// view of a [N, 2h, 2w, C] tensor restricted to rows 2i+a, cols 2j+b: dims {C, w, h, N}
+int strided_map(CUtensorMap* m, const void* base, int C, int w, int h, int N, int a, int b) {
+  const long long Wout = 2ll * w, Hout = 2ll * h;
+  const uint8_t* pbase = reinterpret_cast<const uint8_t*>(base) + ((long long)a * Wout + b) * C * 2;
+  return ub_tmap_act4d(m, pbase, C, w, h, N, 2ll * C * 2, 2ll * Wout * C * 2, Hout * Wout * C * 2, TILE_W, TILE_H);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, void* out,
+                   float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream) {
+  UB_CHECK_ARG(x0 && w && out, "conv3x3_fwd: null pointer");
+  UB_CHECK_SHAPE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0 && Cout % 64 == 0 && (C1 == 0 || x1),
+                 "conv3x3_fwd: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0, "conv3x3_fwd: bad N/H/W");
+  IgemmFwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = dense_map(&p.a_map[0], x0, C0, W, H, N))) return rc;
+  p.nsrc = 1;
+  p.cblk[0] = C0 / 64;
+  if (C1 > 0) {
+    if ((rc = dense_map(&p.a_map[1], x1, C1, W, H, N))) return rc;
+    p.nsrc = 2;
+    p.cblk[1] = C1 / 64;
+  }
+  const int Cin = C0 + C1;
+  const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  if ((rc = ub_tmap_mat2d(&p.b_map, w, Cout, 9ll * Cin, bn))) return rc;
+  if ((rc = dense_map(&p.o_map[0], out, Cout, W, H, N))) return rc;
+  set_taps3x3(p);
+  p.H = H;
+  p.W = W;
+  p.blocks_per_omap = Cout / 64;
+  p.bias = bias;
+  p.bias_mod = Cout;
+  p.relu = relu;
+  p.stats = stats;
+  p.ncols = Cout;
+  return launch(p, N, stream);
+}
+
+int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H,
+                     int W, cudaStream_t stream) {
+  UB_CHECK_ARG(dz && w_t && dx0, "conv3x3_dgrad: null pointer");
+  UB_CHECK_SHAPE(Cout % 64 == 0 && C0 % 64 == 0 && C0 > 0 && (C1 == 0 || (C1 == C0 && dx1)),
+                 "conv3x3_dgrad: channels must be multiples of 64 and split halves equal (Cout=%d C0=%d C1=%d)", Cout, C0, C1);
+  IgemmFwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = dense_map(&p.a_map[0], dz, Cout, W, H, N))) return rc;
+  p.nsrc = 1;
+  p.cblk[0] = Cout / 64;
+  const int Cin = C0 + C1;
+  const int bn = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
+  if ((rc = ub_tmap_mat2d(&p.b_map, w_t, Cin, 9ll * Cout, bn))) return rc;
+  if ((rc = dense_map(&p.o_map[0], dx0, C0, W, H, N))) return rc;
+  if (C1 > 0 && (rc = dense_map(&p.o_map[1], dx1, C1, W, H, N))) return rc;
+  set_taps3x3(p);
+  p.H = H;
+  p.W = W;
+  p.blocks_per_omap = C0 / 64;
+  p.bias = nullptr;
+  p.bias_mod = 1;
+  p.relu = 0;
+  p.stats = nullptr;
+  p.ncols = Cin;
+  return launch(p, N, stream);
+}
+
+int ub_deconv2x2_fwd(const void* x, int Cin, const void* w, const float* bias, void* out, float* stats, int N, int h,
+                     int wd, int Cout, cudaStream_t stream) {
+  UB_CHECK_ARG(x && w && out, "deconv2x2_fwd: null pointer");
+  UB_CHECK_SHAPE(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "deconv2x2_fwd: channels must be multiples of 64");
+  IgemmFwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = dense_map(&p.a_map[0], x, Cin, wd, h, N))) return rc;
+  p.nsrc = 1;
+  p.cblk[0] = Cin / 64;
+  const int ncols = 4 * Cout;
+  if ((rc = ub_tmap_mat2d(&p.b_map, w, ncols, Cin, ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64)))) return rc;
+  for (int ab = 0; ab < 4; ++ab)
+    if ((rc = strided_map(&p.o_map[ab], out, Cout, wd, h, N, ab >> 1, ab & 1))) return rc;
+  p.ntaps = 1;
+  p.H = h;
+  p.W = wd;
+  p.blocks_per_omap = Cout / 64;
+  p.bias = bias;
+  p.bias_mod = Cout;
+  p.relu = 0;
+  p.stats = stats;
+  p.ncols = ncols;
+  return launch(p, N, stream);
+}
+
+int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int wd,
+                       cudaStream_t stream) {
+  UB_CHECK_ARG(dz && w_t && dx, "deconv2x2_dgrad: null pointer");
+  UB_CHECK_SHAPE(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "deconv2x2_dgrad: channels must be multiples of 64");
+  IgemmFwdParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  for (int ab = 0; ab < 4; ++ab) {
+    if ((rc = strided_map(&p.a_map[ab], dz, Cout, wd, h, N, ab >> 1, ab & 1))) return rc;
+    p.cblk[ab] = Cout / 64;
+  }
+  p.nsrc = 4;
+  if ((rc = ub_tmap_mat2d(&p.b_map, w_t, Cin, 4ll * Cout, Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64)))) return rc;
+  if ((rc = dense_map(&p.o_map[0], dx, Cin, wd, h, N))) return rc;
+  p.ntaps = 1;
+  p.H = h;
+  p.W = wd;
+  p.blocks_per_omap = Cin / 64;
+  p.bias = nullptr;
+  p.bias_mod = 1;
+  p.relu = 0;
+  p.stats = nullptr;
+  p.ncols = Cin;
+  return launch(p, N, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,489 @@
+"""Kernel-level parity cases: each CUDA entry point (called through the C ABI) against the numpy oracle
+(oracle/unet_numpy.py) on seeded inputs.  Used by tests/test_kernels_gpu.py (pytest -m gpu) and by
+tests/gpu_probe.py (each case in its own subprocess, so one faulting kernel cannot poison the rest)."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import unet_numpy as ON  # noqa: E402
+
+
+def _C():
+    import unetb200._C as C
+    return C
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def bf16_round(a):
+    return torch.tensor(a, dtype=torch.float32).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+def dev(a, dtype):
+    return torch.tensor(np.ascontiguousarray(a), dtype=dtype, device="cuda")
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(got - ref).max() / (np.abs(ref).max() + 1e-30))
+
+
+def pack_conv(w_hwio):      # [3,3,Cin,Cout] -> [Cout][9][Cin]
+    k = w_hwio.shape[0]
+    return np.ascontiguousarray(np.transpose(w_hwio, (3, 0, 1, 2)).reshape(w_hwio.shape[3], k * k, w_hwio.shape[2]))
+
+
+def pack_deconv(w):         # [2,2,Cout,Cin] -> [4*Cout][Cin]
+    return np.ascontiguousarray(w.reshape(4 * w.shape[2], w.shape[3]))
+
+
+def stats_from_partial(partial, ncols):
+    p = partial.cpu().double().numpy().reshape(-1, 2, ncols)
+    return p[:, 0].sum(0), p[:, 1].sum(0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def case_conv3x3_fwd(C0=64, C1=0, Cout=64, N=2, H=24, W=40, relu=1, seed=0):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    Cin = C0 + C1
+    x = bf16_round(rng.normal(size=(N, H, W, Cin)))
+    w = bf16_round(rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin))
+    b = rng.normal(size=(Cout,)).astype(np.float32)
+    ref = ON.conv_fwd(x, w, b.astype(np.float64))
+    if relu:
+        ref = np.maximum(ref, 0)
+    x0 = dev(x[..., :C0], torch.bfloat16)
+    x1 = dev(x[..., C0:], torch.bfloat16) if C1 else None
+    wd = dev(pack_conv(w), torch.bfloat16)
+    bd = dev(b, torch.float32)
+    out = torch.full((N, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    partial = torch.empty(C.UB_STATS_ROWS * 2 * Cout, dtype=torch.float32, device="cuda")
+    C.call("ub_conv3x3_fwd", x0, C0, x1, C1, wd, bd, out, partial, N, H, W, Cout, relu, stream())
+    torch.cuda.synchronize()
+    got = out.double().cpu().numpy()
+    s, q = stats_from_partial(partial, Cout)
+    e = rel_err(got, ref)
+    es = rel_err(s, ref.sum((0, 1, 2)))
+    eq = rel_err(q, (ref ** 2).sum((0, 1, 2)))
+    return dict(err=e, err_sum=es, err_sq=eq, ok=bool(e < 1e-2 and es < 2e-3 and eq < 2e-3 and np.isfinite(got).all()))
+
+
+def case_conv3x3_dgrad(Cout=64, C0=64, C1=0, N=2, H=24, W=40, seed=1):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    Cin = C0 + C1
+    dz = bf16_round(rng.normal(size=(N, H, W, Cout)))
+    w = bf16_round(rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cout))
+    ref = ON.conv_dgrad(dz, w)
+    wp = dev(pack_conv(w), torch.float32)
+    wt = torch.empty(Cin * 9 * Cout, dtype=torch.bfloat16, device="cuda")
+    C.call("ub_transpose_pack", wp, wt, Cout, 9, Cin, 1, 0, C.UB_BF16, stream())
+    dzd = dev(dz, torch.bfloat16)
+    dx0 = torch.full((N, H, W, C0), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dx1 = torch.full((N, H, W, C1), float("nan"), dtype=torch.bfloat16, device="cuda") if C1 else None
+    C.call("ub_conv3x3_dgrad", dzd, Cout, wt, dx0, C0, dx1, C1, N, H, W, stream())
+    torch.cuda.synchronize()
+    got = dx0.double().cpu().numpy()
+    if C1:
+        got = np.concatenate([got, dx1.double().cpu().numpy()], -1)
+    e = rel_err(got, ref)
+    return dict(err=e, ok=bool(e < 1e-2 and np.isfinite(got).all()))
+
+
+def case_conv3x3_wgrad(C0=64, C1=0, Cout=64, N=2, H=24, W=40, seed=2):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    Cin = C0 + C1
+    x = bf16_round(rng.normal(size=(N, H, W, Cin)))
+    dz = bf16_round(rng.normal(size=(N, H, W, Cout)))
+    dw_ref, _ = ON.conv_wgrad(x, dz, 3)
+    x0 = dev(x[..., :C0], torch.bfloat16)
+    x1 = dev(x[..., C0:], torch.bfloat16) if C1 else None
+    dzd = dev(dz, torch.bfloat16)
+    nbytes = C.lib.ub_conv3x3_wgrad_workspace_bytes(C0, C1, Cout, N, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dw = torch.full((Cout, 9, Cin), float("nan"), dtype=torch.float32, device="cuda")
+    C.call("ub_conv3x3_wgrad", x0, C0, x1, C1, dzd, Cout, dw, ws, nbytes, N, H, W, stream())
+    torch.cuda.synchronize()
+    got = dw.double().cpu().numpy()
+    e = rel_err(got, pack_conv(dw_ref))
+    return dict(err=e, ws_bytes=int(nbytes), ok=bool(e < 1e-3 and np.isfinite(got).all()))
+
+
+def case_deconv_fwd(Cin=128, Cout=64, N=2, h=12, w=20, seed=3):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.normal(size=(N, h, w, Cin)))
+    wt = bf16_round(rng.normal(size=(2, 2, Cout, Cin)) / np.sqrt(Cin))
+    b = rng.normal(size=(Cout,)).astype(np.float32)
+    ref = ON.deconv_fwd(x, wt, b.astype(np.float64))
+    out = torch.full((N, 2 * h, 2 * w, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    partial = torch.empty(C.UB_STATS_ROWS * 2 * 4 * Cout, dtype=torch.float32, device="cuda")
+    C.call("ub_deconv2x2_fwd", dev(x, torch.bfloat16), Cin, dev(pack_deconv(wt), torch.bfloat16), dev(b, torch.float32), out, partial,
+           N, h, w, Cout, stream())
+    torch.cuda.synchronize()
+    got = out.double().cpu().numpy()
+    s, q = stats_from_partial(partial, 4 * Cout)
+    s = s.reshape(4, Cout).sum(0)
+    q = q.reshape(4, Cout).sum(0)
+    e = rel_err(got, ref)
+    es = rel_err(s, ref.sum((0, 1, 2)))
+    eq = rel_err(q, (ref ** 2).sum((0, 1, 2)))
+    return dict(err=e, err_sum=es, err_sq=eq, ok=bool(e < 1e-2 and es < 2e-3 and eq < 2e-3 and np.isfinite(got).all()))
+
+
+def case_deconv_bwd(Cin=128, Cout=64, N=2, h=12, w=20, seed=4):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.normal(size=(N, h, w, Cin)))
+    wt = bf16_round(rng.normal(size=(2, 2, Cout, Cin)) / np.sqrt(Cout))
+    dz = bf16_round(rng.normal(size=(N, 2 * h, 2 * w, Cout)))
+    dx_ref, dw_ref, _ = ON.deconv_bwd(x, dz, wt)
+    wp = dev(pack_deconv(wt), torch.float32)
+    w_t = torch.empty(Cin * 4 * Cout, dtype=torch.bfloat16, device="cuda")
+    C.call("ub_transpose_pack", wp, w_t, Cout, 4, Cin, 0, 1, C.UB_BF16, stream())     # -> [ci][ab][co]
+    dzd = dev(dz, torch.bfloat16)
+    dx = torch.full((N, h, w, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    C.call("ub_deconv2x2_dgrad", dzd, Cout, w_t, dx, Cin, N, h, w, stream())
+    nbytes = C.lib.ub_deconv2x2_wgrad_workspace_bytes(Cin, Cout, N, h, w)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dw = torch.full((4 * Cout, Cin), float("nan"), dtype=torch.float32, device="cuda")
+    C.call("ub_deconv2x2_wgrad", dev(x, torch.bfloat16), Cin, dzd, Cout, dw, ws, nbytes, N, h, w, stream())
+    torch.cuda.synchronize()
+    e1 = rel_err(dx.double().cpu().numpy(), dx_ref)
+    e2 = rel_err(dw.double().cpu().numpy(), pack_deconv(dw_ref))
+    return dict(err_dx=e1, err_dw=e2, ok=bool(e1 < 1e-2 and e2 < 1e-3))
+
+
+def case_bn_pool(C_=128, N=2, H=16, W=24, dtype="bf16", seed=5, dropout=True):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    code = C.UB_BF16 if dtype == "bf16" else C.UB_F32
+    a = np.maximum(rng.normal(size=(N, H, W, C_)), 0)
+    a = bf16_round(a) if dtype == "bf16" else a.astype(np.float32).astype(np.float64)
+    gamma = rng.uniform(0.5, 1.5, C_).astype(np.float32)
+    beta = rng.normal(size=C_).astype(np.float32)
+    mask = rng.integers(0, 2, size=(N, H, W, C_)).astype(np.uint8) if dropout else None
+    ad = dev(a, tdt)
+    partial = torch.empty(C.UB_STATS_ROWS * 2 * C_, dtype=torch.float32, device="cuda")
+    mean = torch.empty(C_, dtype=torch.float32, device="cuda")
+    rstd = torch.empty(C_, dtype=torch.float32, device="cuda")
+    mm = torch.zeros(C_, dtype=torch.float32, device="cuda")
+    mv = torch.ones(C_, dtype=torch.float32, device="cuda")
+    M = N * H * W
+    C.call("ub_bn_stats", ad, partial, M, C_, code, stream())
+    C.call("ub_bn_finalize", partial, C_, 1, M, mean, rstd, mm, mv, 0.99, 1e-3, stream())
+    y = torch.empty_like(ad)
+    pooled = torch.empty((N, H // 2, W // 2, C_), dtype=tdt, device="cuda")
+    idx = torch.empty((N, H // 2, W // 2, C_), dtype=torch.uint8, device="cuda")
+    md = dev(mask, torch.uint8) if dropout else None
+    C.call("ub_bn_apply_pool", ad, y, pooled, idx, mean, rstd, dev(gamma, torch.float32), dev(beta, torch.float32), md, N, H, W, C_, code,
+           stream())
+    y2 = torch.empty_like(ad)
+    C.call("ub_bn_apply", ad, y2, mean, rstd, dev(gamma, torch.float32), dev(beta, torch.float32), md, M, C_, code, stream())
+    torch.cuda.synchronize()
+    yr, mu, rs = ON.bn_fwd(a, gamma.astype(np.float64), beta.astype(np.float64))
+    if dropout:
+        yr = yr * mask * 2.0
+    pr, ir = ON.pool_fwd(yr)
+    tol = 1e-2 if dtype == "bf16" else 1e-5
+    e_mean = rel_err(mean.cpu().numpy(), mu)
+    e_rstd = rel_err(rstd.cpu().numpy(), rs)
+    e_y = rel_err(y.double().cpu().numpy(), yr)
+    e_y2 = rel_err(y2.double().cpu().numpy(), yr)
+    e_p = rel_err(pooled.double().cpu().numpy(), pr)
+    # the saved slot must reproduce the pooled value from the stored y
+    yv = y.double().cpu().numpy().reshape(N, H // 2, 2, W // 2, 2, C_).transpose(0, 1, 3, 5, 2, 4).reshape(N, H // 2, W // 2, C_, 4)
+    sel = np.take_along_axis(yv, idx.cpu().numpy().astype(np.int64)[..., None], -1)[..., 0]
+    slot_ok = bool(np.array_equal(sel, pooled.double().cpu().numpy()) and np.array_equal(sel, yv.max(-1)))
+    e_mm = rel_err(mm.cpu().numpy(), 0.01 * mu)
+    var_unb = a.var(axis=(0, 1, 2)) * M / (M - 1)
+    e_mv = rel_err(mv.cpu().numpy(), 0.99 + 0.01 * var_unb)
+    ok = e_mean < 1e-4 and e_rstd < 1e-4 and e_y < tol and e_y2 < tol and e_p < tol and slot_ok and e_mm < 1e-4 and e_mv < 1e-4
+    return dict(e_mean=e_mean, e_rstd=e_rstd, e_y=e_y, e_y2=e_y2, e_pool=e_p, slot_ok=slot_ok, e_mm=e_mm, e_mv=e_mv, ok=bool(ok))
+
+
+def case_bn_bwd(C_=64, N=2, H=16, W=24, dtype="f32", relu=1, seed=6):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    code = C.UB_BF16 if dtype == "bf16" else C.UB_F32
+    rnd = bf16_round if dtype == "bf16" else (lambda z: z.astype(np.float32).astype(np.float64))
+    a = rnd(np.maximum(rng.normal(size=(N, H, W, C_)), 0))
+    dy = rnd(rng.normal(size=(N, H, W, C_)))
+    gamma = rng.uniform(0.5, 1.5, C_).astype(np.float32)
+    M = N * H * W
+    mu = a.mean((0, 1, 2))
+    rs = 1 / np.sqrt(a.var((0, 1, 2)) + 1e-3)
+    da, dg, db = ON.bn_bwd(dy, a, mu, rs, gamma.astype(np.float64))
+    dz_ref = da * (a > 0) if relu else da
+    ad, dyd = dev(a, tdt), dev(dy, tdt)
+    mean, rstd = dev(mu, torch.float32), dev(rs, torch.float32)
+    partial = torch.empty(C.UB_STATS_ROWS * 2 * C_, dtype=torch.float32, device="cuda")
+    red = torch.empty(2 * C_, dtype=torch.float32, device="cuda")
+    C.call("ub_bn_bwd_reduce", dyd, ad, mean, rstd, partial, M, C_, code, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2 * C_, red, 1.0, stream())
+    dz = torch.empty_like(ad)
+    dbias = torch.empty(C_, dtype=torch.float32, device="cuda")
+    C.call("ub_bn_bwd_apply", dyd, ad, mean, rstd, dev(gamma, torch.float32), red[:C_], red[C_:], dz, partial, M, C_, relu, code, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, C_, dbias, 1.0, stream())
+    torch.cuda.synchronize()
+    tol = 1e-2 if dtype == "bf16" else 1e-5
+    e_db = rel_err(red[:C_].cpu().numpy(), db)
+    e_dg = rel_err(red[C_:].cpu().numpy(), dg)
+    e_dz = rel_err(dz.double().cpu().numpy(), dz_ref)
+    e_bias = rel_err(dbias.cpu().numpy(), dz_ref.sum((0, 1, 2))) if relu else 0.0
+    ok = e_db < 1e-4 and e_dg < 1e-4 and e_dz < tol and e_bias < max(tol, 1e-3)
+    return dict(e_dbeta=e_db, e_dgamma=e_dg, e_dz=e_dz, e_dbias=e_bias, ok=bool(ok))
+
+
+def case_pool_bwd(C_=64, N=2, H=16, W=24, seed=7):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    dp = rng.normal(size=(N, H // 2, W // 2, C_)).astype(np.float32)
+    idx = rng.integers(0, 4, size=(N, H // 2, W // 2, C_)).astype(np.uint8)
+    dskip = rng.normal(size=(N, H, W, C_)).astype(np.float32)
+    mask = rng.integers(0, 2, size=(N, H, W, C_)).astype(np.uint8)
+    ref = (ON.pool_bwd(dp.astype(np.float64), idx.astype(np.int64)) + dskip) * mask * 2.0
+    dy = torch.empty((N, H, W, C_), dtype=torch.float32, device="cuda")
+    C.call("ub_maxpool2x2_bwd_add", dev(dp, torch.float32), dev(idx, torch.uint8), dev(dskip, torch.float32), dev(mask, torch.uint8), dy,
+           N, H, W, C_, C.UB_F32, stream())
+    torch.cuda.synchronize()
+    e = rel_err(dy.cpu().numpy(), ref)
+    return dict(err=e, ok=bool(e < 1e-6))
+
+
+def case_conv_first(Cin=1, N=2, H=16, W=24, seed=8):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(N, Cin, H, W)).astype(np.float32)
+    w = (rng.normal(size=(3, 3, Cin, 64)) / 3).astype(np.float32)
+    b = rng.normal(size=64).astype(np.float32)
+    xh = np.transpose(x, (0, 2, 3, 1)).astype(np.float64)
+    ref = np.maximum(ON.conv_fwd(xh, w.astype(np.float64), b.astype(np.float64)), 0)
+    out = torch.empty((N, H, W, 64), dtype=torch.float32, device="cuda")
+    partial = torch.empty(C.UB_STATS_ROWS * 2 * 64, dtype=torch.float32, device="cuda")
+    xd = dev(x, torch.float32)
+    C.call("ub_conv_first_fwd", xd, dev(pack_conv(w), torch.float32), dev(b, torch.float32), out, partial, N, H, W, Cin, C.UB_F32, stream())
+    dz = rng.normal(size=(N, H, W, 64)).astype(np.float32)
+    dw = torch.empty((64, 9, Cin), dtype=torch.float32, device="cuda")
+    scratch = torch.empty(C.UB_STATS_ROWS * Cin * 9 * 64, dtype=torch.float32, device="cuda")
+    C.call("ub_conv_first_wgrad", xd, dev(dz, torch.float32), dw, scratch, N, H, W, Cin, C.UB_F32, stream())
+    torch.cuda.synchronize()
+    dw_ref, _ = ON.conv_wgrad(xh, dz.astype(np.float64), 3)
+    s, q = stats_from_partial(partial, 64)
+    e = rel_err(out.cpu().numpy(), ref)
+    es = rel_err(s, ref.sum((0, 1, 2)))
+    ew = rel_err(dw.cpu().numpy(), pack_conv(dw_ref))
+    return dict(err=e, err_sum=es, err_dw=ew, ok=bool(e < 1e-5 and es < 1e-4 and ew < 1e-4))
+
+
+def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    P = N * H * W
+    x = rng.normal(size=(P, 64)).astype(np.float32)
+    w = (rng.normal(size=(K, 64)) / 8).astype(np.float32)
+    b = rng.normal(size=K).astype(np.float32) * 0.1
+    gamma = rng.uniform(0.5, 1.5, K).astype(np.float32)
+    beta = rng.normal(size=K).astype(np.float32)
+    lab = rng.integers(0, K, size=P).astype(np.uint8)
+    cw = rng.uniform(0.5, 2.0, K).astype(np.float32) if weighted else None
+    gb = 4
+    inv_denom = 1.0 / (gb * H * W)
+    # oracle (fp64)
+    a = np.maximum(x.astype(np.float64) @ w.T.astype(np.float64) + b, 0)
+    mu, var = a.mean(0), a.var(0)
+    rs = 1 / np.sqrt(var + 1e-3)
+    y = (a - mu) * rs * gamma + beta
+    e_ = np.exp(y - y.max(-1, keepdims=True))
+    p = e_ / e_.sum(-1, keepdims=True)
+    oh = np.eye(K)[lab]
+    cwl = cw[lab].astype(np.float64) if weighted else np.ones(P)
+    loss_ref = float((-(np.log(p) * oh).sum(-1) * cwl).sum() * inv_denom)
+    acc_ref = float((p.argmax(-1) == lab).mean())
+    dy_ref = (p - oh) * cwl[:, None] * inv_denom
+    xh = (a - mu) * rs
+    dbeta, dgamma = dy_ref.sum(0), (dy_ref * xh).sum(0)
+    dz = gamma * rs * (dy_ref - dbeta / P - xh * dgamma / P) * (a > 0)
+    dW_ref, db_ref, dx_ref = dz.T @ x.astype(np.float64), dz.sum(0), dz @ w.astype(np.float64)
+    # device
+    xd, wd, bd = dev(x, torch.float32), dev(w, torch.float32), dev(b, torch.float32)
+    a_d = torch.empty((P, K), dtype=torch.float32, device="cuda")
+    partial = torch.empty(C.UB_STATS_ROWS * (K * 64 + K + 2 * K + 2), dtype=torch.float32, device="cuda")
+    mean, rstd = torch.empty(K, device="cuda"), torch.empty(K, device="cuda")
+    C.call("ub_head_fwd", xd, wd, bd, a_d, partial, P, K, C.UB_F32, stream())
+    C.call("ub_bn_finalize", partial, K, 1, P, mean, rstd, None, None, 0.99, 1e-3, stream())
+    sm = torch.empty((P, K), dtype=torch.float32, device="cuda")
+    dl = torch.empty((P, K), dtype=torch.float32, device="cuda")
+    gd, btd = dev(gamma, torch.float32), dev(beta, torch.float32)
+    cwd = dev(cw, torch.float32) if weighted else None
+    C.call("ub_head_loss", a_d, mean, rstd, gd, btd, dev(lab, torch.uint8), cwd, inv_denom, sm, dl, partial, P, K, stream())
+    la = torch.empty(2, device="cuda")
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2, la, 1.0, stream())
+    red = torch.empty(2 * K, device="cuda")
+    C.call("ub_head_bwd_reduce", dl, a_d, mean, rstd, partial, P, K, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2 * K, red, 1.0, stream())
+    dx = torch.empty((P, 64), dtype=torch.float32, device="cuda")
+    gw = torch.empty(K * 64 + K, device="cuda")
+    C.call("ub_head_bwd_apply", dl, a_d, xd, wd, mean, rstd, gd, red[:K], red[K:], dx, partial, P, K, C.UB_F32, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, K * 64 + K, gw, 1.0, stream())
+    torch.cuda.synchronize()
+    la = la.cpu().numpy()
+    r = dict(e_a=rel_err(a_d.cpu().numpy(), a), e_sm=rel_err(sm.cpu().numpy(), p), e_loss=abs(la[0] * inv_denom - loss_ref) / abs(loss_ref),
+             e_acc=abs(la[1] / P - acc_ref), e_dl=rel_err(dl.cpu().numpy(), dy_ref), e_dbeta=rel_err(red[:K].cpu().numpy(), dbeta),
+             e_dgamma=rel_err(red[K:].cpu().numpy(), dgamma), e_dx=rel_err(dx.cpu().numpy(), dx_ref),
+             e_dW=rel_err(gw[:K * 64].cpu().numpy().reshape(K, 64), dW_ref), e_db=rel_err(gw[K * 64:].cpu().numpy(), db_ref))
+    r["ok"] = bool(all(v < 2e-4 for k, v in r.items() if k.startswith("e_")))
+    return r
+
+
+def case_adam(n=10007, seed=10):
+    C = _C()
+    rng = np.random.default_rng(seed)
+    p = rng.normal(size=n).astype(np.float32)
+    g = rng.normal(size=n).astype(np.float32)
+    m = rng.normal(size=n).astype(np.float32) * 0.1
+    v = rng.uniform(0, 1, size=n).astype(np.float32)
+    lr_t, b1, b2, eps = 3e-4, 0.9, 0.999, 1e-7
+    m_ref = b1 * m.astype(np.float64) + (1 - b1) * g
+    v_ref = b2 * v.astype(np.float64) + (1 - b2) * g.astype(np.float64) ** 2
+    p_ref = p - lr_t * m_ref / (np.sqrt(v_ref) + eps)
+    pd, gd, md, vd = (dev(t, torch.float32) for t in (p, g, m, v))
+    sh = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    C.call("ub_adam", pd, gd, md, vd, sh, n, lr_t, b1, b2, eps, 1.0, stream())
+    torch.cuda.synchronize()
+    e = max(rel_err(pd.cpu().numpy(), p_ref), rel_err(md.cpu().numpy(), m_ref), rel_err(vd.cpu().numpy(), v_ref))
+    es = rel_err(sh.double().cpu().numpy(), p_ref)
+    return dict(err=e, err_shadow=es, ok=bool(e < 1e-6 and es < 5e-3))
+
+
+def case_zscore(seed=11):
+    C = _C()
+    from oracle import unet_oracle as O
+    rng = np.random.default_rng(seed)
+    planes, H, W = 3, 40, 56
+    img = np.clip(np.round(rng.normal(3045, 376, size=(planes, H, W))), 0, 65535).astype(np.uint16)
+    img[2] = 7          # std <= 1 branch
+    ref = O.zscore_normalize(img, channels_first=True)
+    src = torch.from_numpy(img.view(np.int16).copy()).cuda()      # same bits as uint16
+    dst = torch.empty((planes, H, W), dtype=torch.float32, device="cuda")
+    scratch = torch.empty(planes * C.UB_ZSCORE_BLOCKS * 2, dtype=torch.float64, device="cuda")
+    C.call("ub_zscore", src, 1, dst, scratch, planes, H * W, stream())
+    torch.cuda.synchronize()
+    e = float(np.abs(dst.cpu().numpy() - ref).max())
+    return dict(err=e, ok=bool(e < 1e-4))
+
+
+def case_dropout_mask(seed=12):
+    C = _C()
+    n = 1 << 20
+    m1 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    m2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    C.call("ub_dropout_mask", m1, n, 1234, 0, stream())
+    C.call("ub_dropout_mask", m2, n, 1234, 0, stream())
+    m3 = torch.empty(n, dtype=torch.uint8, device="cuda")
+    C.call("ub_dropout_mask", m3, n, 1234, n // 16, stream())
+    torch.cuda.synchronize()
+    a = m1.cpu().numpy()
+    frac = float(a.mean())
+    ok = np.array_equal(a, m2.cpu().numpy()) and set(np.unique(a)) <= {0, 1} and abs(frac - 0.5) < 5e-3 and not np.array_equal(a, m3.cpu().numpy())
+    return dict(frac=frac, ok=bool(ok))
+
+
+def case_check_convs(seed=13):
+    """fp32 check-mode kernels vs the oracle (tight tolerance)."""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    N, H, W, C0, C1, Co = 2, 10, 12, 16, 8, 24
+    x = rng.normal(size=(N, H, W, C0 + C1)).astype(np.float32)
+    w = (rng.normal(size=(3, 3, C0 + C1, Co)) / 10).astype(np.float32)
+    b = rng.normal(size=Co).astype(np.float32)
+    ref = np.maximum(ON.conv_fwd(x.astype(np.float64), w.astype(np.float64), b.astype(np.float64)), 0)
+    out = torch.empty((N, H, W, Co), dtype=torch.float32, device="cuda")
+    x0, x1 = dev(x[..., :C0], torch.float32), dev(x[..., C0:], torch.float32)
+    wp = dev(pack_conv(w), torch.float32)
+    C.call("ub_check_conv3x3", x0, C0, x1, C1, wp, dev(b, torch.float32), out, Co, None, 0, N, H, W, 1, stream())
+    dz = rng.normal(size=(N, H, W, Co)).astype(np.float32)
+    dzd = dev(dz, torch.float32)
+    wt = torch.empty((C0 + C1) * 9 * Co, dtype=torch.float32, device="cuda")
+    C.call("ub_transpose_pack", wp, wt, Co, 9, C0 + C1, 1, 0, C.UB_F32, stream())
+    dx0 = torch.empty((N, H, W, C0), dtype=torch.float32, device="cuda")
+    dx1 = torch.empty((N, H, W, C1), dtype=torch.float32, device="cuda")
+    C.call("ub_check_conv3x3", dzd, Co, None, 0, wt, None, dx0, C0, dx1, C1, N, H, W, 0, stream())
+    dw = torch.empty((Co, 9, C0 + C1), dtype=torch.float32, device="cuda")
+    C.call("ub_check_conv3x3_wgrad", x0, C0, x1, C1, dzd, Co, dw, N, H, W, stream())
+    # deconv
+    Ci2, Co2, h, wd_ = 16, 8, 5, 6
+    xx = rng.normal(size=(N, h, wd_, Ci2)).astype(np.float32)
+    wdc = (rng.normal(size=(2, 2, Co2, Ci2)) / 4).astype(np.float32)
+    bb = rng.normal(size=Co2).astype(np.float32)
+    dzz = rng.normal(size=(N, 2 * h, 2 * wd_, Co2)).astype(np.float32)
+    o2 = torch.empty((N, 2 * h, 2 * wd_, Co2), dtype=torch.float32, device="cuda")
+    wdp = dev(pack_deconv(wdc), torch.float32)
+    C.call("ub_check_deconv2x2_fwd", dev(xx, torch.float32), wdp, dev(bb, torch.float32), o2, N, h, wd_, Ci2, Co2, stream())
+    dxx = torch.empty((N, h, wd_, Ci2), dtype=torch.float32, device="cuda")
+    C.call("ub_check_deconv2x2_dgrad", dev(dzz, torch.float32), wdp, dxx, N, h, wd_, Ci2, Co2, stream())
+    dww = torch.empty((4 * Co2, Ci2), dtype=torch.float32, device="cuda")
+    C.call("ub_check_deconv2x2_wgrad", dev(xx, torch.float32), dev(dzz, torch.float32), dww, N, h, wd_, Ci2, Co2, stream())
+    torch.cuda.synchronize()
+    dx_ref = ON.conv_dgrad(dz.astype(np.float64), w.astype(np.float64))
+    dw_ref, _ = ON.conv_wgrad(x.astype(np.float64), dz.astype(np.float64), 3)
+    d_dx, d_dw, _ = ON.deconv_bwd(xx.astype(np.float64), dzz.astype(np.float64), wdc.astype(np.float64))
+    r = dict(e_fwd=rel_err(out.cpu().numpy(), ref),
+             e_dgrad=rel_err(np.concatenate([dx0.cpu().numpy(), dx1.cpu().numpy()], -1), dx_ref),
+             e_wgrad=rel_err(dw.cpu().numpy(), pack_conv(dw_ref)),
+             e_dfwd=rel_err(o2.cpu().numpy(), ON.deconv_fwd(xx.astype(np.float64), wdc.astype(np.float64), bb.astype(np.float64))),
+             e_ddx=rel_err(dxx.cpu().numpy(), d_dx), e_ddw=rel_err(dww.cpu().numpy(), pack_deconv(d_dw)))
+    r["ok"] = bool(all(v < 1e-5 for v in r.values()))
+    return r
+
+
+CASES = {
+    # tcgen05 implicit GEMMs
+    "conv_fwd_64_64": lambda: case_conv3x3_fwd(64, 0, 64),
+    "conv_fwd_128_128": lambda: case_conv3x3_fwd(128, 0, 128),
+    "conv_fwd_cat_64+64_256": lambda: case_conv3x3_fwd(64, 64, 256),
+    "conv_fwd_128_512_norelu": lambda: case_conv3x3_fwd(128, 0, 512, relu=0),
+    "conv_fwd_small_image": lambda: case_conv3x3_fwd(64, 0, 64, N=1, H=2, W=2),
+    "conv_fwd_big": lambda: case_conv3x3_fwd(64, 0, 64, N=3, H=64, W=80),
+    "conv_dgrad_64_64": lambda: case_conv3x3_dgrad(64, 64, 0),
+    "conv_dgrad_split_128": lambda: case_conv3x3_dgrad(128, 64, 64),
+    "conv_dgrad_256_512": lambda: case_conv3x3_dgrad(256, 512, 0, H=8, W=16),
+    "conv_wgrad_64_64": lambda: case_conv3x3_wgrad(64, 0, 64),
+    "conv_wgrad_cat_64+64_128": lambda: case_conv3x3_wgrad(64, 64, 128),
+    "conv_wgrad_128_256": lambda: case_conv3x3_wgrad(128, 0, 256, H=16, W=16),
+    "deconv_fwd_128_64": lambda: case_deconv_fwd(128, 64),
+    "deconv_fwd_256_128": lambda: case_deconv_fwd(256, 128, h=4, w=6),
+    "deconv_bwd_128_64": lambda: case_deconv_bwd(128, 64),
+    "deconv_bwd_256_128": lambda: case_deconv_bwd(256, 128, h=4, w=6),
+    # memory-bound kernels
+    "bn_pool_bf16": lambda: case_bn_pool(128, dtype="bf16"),
+    "bn_pool_f32_nodrop": lambda: case_bn_pool(64, dtype="f32", dropout=False),
+    "bn_pool_1024": lambda: case_bn_pool(1024, N=1, H=4, W=6, dtype="f32"),
+    "bn_bwd_f32": lambda: case_bn_bwd(64, dtype="f32"),
+    "bn_bwd_bf16_512": lambda: case_bn_bwd(512, N=1, H=8, W=8, dtype="bf16"),
+    "bn_bwd_norelu": lambda: case_bn_bwd(128, dtype="f32", relu=0),
+    "pool_bwd": case_pool_bwd,
+    "conv_first_c1": lambda: case_conv_first(1),
+    "conv_first_c3": lambda: case_conv_first(3),
+    "head_k2": lambda: case_head(2),
+    "head_k8_weighted": lambda: case_head(8, weighted=True),
+    "adam": case_adam,
+    "zscore": case_zscore,
+    "dropout_mask": case_dropout_mask,
+    "check_convs": case_check_convs,
+}
