@@ -79,10 +79,11 @@ int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, flo
                 cudaStream_t stream);
 /* BatchNorm -> Softmax -> CategoricalCrossentropy + CategoricalAccuracy -- UNet/model.py:136-142, :211-215, :225-226.
  * labels: uint8 class index per pixel (nullable: inference); class_w nullable (all ones = reference behaviour);
- * dlogits = (softmax - onehot) * class_w[label] * inv_denom; partial[UB_STATS_ROWS][2] = {sum CE, #correct}. */
+ * dlogits = (softmax - onehot) * class_w[label] * inv_denom;
+ * partial[UB_STATS_ROWS][2] = {inv_denom * sum CE, acc_scale * #correct} (sum the rows with ub_reduce_rows). */
 int ub_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                 const unsigned char* labels, const float* class_w, float inv_denom, float* softmax_out, float* dlogits,
-                 float* partial, long long P, int K, cudaStream_t stream);
+                 const unsigned char* labels, const float* class_w, float inv_denom, float acc_scale, float* softmax_out,
+                 float* dlogits, float* partial, long long P, int K, cudaStream_t stream);
 /* one-hot int32 [P][K] (the reference's label tensor, UNet/imagereader.py:302-312) -> uint8 index */
 int ub_onehot_to_index(const int* onehot, unsigned char* idx, long long P, int K, cudaStream_t stream);
 int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const float* rstd, float* partial, long long P, int K,
@@ -110,7 +111,10 @@ int ub_bn_bwd_reduce(const void* dy, const void* a, const float* mean, const flo
                      int dtype, cudaStream_t stream);
 int ub_bn_bwd_apply(const void* dy, const void* a, const float* mean, const float* rstd, const float* gamma, const float* dbeta,
                     const float* dgamma, void* dz, float* partial, long long M, int C, int relu, int dtype, cudaStream_t stream);
-int ub_reduce_rows(const float* partial, int rows, int ncols, float* out, float scale, cudaStream_t stream);
+/* out[c] = scale * sum_r partial[r * row_stride + c], c < ncols (fp64 accumulation, fixed order) */
+int ub_reduce_rows(const float* partial, int rows, int row_stride, int ncols, float* out, float scale, cudaStream_t stream);
+/* inference: rstd = 1/sqrt(moving_var + eps) (BN with training=False, UNet/model.py:240, inference.py:105) */
+int ub_bn_inference_rstd(const float* moving_var, float* rstd, int n, float eps, cudaStream_t stream);
 
 /* ---- pool / dropout backward ----------------------------------------------------------------------------------- */
 /* dy = maxpool_bwd(dpool, idx) + dskip (skip fan-out, model.py:91/:132 ...), optional dropout backward */

@@ -123,13 +123,18 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
   }
 }
 
-// out[c] = scale * sum_rows partial[r][c]
-__global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, int ncols, float* __restrict__ out, float scale) {
+// out[c] = scale * sum_rows partial[r * row_stride + c],  c < ncols
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, int row_stride, int ncols, float* __restrict__ out, float scale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncols) return;
   double s = 0.0;
-  for (int r = 0; r < rows; ++r) s += (double)partial[(size_t)r * ncols + c];
+  for (int r = 0; r < rows; ++r) s += (double)partial[(size_t)r * row_stride + c];
   out[c] = (float)(s * (double)scale);
+}
+
+__global__ void rsqrt_eps_kernel(const float* __restrict__ v, float* __restrict__ out, int n, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)(1.0 / sqrt((double)v[i] + (double)eps));
 }
 
 // ------------------------------------------------------------------ BN apply (+dropout) (+2x2 max-pool)
@@ -521,9 +526,16 @@ int ub_bn_finalize(const float* partial, int ncols, int groups, long long count,
   return UB_OK;
 }
 
-int ub_reduce_rows(const float* partial, int rows, int ncols, float* out, float scale, cudaStream_t stream) {
-  UB_CHECK_ARG(partial && out && rows > 0 && ncols > 0, "reduce_rows: bad args");
-  reduce_rows_kernel<<<(ncols + 127) / 128, 128, 0, stream>>>(partial, rows, ncols, out, scale);
+int ub_reduce_rows(const float* partial, int rows, int row_stride, int ncols, float* out, float scale, cudaStream_t stream) {
+  UB_CHECK_ARG(partial && out && rows > 0 && ncols > 0 && row_stride >= ncols, "reduce_rows: bad args");
+  reduce_rows_kernel<<<(ncols + 127) / 128, 128, 0, stream>>>(partial, rows, row_stride, ncols, out, scale);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_inference_rstd(const float* moving_var, float* rstd, int n, float eps, cudaStream_t stream) {
+  UB_CHECK_ARG(moving_var && rstd && n > 0, "bn_inference_rstd: bad args");
+  rsqrt_eps_kernel<<<(n + 255) / 256, 256, 0, stream>>>(moving_var, rstd, n, eps);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

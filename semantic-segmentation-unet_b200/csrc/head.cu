@@ -227,12 +227,12 @@ __global__ void __launch_bounds__(TPB) head_fwd_kernel(const T* __restrict__ x, 
 }
 
 // ------------------------------------------------------------------ head loss
-// per pixel: y = BN(a); p = softmax(y); ce = -log p[label]; partial[row] = {sum ce * cw[label], #correct}
+// per pixel: y = BN(a); p = softmax(y); ce = -log p[label]; partial[row] = {inv_denom * sum ce * cw[label], acc_scale * #correct}
 // dlogits = (p - onehot) * cw[label] * inv_denom ; optional softmax output
 __global__ void __launch_bounds__(TPB) head_loss_kernel(const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         const uint8_t* __restrict__ labels, const float* __restrict__ class_w, float inv_denom,
-                                                        float* __restrict__ softmax_out, float* __restrict__ dlogits, float* __restrict__ partial,
+                                                        float acc_scale, float* __restrict__ softmax_out, float* __restrict__ dlogits, float* __restrict__ partial,
                                                         long long P, int K) {
   __shared__ float sh[TPB / 32];
   float sc[KMAX], sf[KMAX];
@@ -284,8 +284,8 @@ __global__ void __launch_bounds__(TPB) head_loss_kernel(const float* __restrict_
     const float tl = block_sum(loss, sh);
     const float tc = block_sum(correct, sh);
     if (threadIdx.x == 0) {
-      partial[(size_t)blockIdx.x * 2 + 0] = tl;
-      partial[(size_t)blockIdx.x * 2 + 1] = tc;
+      partial[(size_t)blockIdx.x * 2 + 0] = tl * inv_denom;
+      partial[(size_t)blockIdx.x * 2 + 1] = tc * acc_scale;
     }
   }
 }
@@ -530,13 +530,13 @@ int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, flo
 }
 
 int ub_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const unsigned char* labels,
-                 const float* class_w, float inv_denom, float* softmax_out, float* dlogits, float* partial, long long P, int K,
-                 cudaStream_t stream) {
+                 const float* class_w, float inv_denom, float acc_scale, float* softmax_out, float* dlogits, float* partial, long long P,
+                 int K, cudaStream_t stream) {
   UB_CHECK_ARG(a && mean && rstd && gamma && beta && P > 0, "head_loss: bad args");
   UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_loss: number_classes=%d exceeds UB_MAX_CLASSES=%d", K, KMAX);
   const int grid = grid_for(P, TPB * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2, stream));
-  head_loss_kernel<<<grid, TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, softmax_out, dlogits, partial, P, K);
+  head_loss_kernel<<<grid, TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, softmax_out, dlogits, partial, P, K);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -1,0 +1,719 @@
+"""B200-native restatement of the reference `UNet` class (UNet/model.py:19-256) -- same constructor, constants and
+public methods; every op of the graph is a hand-written sm_100a kernel reached through the C ABI (`_C.call`).
+
+torch is only the allocation shell here: tensors own device memory, `data_ptr()` is what crosses the boundary.
+There is no autograd tape: the backward schedule of the fixed reference graph is written out.
+
+Layout decisions:
+  activations NHWC, bf16 (precision='bf16', tcgen05 path) or fp32 (precision='fp32', CUDA-core check mode);
+  trainables in ONE flat fp32 buffer (`P`), gradients in a flat twin (`G`), Adam moments `M`/`V`, bf16 shadow `S`;
+  per layer the segments are [kernel | bias | beta | gamma], layers in REVERSE forward order so that gradient
+  buckets for the data-parallel all-reduce are contiguous prefixes of `G` as backward proceeds.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _C
+from ._C import call as _raw_call
+
+BN_EPS = 1e-3          # Keras BatchNormalization defaults
+BN_MOMENTUM = 0.99
+ADAM_B1, ADAM_B2, ADAM_EPS = 0.9, 0.999, 1e-7   # Keras Adam defaults (App. A.6)
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class _Layer:
+    __slots__ = ("name", "kind", "cin", "cout", "level", "ksize", "off_w", "off_b", "off_beta", "off_gamma", "n_w",
+                 "off_stat", "seg_begin", "seg_end", "c0", "c1")
+
+
+class UNet:
+    _BASELINE_FEATURE_DEPTH = 64     # UNet/model.py:20
+    _KERNEL_SIZE = 3
+    _DECONV_KERNEL_SIZE = 2
+    _POOLING_STRIDE = 2
+    SIZE_FACTOR = 16                 # UNet/model.py:25
+    RADIUS = 96                      # UNet/model.py:26
+
+    def __init__(self, number_classes, global_batch_size, number_channels, learning_rate=3e-4, label_smoothing=0,
+                 *, precision="bf16", device=None, seed=None, class_weights=None, dist=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("unetb200 requires a CUDA device (sm_100a); there is no CPU fallback")
+        if label_smoothing != 0:
+            raise NotImplementedError("label_smoothing != 0 is not used by the reference (UNet/model.py:65) and not built")
+        if number_classes < 1 or number_classes > _C.UB_MAX_CLASSES:
+            raise ValueError(f"number_classes must be in [1, {_C.UB_MAX_CLASSES}]")
+        if number_channels < 1 or number_channels > 4:
+            raise ValueError("number_channels must be in [1, 4]")
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.number_channels = int(number_channels)
+        self.number_classes = int(number_classes)
+        self.learning_rate = float(learning_rate)
+        self.global_batch_size = int(global_batch_size)
+        self.precision = precision
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.act_code = _C.UB_BF16 if precision == "bf16" else _C.UB_F32
+        self.dist = dist
+        self.step_count = 0
+        self.launches = 0
+        self.profile = None
+        self._buf = {}
+        self._inference_stale = True
+        self._build_layout()
+        self.class_weights = None
+        if class_weights is not None:
+            self.class_weights = torch.tensor(np.asarray(class_weights, dtype=np.float32), device=self.device)
+        self._init_params(seed)
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def _call(self, name, *args):
+        self.launches += 1
+        if self.profile is not None:       # bench.py: CUDA events around every entry point
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = _raw_call(name, *args, self._stream())
+            b.record()
+            self.profile.append((name, a, b))
+            return rc
+        return _raw_call(name, *args, self._stream())
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _ensure(self, name, numel, dtype):
+        t = self._buf.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(max(int(numel), 16), dtype=dtype, device=self.device)
+            self._buf[name] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------------ layout
+    def _build_layout(self):
+        b, nc, K = self._BASELINE_FEATURE_DEPTH, self.number_channels, self.number_classes
+        fwd = [("enc1a", "first", nc, b, 1), ("enc1b", "conv", b, b, 1),
+               ("enc2a", "conv", b, 2 * b, 2), ("enc2b", "conv", 2 * b, 2 * b, 2),
+               ("enc3a", "conv", 2 * b, 4 * b, 3), ("enc3b", "conv", 4 * b, 4 * b, 3),
+               ("enc4a", "conv", 4 * b, 8 * b, 4), ("enc4b", "conv", 8 * b, 8 * b, 4),
+               ("bota", "conv", 8 * b, 16 * b, 5), ("botb", "conv", 16 * b, 16 * b, 5)]
+        for lvl in (4, 3, 2, 1):
+            c = b * (1 << (lvl - 1))
+            fwd += [(f"up{lvl}", "deconv", 2 * c, c, lvl), (f"dec{lvl}a", "conv", 2 * c, c, lvl), (f"dec{lvl}b", "conv", c, c, lvl)]
+        fwd.append(("head", "head", b, K, 1))
+        self.layers = OrderedDict()
+        for name, kind, cin, cout, level in fwd:
+            L = _Layer()
+            L.name, L.kind, L.cin, L.cout, L.level = name, kind, cin, cout, level
+            L.ksize = {"first": 9, "conv": 9, "deconv": 4, "head": 1}[kind]
+            L.n_w = cout * L.ksize * cin
+            L.c0 = L.c1 = 0
+            self.layers[name] = L
+        off = 0
+        soff = 0
+        for name in reversed(list(self.layers)):       # head first: bucket order == backward order
+            L = self.layers[name]
+            L.seg_begin = off
+            L.off_w = off
+            off += _pad8(L.n_w)
+            L.off_b = off
+            off += _pad8(L.cout)
+            L.off_beta = off
+            off += _pad8(L.cout)
+            L.off_gamma = off
+            off += _pad8(L.cout)
+            L.seg_end = off
+            L.off_stat = soff
+            soff += _pad8(L.cout)
+        self.n_flat = off
+        self.n_stat = soff
+        dev = self.device
+        self.P = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.G = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.M = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.V = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.S = torch.zeros(off, dtype=torch.bfloat16, device=dev) if self.precision == "bf16" else None
+        self.MM = torch.zeros(soff, dtype=torch.float32, device=dev)      # moving_mean
+        self.MV = torch.ones(soff, dtype=torch.float32, device=dev)       # moving_variance
+        self.MR = torch.ones(soff, dtype=torch.float32, device=dev)       # 1/sqrt(moving_var + eps) for inference
+        self.mean = torch.zeros(soff, dtype=torch.float32, device=dev)    # batch statistics of the last training fwd
+        self.rstd = torch.ones(soff, dtype=torch.float32, device=dev)
+        wt_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        self.WT = {n: torch.zeros(L.n_w, dtype=wt_dtype, device=dev) for n, L in self.layers.items() if L.kind in ("conv", "deconv")}
+        self.metrics = torch.zeros(2, dtype=torch.float32, device=dev)    # [loss, accuracy] of the last step
+        self.partial = torch.zeros(_C.UB_STATS_ROWS * 2 * 2048, dtype=torch.float32, device=dev)
+        self.red = torch.zeros(4096, dtype=torch.float32, device=dev)
+
+    def trainable_count(self):
+        return sum(L.n_w + 3 * L.cout for L in self.layers.values())
+
+    # views into the flat buffers ---------------------------------------------------------------------
+    def _seg(self, flat, off, n):
+        return flat[off:off + n]
+
+    def _w(self, L, flat=None):
+        return self._seg(self.P if flat is None else flat, L.off_w, L.n_w)
+
+    def _wptr(self, L):
+        """weights as the conv kernels consume them: bf16 shadow (tcgen05 path) or the fp32 master (check mode)"""
+        if self.precision == "bf16" and L.kind in ("conv", "deconv"):
+            return self.S[L.off_w:L.off_w + L.n_w]
+        return self.P[L.off_w:L.off_w + L.n_w]
+
+    # ------------------------------------------------------------------------------------------------ params
+    def _init_params(self, seed):
+        """Keras initial state: glorot_uniform kernels, zero bias, gamma 1, beta 0, moving 0 / 1."""
+        g = torch.Generator(device="cpu")
+        g.manual_seed(int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (1 << 62)))
+        host = torch.zeros(self.n_flat, dtype=torch.float32)
+        for L in self.layers.values():
+            k2 = {"first": 9, "conv": 9, "deconv": 4, "head": 1}[L.kind]
+            lim = math.sqrt(6.0 / (k2 * L.cin + k2 * L.cout))
+            host[L.off_w:L.off_w + L.n_w] = (torch.rand(L.n_w, generator=g) * 2 - 1) * lim
+            host[L.off_gamma:L.off_gamma + L.cout] = 1.0
+        self.P.copy_(host)
+        self._weights_changed()
+
+    def _weights_changed(self):
+        """refresh the bf16 shadow and the dgrad packs after the fp32 master changed outside of Adam"""
+        if self.S is not None:
+            self._call("ub_cast_bf16", self.P, self.S, self.n_flat)
+        self._repack_dgrad()
+        self._inference_stale = True
+
+    def _repack_dgrad(self):
+        code = self.act_code
+        for n, L in self.layers.items():
+            if L.kind == "conv":
+                self._call("ub_transpose_pack", self._w(L), self.WT[n], L.cout, 9, L.cin, 1, 0, code)
+            elif L.kind == "deconv":
+                self._call("ub_transpose_pack", self._w(L), self.WT[n], L.cout, 4, L.cin, 0, 1, code)
+
+    def load_oracle_params(self, params):
+        """params: dict in the TF layouts used by the oracle / a Keras checkpoint (conv [kh,kw,Cin,Cout], deconv
+        [kh,kw,Cout,Cin], head [1,1,Cin,K]); also moving_mean / moving_var."""
+        host = self.P.cpu()
+        mm, mv = self.MM.cpu(), self.MV.cpu()
+        for n, L in self.layers.items():
+            w = torch.as_tensor(np.asarray(params[n + "/kernel"], dtype=np.float32))
+            if L.kind == "deconv":
+                packed = w.reshape(4 * L.cout, L.cin)
+            else:
+                packed = w.permute(3, 0, 1, 2).reshape(L.cout, -1)
+            host[L.off_w:L.off_w + L.n_w] = packed.reshape(-1)
+            host[L.off_b:L.off_b + L.cout] = torch.as_tensor(np.asarray(params[n + "/bias"], dtype=np.float32))
+            host[L.off_beta:L.off_beta + L.cout] = torch.as_tensor(np.asarray(params[n + "/beta"], dtype=np.float32))
+            host[L.off_gamma:L.off_gamma + L.cout] = torch.as_tensor(np.asarray(params[n + "/gamma"], dtype=np.float32))
+            if n + "/moving_mean" in params:
+                mm[L.off_stat:L.off_stat + L.cout] = torch.as_tensor(np.asarray(params[n + "/moving_mean"], dtype=np.float32))
+                mv[L.off_stat:L.off_stat + L.cout] = torch.as_tensor(np.asarray(params[n + "/moving_var"], dtype=np.float32))
+        self.P.copy_(host)
+        self.MM.copy_(mm)
+        self.MV.copy_(mv)
+        self._weights_changed()
+
+    def _unpack(self, flat_host, L):
+        w = flat_host[L.off_w:L.off_w + L.n_w]
+        if L.kind == "deconv":
+            return w.reshape(2, 2, L.cout, L.cin)
+        k = 3 if L.kind in ("conv", "first") else 1
+        return w.reshape(L.cout, k, k, L.cin).permute(1, 2, 3, 0).contiguous()
+
+    def export_flat(self, flat, with_stats=False):
+        """flat buffer (P or G) -> dict in TF layouts (for parity checks and checkpoints)"""
+        host = flat.detach().float().cpu()
+        out = OrderedDict()
+        for n, L in self.layers.items():
+            out[n + "/kernel"] = self._unpack(host, L).numpy()
+            out[n + "/bias"] = host[L.off_b:L.off_b + L.cout].numpy().copy()
+            out[n + "/gamma"] = host[L.off_gamma:L.off_gamma + L.cout].numpy().copy()
+            out[n + "/beta"] = host[L.off_beta:L.off_beta + L.cout].numpy().copy()
+        if with_stats:
+            mm, mv = self.MM.cpu(), self.MV.cpu()
+            for n, L in self.layers.items():
+                out[n + "/moving_mean"] = mm[L.off_stat:L.off_stat + L.cout].numpy().copy()
+                out[n + "/moving_var"] = mv[L.off_stat:L.off_stat + L.cout].numpy().copy()
+        return out
+
+    def export_params(self):
+        return self.export_flat(self.P, with_stats=True)
+
+    def export_grads(self):
+        return self.export_flat(self.G)
+
+    # reference API ------------------------------------------------------------------------------------
+    def get_optimizer(self):
+        return self
+
+    def set_learning_rate(self, learning_rate):          # UNet/model.py:154-155
+        self.learning_rate = float(learning_rate)
+
+    def get_learning_rate(self):
+        return self.learning_rate
+
+    def get_keras_model(self):                           # UNet/model.py:148-149
+        return self._model_call
+
+    def estimate_radius(self):
+        """UNet/model.py:160-202 derives the halo from the empirical receptive field of a noise image and rounds it
+        up to a multiple of 16; structurally that is 96 for this topology, which is what is returned.
+        (Deviation: the reference recomputes it per image from unseeded noise; see DESIGN.md.)"""
+        return UNet.RADIUS
+
+    # ------------------------------------------------------------------------------------------------ shapes
+    def _dims(self, H, W, level):
+        s = 1 << (level - 1)
+        return H // s, W // s
+
+    def _alloc(self, N, H, W, training):
+        adt = self.act_dtype
+        for n, L in self.layers.items():
+            if L.kind == "head":
+                continue
+            h, w = self._dims(H, W, L.level)
+            numel = N * h * w * L.cout
+            self._ensure("a:" + n, numel, adt)
+            self._ensure("y:" + n, numel, adt)
+            if training:
+                self._ensure("g:" + n, numel, adt)
+        for lvl in (1, 2, 3, 4):
+            h, w = self._dims(H, W, lvl + 1)
+            C = self._BASELINE_FEATURE_DEPTH << (lvl - 1)
+            self._ensure(f"pool{lvl}", N * h * w * C, adt)
+            self._ensure(f"idx{lvl}", N * h * w * C, torch.uint8)
+            if training:
+                self._ensure(f"gpool{lvl}", N * h * w * C, adt)
+                self._ensure(f"gskip{lvl}", N * 4 * h * w * C, adt)
+        P = N * H * W
+        K = self.number_classes
+        self._ensure("a:head", P * K, torch.float32)
+        if training:
+            self._ensure("dlogits", P * K, torch.float32)
+            need = 0
+            for n, L in self.layers.items():
+                h, w = self._dims(H, W, L.level)
+                if L.kind == "conv":
+                    c0 = L.cin // 2 if n.startswith("dec") and n.endswith("a") else L.cin
+                    need = max(need, _C.lib.ub_conv3x3_wgrad_workspace_bytes(c0, L.cin - c0, L.cout, N, h, w)
+                               if self.precision == "bf16" else 0)
+                elif L.kind == "deconv":
+                    need = max(need, _C.lib.ub_deconv2x2_wgrad_workspace_bytes(L.cin, L.cout, N, h // 2, w // 2)
+                               if self.precision == "bf16" else 0)
+            self._ensure("wgrad_ws", max(need, 16), torch.uint8)
+            self._ensure("first_ws", _C.UB_STATS_ROWS * self.number_channels * 9 * 64, torch.float32)
+
+    def _b(self, name):
+        return self._buf[name]
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def _bn_vectors(self, L, training):
+        o, c = L.off_stat, L.cout
+        if training:
+            return self.mean[o:o + c], self.rstd[o:o + c]
+        return self.MM[o:o + c], self.MR[o:o + c]
+
+    def _affine(self, L):
+        return self.P[L.off_gamma:L.off_gamma + L.cout], self.P[L.off_beta:L.off_beta + L.cout]
+
+    def _finalize(self, L, ncols, groups, count):
+        o, c = L.off_stat, L.cout
+        self._call("ub_bn_finalize", self.partial, ncols, groups, count, self.mean[o:o + c], self.rstd[o:o + c],
+                   self.MM[o:o + c], self.MV[o:o + c], BN_MOMENTUM, BN_EPS)
+
+    def _conv_fwd(self, L, x0, c0, x1, c1, N, h, w, training):
+        """conv3x3 + bias + relu -> a:<name>; batch statistics -> mean/rstd (training)"""
+        a = self._b("a:" + L.name)
+        bias = self.P[L.off_b:L.off_b + L.cout]
+        L.c0, L.c1 = c0, c1
+        if self.precision == "bf16":
+            self._call("ub_conv3x3_fwd", x0, c0, x1, c1, self._wptr(L), bias, a, self.partial if training else None,
+                       N, h, w, L.cout, 1)
+        else:
+            self._call("ub_check_conv3x3", x0, c0, x1, c1, self._wptr(L), bias, a, L.cout, None, 0, N, h, w, 1)
+            if training:
+                self._call("ub_bn_stats", a, self.partial, N * h * w, L.cout, self.act_code)
+        if training:
+            self._finalize(L, L.cout, 1, N * h * w)
+        return a
+
+    def _bn_apply(self, L, N, h, w, training, drop=None, pool_lvl=None):
+        a, y = self._b("a:" + L.name), self._b("y:" + L.name)
+        mean, rstd = self._bn_vectors(L, training)
+        gamma, beta = self._affine(L)
+        if pool_lvl is None:
+            self._call("ub_bn_apply", a, y, mean, rstd, gamma, beta, drop, N * h * w, L.cout, self.act_code)
+        else:
+            self._call("ub_bn_apply_pool", a, y, self._b(f"pool{pool_lvl}"), self._b(f"idx{pool_lvl}"), mean, rstd, gamma, beta,
+                       drop, N, h, w, L.cout, self.act_code)
+        return y
+
+    def _forward(self, x, N, H, W, training, drop_masks=None):
+        """x: fp32 NCHW device tensor, contiguous.  Leaves y:dec1b ready for the head; returns nothing."""
+        if H % self.SIZE_FACTOR or W % self.SIZE_FACTOR:
+            raise IOError(f"Input image tile size needs to be a multiple of {self.SIZE_FACTOR} to allow integer sized downscaled feature maps")
+        self._alloc(N, H, W, training)
+        if not training and self._inference_stale:
+            self._call("ub_bn_inference_rstd", self.MV, self.MR, self.n_stat, BN_EPS)
+            self._inference_stale = False
+        Ls = self.layers
+        dm = drop_masks or {}
+        # ---- encoder
+        L = Ls["enc1a"]
+        self._call("ub_conv_first_fwd", x, self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], self._b("a:enc1a"),
+                   self.partial if training else None, N, H, W, self.number_channels, self.act_code)
+        if training:
+            self._finalize(L, L.cout, 1, N * H * W)
+        cur = self._bn_apply(L, N, H, W, training)
+        for lvl in (1, 2, 3, 4):
+            h, w = self._dims(H, W, lvl)
+            if lvl > 1:
+                La = Ls[f"enc{lvl}a"]
+                self._conv_fwd(La, self._b(f"pool{lvl - 1}"), La.cin, None, 0, N, h, w, training)
+                cur = self._bn_apply(La, N, h, w, training)
+            Lb = Ls[f"enc{lvl}b"]
+            self._conv_fwd(Lb, cur, Lb.cin, None, 0, N, h, w, training)
+            self._bn_apply(Lb, N, h, w, training, drop=dm.get("drop4") if (lvl == 4 and training) else None, pool_lvl=lvl)
+        # ---- bottleneck
+        h, w = self._dims(H, W, 5)
+        La, Lb = Ls["bota"], Ls["botb"]
+        self._conv_fwd(La, self._b("pool4"), La.cin, None, 0, N, h, w, training)
+        cur = self._bn_apply(La, N, h, w, training)
+        self._conv_fwd(Lb, cur, Lb.cin, None, 0, N, h, w, training)
+        cur = self._bn_apply(Lb, N, h, w, training, drop=dm.get("dropb") if training else None)
+        # ---- decoder
+        for lvl in (4, 3, 2, 1):
+            hi, wi = self._dims(H, W, lvl + 1)
+            h, w = self._dims(H, W, lvl)
+            Lu = Ls[f"up{lvl}"]
+            z = self._b("a:" + Lu.name)
+            bias = self.P[Lu.off_b:Lu.off_b + Lu.cout]
+            if self.precision == "bf16":
+                self._call("ub_deconv2x2_fwd", cur, Lu.cin, self._wptr(Lu), bias, z, self.partial if training else None,
+                           N, hi, wi, Lu.cout)
+                if training:
+                    self._finalize(Lu, 4 * Lu.cout, 4, N * h * w)
+            else:
+                self._call("ub_check_deconv2x2_fwd", cur, self._wptr(Lu), bias, z, N, hi, wi, Lu.cin, Lu.cout)
+                if training:
+                    self._call("ub_bn_stats", z, self.partial, N * h * w, Lu.cout, self.act_code)
+                    self._finalize(Lu, Lu.cout, 1, N * h * w)
+            u = self._bn_apply(Lu, N, h, w, training)
+            La, Lb = Ls[f"dec{lvl}a"], Ls[f"dec{lvl}b"]
+            skip = self._b(f"y:enc{lvl}b")
+            self._conv_fwd(La, skip, Lu.cout, u, Lu.cout, N, h, w, training)       # concat [skip, up] (model.py:117)
+            cur = self._bn_apply(La, N, h, w, training)
+            self._conv_fwd(Lb, cur, Lb.cin, None, 0, N, h, w, training)
+            cur = self._bn_apply(Lb, N, h, w, training)
+        return cur
+
+    def _head_forward(self, N, H, W, training):
+        L = self.layers["head"]
+        K = self.number_classes
+        P = N * H * W
+        a = self._b("a:head")
+        self._call("ub_head_fwd", self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K], a,
+                   self.partial if training else None, P, K, self.act_code)
+        if training:
+            self._finalize(L, K, 1, P)
+        return a
+
+    def _head_loss(self, N, H, W, training, labels_u8, want_softmax, want_grad):
+        L = self.layers["head"]
+        K = self.number_classes
+        P = N * H * W
+        mean, rstd = self._bn_vectors(L, training)
+        gamma, beta = self._affine(L)
+        sm = self._ensure("softmax", P * K, torch.float32) if want_softmax else None
+        inv_denom = 1.0 / (self.global_batch_size * H * W)            # UNet/model.py:213-215
+        self._call("ub_head_loss", self._b("a:head"), mean, rstd, gamma, beta, labels_u8, self.class_weights, inv_denom, 1.0 / P,
+                   sm, self._b("dlogits") if want_grad else None, self.partial if labels_u8 is not None else None, P, K)
+        if labels_u8 is not None:
+            self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2, 2, self.metrics, 1.0)
+        return sm
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def _bn_bwd(self, L, N, h, w, relu):
+        """g:<name> holds dL/dy on entry and dL/dz (pre-activation gradient) on exit; fills dgamma/dbeta/dbias in G"""
+        g, a = self._b("g:" + L.name), self._b("a:" + L.name)
+        mean, rstd = self._bn_vectors(L, True)
+        C, M = L.cout, N * h * w
+        self._call("ub_bn_bwd_reduce", g, a, mean, rstd, self.partial, M, C, self.act_code)
+        # [sum dy | sum dy*xhat] lands directly in the flat gradient buffer: beta and gamma segments are adjacent
+        assert L.off_gamma == L.off_beta + C
+        self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2 * C, 2 * C, self.G[L.off_beta:L.off_beta + 2 * C], 1.0)
+        dbeta, dgamma = self.G[L.off_beta:L.off_beta + C], self.G[L.off_gamma:L.off_gamma + C]
+        self._call("ub_bn_bwd_apply", g, a, mean, rstd, self.P[L.off_gamma:L.off_gamma + C], dbeta, dgamma, g, self.partial, M, C,
+                   relu, self.act_code)
+        self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, C, C, self.G[L.off_b:L.off_b + C], 1.0)
+        return g
+
+    def _conv_bwd(self, L, x0, x1, N, h, w, dx0, dx1):
+        dz = self._bn_bwd(L, N, h, w, 1)
+        dw = self.G[L.off_w:L.off_w + L.n_w]
+        c0, c1 = L.c0, L.c1
+        if self.precision == "bf16":
+            ws = self._b("wgrad_ws")
+            self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
+            if dx0 is not None:
+                self._call("ub_conv3x3_dgrad", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w)
+        else:
+            self._call("ub_check_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, N, h, w)
+            if dx0 is not None:
+                self._call("ub_check_conv3x3", dz, L.cout, None, 0, self.WT[L.name], None, dx0, c0, dx1, c1, N, h, w, 0)
+
+    def _backward(self, x, N, H, W, drop_masks=None, on_layer_done=None):
+        Ls = self.layers
+        dm = drop_masks or {}
+        K = self.number_classes
+        P = N * H * W
+        done = on_layer_done or (lambda name: None)
+        # ---- head: BN backward + relu mask + 1x1 dgrad/wgrad
+        L = Ls["head"]
+        mean, rstd = self._bn_vectors(L, True)
+        dl, a = self._b("dlogits"), self._b("a:head")
+        self._call("ub_head_bwd_reduce", dl, a, mean, rstd, self.partial, P, K)
+        dbeta, dgamma = self.G[L.off_beta:L.off_beta + K], self.G[L.off_gamma:L.off_gamma + K]
+        self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2 * K, K, dbeta, 1.0)
+        self._call("ub_reduce_rows", self.partial[K:], _C.UB_STATS_ROWS, 2 * K, K, dgamma, 1.0)
+        self._call("ub_head_bwd_apply", dl, a, self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
+                   self.P[L.off_gamma:L.off_gamma + K], dbeta, dgamma, self._b("g:dec1b"), self.partial, P, K, self.act_code)
+        ncomp = K * 64 + K
+        self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, ncomp, K * 64, self.G[L.off_w:L.off_w + K * 64], 1.0)
+        self._call("ub_reduce_rows", self.partial[K * 64:], _C.UB_STATS_ROWS, ncomp, K, self.G[L.off_b:L.off_b + K], 1.0)
+        done("head")
+        # ---- decoder
+        for lvl in (1, 2, 3, 4):
+            h, w = self._dims(H, W, lvl)
+            hi, wi = self._dims(H, W, lvl + 1)
+            La, Lb, Lu = Ls[f"dec{lvl}a"], Ls[f"dec{lvl}b"], Ls[f"up{lvl}"]
+            self._conv_bwd(Lb, self._b("y:" + La.name), None, N, h, w, self._b("g:" + La.name), None)
+            done(Lb.name)
+            self._conv_bwd(La, self._b(f"y:enc{lvl}b"), self._b("y:" + Lu.name), N, h, w, self._b(f"gskip{lvl}"), self._b("g:" + Lu.name))
+            done(La.name)
+            prev = Ls[f"dec{lvl + 1}b"] if lvl < 4 else Ls["botb"]
+            dz = self._bn_bwd(Lu, N, h, w, 0)
+            dw = self.G[Lu.off_w:Lu.off_w + Lu.n_w]
+            xin = self._b("y:" + prev.name)
+            if self.precision == "bf16":
+                ws = self._b("wgrad_ws")
+                self._call("ub_deconv2x2_wgrad", xin, Lu.cin, dz, Lu.cout, dw, ws, ws.numel(), N, hi, wi)
+                self._call("ub_deconv2x2_dgrad", dz, Lu.cout, self.WT[Lu.name], self._b("g:" + prev.name), Lu.cin, N, hi, wi)
+            else:
+                self._call("ub_check_deconv2x2_wgrad", xin, dz, dw, N, hi, wi, Lu.cin, Lu.cout)
+                self._call("ub_check_deconv2x2_dgrad", dz, self._wptr(Lu), self._b("g:" + prev.name), N, hi, wi, Lu.cin, Lu.cout)
+            done(Lu.name)
+        # ---- bottleneck
+        h, w = self._dims(H, W, 5)
+        La, Lb = Ls["bota"], Ls["botb"]
+        if "dropb" in dm:
+            g = self._b("g:botb")
+            self._call("ub_dropout_bwd", g, dm["dropb"], g, N * h * w * Lb.cout, self.act_code)
+        self._conv_bwd(Lb, self._b("y:bota"), None, N, h, w, self._b("g:bota"), None)
+        done("botb")
+        self._conv_bwd(La, self._b("pool4"), None, N, h, w, self._b("gpool4"), None)
+        done("bota")
+        # ---- encoder
+        for lvl in (4, 3, 2, 1):
+            h, w = self._dims(H, W, lvl)
+            La, Lb = Ls[f"enc{lvl}a"], Ls[f"enc{lvl}b"]
+            self._call("ub_maxpool2x2_bwd_add", self._b(f"gpool{lvl}"), self._b(f"idx{lvl}"), self._b(f"gskip{lvl}"),
+                       dm.get("drop4") if lvl == 4 else None, self._b("g:" + Lb.name), N, h, w, Lb.cout, self.act_code)
+            self._conv_bwd(Lb, self._b("y:" + La.name), None, N, h, w, self._b("g:" + La.name), None)
+            done(Lb.name)
+            if lvl > 1:
+                self._conv_bwd(La, self._b(f"pool{lvl - 1}"), None, N, h, w, self._b(f"gpool{lvl - 1}"), None)
+            else:
+                dz = self._bn_bwd(La, N, h, w, 1)
+                self._call("ub_conv_first_wgrad", x, dz, self.G[La.off_w:La.off_w + La.n_w], self._b("first_ws"), N, H, W,
+                           self.number_channels, self.act_code)
+            done(La.name)
+
+    # ------------------------------------------------------------------------------------------------ optimizer
+    def _adam(self, lo=0, hi=None):
+        hi = self.n_flat if hi is None else hi
+        t = self.step_count
+        lr_t = self.learning_rate * math.sqrt(1.0 - ADAM_B2 ** t) / (1.0 - ADAM_B1 ** t)
+        self._call("ub_adam", self.P[lo:hi], self.G[lo:hi], self.M[lo:hi], self.V[lo:hi],
+                   self.S[lo:hi] if self.S is not None else None, hi - lo, lr_t, ADAM_B1, ADAM_B2, ADAM_EPS, 1.0)
+
+    # ------------------------------------------------------------------------------------------------ inputs
+    def _prep_images(self, images):
+        x = images if torch.is_tensor(images) else torch.as_tensor(np.asarray(images))
+        if x.dim() != 4 or x.shape[1] != self.number_channels:
+            raise IOError(f"images must be [N,{self.number_channels},H,W], got {tuple(x.shape)}")
+        x = x.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        return x
+
+    def _prep_labels(self, labels, N, H, W):
+        """one-hot int32 [N,H,W,K] (reference contract, imagereader.py:353-355) or uint8/int class index [N,H,W]"""
+        t = labels if torch.is_tensor(labels) else torch.as_tensor(np.asarray(labels))
+        t = t.to(self.device, non_blocking=True)
+        K = self.number_classes
+        if t.dim() == 4:
+            if tuple(t.shape) != (N, H, W, K):
+                raise IOError(f"labels must be [N,H,W,{K}] one-hot, got {tuple(t.shape)}")
+            idx = self._ensure("labels_u8", N * H * W, torch.uint8)
+            self._call("ub_onehot_to_index", t.to(torch.int32).contiguous(), idx, N * H * W, K)
+            return idx
+        if tuple(t.shape) != (N, H, W):
+            raise IOError(f"labels must be [N,H,W] class indices, got {tuple(t.shape)}")
+        return t.to(torch.uint8).contiguous()
+
+    def _make_drop_masks(self, N, H, W):
+        b = self._BASELINE_FEATURE_DEPTH
+        n4 = N * (H // 8) * (W // 8) * 8 * b
+        nb = N * (H // 16) * (W // 16) * 16 * b
+        m4 = self._ensure("drop4", _pad8(n4) + 16, torch.uint8)
+        mb = self._ensure("dropb", _pad8(nb) + 16, torch.uint8)
+        seed = getattr(self, "dropout_seed", 0x5EED) + (self.dist.rank if self.dist is not None else 0) * 7919
+        off = self.step_count * (1 << 24)
+        self._call("ub_dropout_mask", m4, (n4 + 15) // 16 * 16, seed, off)
+        self._call("ub_dropout_mask", mb, (nb + 15) // 16 * 16, seed + 1, off)
+        return {"drop4": m4, "dropb": mb}
+
+    def _import_drop_masks(self, masks):
+        """oracle-style masks (NCHW, {0,1}) -> NHWC uint8 device tensors"""
+        out = {}
+        for k, v in masks.items():
+            t = torch.as_tensor(np.asarray(v)).to(torch.uint8)
+            out[k] = t.permute(0, 2, 3, 1).contiguous().to(self.device)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ steps
+    def train_step(self, inputs, labels=None, *, dropout_masks=None, apply_update=True):
+        """UNet/model.py:204-228.  Accepts the reference tuple (images, labels, loss_metric, accuracy_metric) or
+        (images, labels).  Returns the loss as a 0-d device tensor (no host sync).
+        dropout_masks: None -> fresh Philox masks; {} / False -> no dropout; dict of NCHW {0,1} arrays -> injected."""
+        loss_metric = acc_metric = None
+        if labels is None:
+            if len(inputs) == 4:
+                images, labels, loss_metric, acc_metric = inputs
+            else:
+                images, labels = inputs
+        else:
+            images = inputs
+        x = self._prep_images(images)
+        N, _, H, W = x.shape
+        lab = self._prep_labels(labels, N, H, W)
+        self.step_count += 1
+        if dropout_masks is None:
+            dm = self._make_drop_masks(N, H, W)
+        elif not dropout_masks:
+            dm = {}
+        else:
+            dm = self._import_drop_masks(dropout_masks)
+        self._forward(x, N, H, W, True, dm)
+        self._head_forward(N, H, W, True)
+        self._head_loss(N, H, W, True, lab, False, True)
+        if self.dist is not None and self.dist.world_size > 1:
+            self.dist.begin_step(self)
+            self._backward(x, N, H, W, dm, on_layer_done=lambda name: self.dist.layer_done(self, name))
+            self.dist.finish_step(self)
+        else:
+            self._backward(x, N, H, W, dm)
+        if apply_update:
+            self._adam()
+            self._repack_dgrad()
+            self._inference_stale = True
+        loss = self.metrics[0]
+        if loss_metric is not None:
+            loss_metric.update_state(loss)
+        if acc_metric is not None:
+            acc_metric.update_state(self.metrics[1])
+        return loss
+
+    def test_step(self, inputs, labels=None):
+        """UNet/model.py:237-250: training=False (moving statistics, no dropout)."""
+        loss_metric = acc_metric = None
+        if labels is None:
+            if len(inputs) == 4:
+                images, labels, loss_metric, acc_metric = inputs
+            else:
+                images, labels = inputs
+        else:
+            images = inputs
+        x = self._prep_images(images)
+        N, _, H, W = x.shape
+        lab = self._prep_labels(labels, N, H, W)
+        self._forward(x, N, H, W, False)
+        self._head_forward(N, H, W, False)
+        self._head_loss(N, H, W, False, lab, False, False)
+        loss = self.metrics[0].clone()
+        if loss_metric is not None:
+            loss_metric.update_state(loss)
+        if acc_metric is not None:
+            acc_metric.update_state(self.metrics[1].clone())
+        return loss
+
+    def dist_train_step(self, dist_strategy, inputs):
+        """UNet/model.py:230-235: per-replica step + SUM of the per-replica losses (each already divided by the
+        global batch).  One process per GPU here: `dist_strategy` reduces the scalar across ranks."""
+        loss = self.train_step(inputs)
+        return dist_strategy.reduce_sum(loss) if dist_strategy is not None else loss
+
+    def dist_test_step(self, dist_strategy, inputs):
+        loss = self.test_step(inputs)
+        return dist_strategy.reduce_sum(loss) if dist_strategy is not None else loss
+
+    def forward_softmax(self, images, training=False, dropout_masks=None):
+        """model(images, training=...) of the reference: NCHW float32 -> softmax NHWC [N,H,W,K] (device tensor)."""
+        x = self._prep_images(images)
+        N, _, H, W = x.shape
+        dm = self._import_drop_masks(dropout_masks) if (training and dropout_masks) else {}
+        self._forward(x, N, H, W, training, dm)
+        self._head_forward(N, H, W, training)
+        sm = self._head_loss(N, H, W, training, None, True, False)
+        return sm[:N * H * W * self.number_classes].view(N, H, W, self.number_classes)
+
+    def _model_call(self, batch_data):
+        """get_keras_model()(batch) contract of UNet/inference.py:105: numpy in, array-like softmax out."""
+        return self.forward_softmax(batch_data, training=False).cpu().numpy()
+
+    def predict_tile_into(self, x, mask, mask_ld, crop, dst):
+        """Inference fast path: forward one NCHW fp32 device tile and write the argmax of its zone of responsibility
+        straight into the device mask (UNet/inference.py:105-129 without the softmax round trip).
+        crop = (cy0, cy1, cx0, cx1) inside the tile, dst = (y, x) in the mask."""
+        N, _, H, W = x.shape
+        assert N == 1
+        self._forward(x, 1, H, W, False)
+        L = self.layers["head"]
+        K = self.number_classes
+        gamma, beta = self._affine(L)
+        mm, mr = self._bn_vectors(L, False)
+        sc = self._ensure("head_scale", 2 * _C.UB_MAX_CLASSES, torch.float32)
+        # folded BN affine of the head: scale = gamma * rstd, shift = beta - mean * scale (tiny, K elements)
+        sc[:K] = gamma * mr
+        sc[K:2 * K] = beta - mm * sc[:K]
+        self._call("ub_head_argmax", self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K], sc[:K], sc[K:2 * K],
+                   K, H, W, crop[0], crop[1], crop[2], crop[3], mask, mask_ld, dst[0], dst[1], None, self.act_code)
+
+    # ------------------------------------------------------------------------------------------------ checkpoint
+    def state_dict(self):
+        return {"P": self.P.cpu(), "M": self.M.cpu(), "V": self.V.cpu(), "MM": self.MM.cpu(), "MV": self.MV.cpu(),
+                "step": self.step_count, "number_classes": self.number_classes, "number_channels": self.number_channels,
+                "learning_rate": self.learning_rate}
+
+    def save_checkpoint(self, checkpoint_filepath):
+        """counterpart of tf.train.Checkpoint(optimizer, model).write(path) (UNet/train.py:96, :181-184); native format"""
+        torch.save(self.state_dict(), checkpoint_filepath)
+
+    def load_checkpoint(self, checkpoint_filepath: str):     # UNet/model.py:81-83 (expect_partial: optimizer slots optional)
+        sd = torch.load(checkpoint_filepath, map_location="cpu")
+        if sd["number_classes"] != self.number_classes or sd["number_channels"] != self.number_channels:
+            raise IOError("checkpoint was written for a different number_classes / number_channels")
+        self.P.copy_(sd["P"])
+        self.MM.copy_(sd["MM"])
+        self.MV.copy_(sd["MV"])
+        if "M" in sd:
+            self.M.copy_(sd["M"])
+            self.V.copy_(sd["V"])
+            self.step_count = int(sd.get("step", 0))
+        self._weights_changed()

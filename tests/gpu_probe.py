@@ -11,11 +11,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def run_one(name):
+def all_cases():
+    import graph_cases as G
     import kernel_cases as K
+    d = dict(K.CASES)
+    d.update(G.CASES)
+    return d
+
+
+def run_one(name):
     import torch
     torch.cuda.init()
-    r = K.CASES[name]()
+    r = all_cases()[name]()
     print("RESULT " + json.dumps(r))
 
 
@@ -23,16 +30,16 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
         run_one(sys.argv[2])
         sys.exit(0)
-    import kernel_cases as K
     pat = sys.argv[1] if len(sys.argv) > 1 else ""
+    cases = all_cases()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     report = {}
-    for name in K.CASES:
-        if pat and pat not in name:
+    for name in cases:
+        if pat and not any(q in name for q in pat.split(",")):
             continue
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=180)
+            p = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=300)
             res = None
             for line in p.stdout.splitlines():
                 if line.startswith("RESULT "):

@@ -235,11 +235,11 @@ def case_bn_bwd(C_=64, N=2, H=16, W=24, dtype="f32", relu=1, seed=6):
     partial = torch.empty(C.UB_STATS_ROWS * 2 * C_, dtype=torch.float32, device="cuda")
     red = torch.empty(2 * C_, dtype=torch.float32, device="cuda")
     C.call("ub_bn_bwd_reduce", dyd, ad, mean, rstd, partial, M, C_, code, stream())
-    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2 * C_, red, 1.0, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2 * C_, 2 * C_, red, 1.0, stream())
     dz = torch.empty_like(ad)
     dbias = torch.empty(C_, dtype=torch.float32, device="cuda")
     C.call("ub_bn_bwd_apply", dyd, ad, mean, rstd, dev(gamma, torch.float32), red[:C_], red[C_:], dz, partial, M, C_, relu, code, stream())
-    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, C_, dbias, 1.0, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, C_, C_, dbias, 1.0, stream())
     torch.cuda.synchronize()
     tol = 1e-2 if dtype == "bf16" else 1e-5
     e_db = rel_err(red[:C_].cpu().numpy(), db)
@@ -331,22 +331,23 @@ def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
     dl = torch.empty((P, K), dtype=torch.float32, device="cuda")
     gd, btd = dev(gamma, torch.float32), dev(beta, torch.float32)
     cwd = dev(cw, torch.float32) if weighted else None
-    C.call("ub_head_loss", a_d, mean, rstd, gd, btd, dev(lab, torch.uint8), cwd, inv_denom, sm, dl, partial, P, K, stream())
+    C.call("ub_head_loss", a_d, mean, rstd, gd, btd, dev(lab, torch.uint8), cwd, inv_denom, 1.0 / P, sm, dl, partial, P, K, stream())
     la = torch.empty(2, device="cuda")
-    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2, la, 1.0, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2, 2, la, 1.0, stream())
     red = torch.empty(2 * K, device="cuda")
     C.call("ub_head_bwd_reduce", dl, a_d, mean, rstd, partial, P, K, stream())
-    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2 * K, red, 1.0, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2 * K, 2 * K, red, 1.0, stream())
     dx = torch.empty((P, 64), dtype=torch.float32, device="cuda")
     gw = torch.empty(K * 64 + K, device="cuda")
     C.call("ub_head_bwd_apply", dl, a_d, xd, wd, mean, rstd, gd, red[:K], red[K:], dx, partial, P, K, C.UB_F32, stream())
-    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, K * 64 + K, gw, 1.0, stream())
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, K * 64 + K, K * 64 + K, gw, 1.0, stream())
     torch.cuda.synchronize()
     la = la.cpu().numpy()
-    r = dict(e_a=rel_err(a_d.cpu().numpy(), a), e_sm=rel_err(sm.cpu().numpy(), p), e_loss=abs(la[0] * inv_denom - loss_ref) / abs(loss_ref),
-             e_acc=abs(la[1] / P - acc_ref), e_dl=rel_err(dl.cpu().numpy(), dy_ref), e_dbeta=rel_err(red[:K].cpu().numpy(), dbeta),
+    r = dict(e_a=rel_err(a_d.cpu().numpy(), a), e_sm=rel_err(sm.cpu().numpy(), p), e_loss=abs(la[0] - loss_ref) / abs(loss_ref),
+             e_acc=abs(la[1] - acc_ref), e_dl=rel_err(dl.cpu().numpy(), dy_ref), e_dbeta=rel_err(red[:K].cpu().numpy(), dbeta),
              e_dgamma=rel_err(red[K:].cpu().numpy(), dgamma), e_dx=rel_err(dx.cpu().numpy(), dx_ref),
              e_dW=rel_err(gw[:K * 64].cpu().numpy().reshape(K, 64), dW_ref), e_db=rel_err(gw[K * 64:].cpu().numpy(), db_ref))
+    r = {k: float(v) for k, v in r.items()}
     r["ok"] = bool(all(v < 2e-4 for k, v in r.items() if k.startswith("e_")))
     return r
 
