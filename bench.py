@@ -171,6 +171,20 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def write_layer_table(path, layer_ms):
+    """per (layer, entry point): ms per step, and TFLOP/s for the tensor-core entry points (events around each launch)"""
+    fl = layer_flops()
+    rows = []
+    for (layer, name), ms in sorted(layer_ms.items(), key=lambda kv: -kv[1]):
+        tf = None
+        if name in FAMILY and layer in fl:
+            tf = BATCH * fl[layer][1] / (ms * 1e-3) / 1e12
+        rows.append({"layer": layer, "entry": name, "ms": round(ms, 4), "tflops": round(tf, 1) if tf else None})
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(rows, f, indent=0)
+
+
 # ---------------------------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
     import torch
@@ -253,13 +267,17 @@ def run_cuda(args):
         for i in range(nprof):
             model.train_step(dx[i % nb], dl[i % nb])
         torch.cuda.synchronize(dev)
-        for name, a, b in model.profile:
+        layer_ms = {}
+        for name, layer, a, b in model.profile:
             t = a.elapsed_time(b)
             kern_ms[name] = kern_ms.get(name, 0.0) + t / nprof
             f = FAMILY.get(name)
             if f:
                 fam_ms[f] = fam_ms.get(f, 0.0) + t / nprof
+            layer_ms[(layer, name)] = layer_ms.get((layer, name), 0.0) + t / nprof
         model.profile = None
+        if args.layers:
+            write_layer_table(args.layers, layer_ms)
     if dp:
         dp.barrier()
 
@@ -311,6 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", default=None, help="write a per-layer / per-entry-point timing table (JSON) to this path")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3

@@ -113,10 +113,16 @@ def _bn(x, name, params, training, new_stats):
     return (x - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + BN_EPS) * g + b
 
 
-def _conv_block(x, name, params, training, new_stats, taps):
+def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None):
     w = params[name + "/kernel"].permute(3, 2, 0, 1)          # HWIO -> OIHW  (App. A.1)
     z = F.conv2d(x, w, params[name + "/bias"], padding=w.shape[-1] // 2)
-    a = F.relu(z)
+    if relu_masks is not None and name in relu_masks:
+        # conditioned comparison (tests only): the activation pattern [z > 0] is taken from the implementation under
+        # test, so that sign flips of pre-activations within rounding distance of 0 do not turn a 1e-7 forward
+        # difference into an O(1) change of the piecewise-linear backward.  Forward values differ by <= |z| ~ rounding.
+        a = z * relu_masks[name].to(z.dtype)
+    else:
+        a = F.relu(z)
     if taps is not None:
         taps[name + "/act"] = a
     y = _bn(a, name, params, training, new_stats)
@@ -145,30 +151,41 @@ def _dropout(x, mask, training):
     return x * mask.to(x.dtype) * 2.0
 
 
-def forward(params, x, training, dropout_masks=None, new_stats=None, taps=None):
+def _pool(x, idx=None):
+    """MaxPool2D(2) (UNet/model.py:50-53).  idx (tests only): [N,C,H/2,W/2] window slot 2*dy+dx chosen by the
+    implementation under test; routes value and gradient through that element instead of torch's own argmax."""
+    if idx is None:
+        return F.max_pool2d(x, 2)
+    n, c, h, w = x.shape
+    win = x.reshape(n, c, h // 2, 2, w // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(n, c, h // 2, w // 2, 4)
+    return torch.gather(win, -1, idx.long().unsqueeze(-1)).squeeze(-1)
+
+
+def forward(params, x, training, dropout_masks=None, new_stats=None, taps=None, relu_masks=None, pool_idx=None):
     """UNet/model.py:85-146.  x: [N,C,H,W].  Returns (softmax NHWC [N,H,W,K], logits NHWC).
 
     `logits` is what the Softmax layer consumes: the BN output of the ReLU'd 1x1 conv.
     dropout_masks: {'drop4': [N,8b,H/8,W/8], 'dropb': [N,16b,H/16,W/16]} of {0,1}; None => no dropout.
     """
     dm = dropout_masks or {}
-    c1 = _conv_block(_conv_block(x, "enc1a", params, training, new_stats, taps), "enc1b", params, training, new_stats, taps)
-    p1 = F.max_pool2d(c1, 2)
-    c2 = _conv_block(_conv_block(p1, "enc2a", params, training, new_stats, taps), "enc2b", params, training, new_stats, taps)
-    p2 = F.max_pool2d(c2, 2)
-    c3 = _conv_block(_conv_block(p2, "enc3a", params, training, new_stats, taps), "enc3b", params, training, new_stats, taps)
-    p3 = F.max_pool2d(c3, 2)
-    c4 = _conv_block(_conv_block(p3, "enc4a", params, training, new_stats, taps), "enc4b", params, training, new_stats, taps)
+    pool_idx = pool_idx or {}
+    c1 = _conv_block(_conv_block(x, "enc1a", params, training, new_stats, taps, relu_masks), "enc1b", params, training, new_stats, taps, relu_masks)
+    p1 = _pool(c1, pool_idx.get("pool1"))
+    c2 = _conv_block(_conv_block(p1, "enc2a", params, training, new_stats, taps, relu_masks), "enc2b", params, training, new_stats, taps, relu_masks)
+    p2 = _pool(c2, pool_idx.get("pool2"))
+    c3 = _conv_block(_conv_block(p2, "enc3a", params, training, new_stats, taps, relu_masks), "enc3b", params, training, new_stats, taps, relu_masks)
+    p3 = _pool(c3, pool_idx.get("pool3"))
+    c4 = _conv_block(_conv_block(p3, "enc4a", params, training, new_stats, taps, relu_masks), "enc4b", params, training, new_stats, taps, relu_masks)
     c4 = _dropout(c4, dm.get("drop4"), training)                 # skip-4 carries the dropped tensor (Q2)
-    p4 = F.max_pool2d(c4, 2)
-    bt = _conv_block(_conv_block(p4, "bota", params, training, new_stats, taps), "botb", params, training, new_stats, taps)
+    p4 = _pool(c4, pool_idx.get("pool4"))
+    bt = _conv_block(_conv_block(p4, "bota", params, training, new_stats, taps, relu_masks), "botb", params, training, new_stats, taps, relu_masks)
     bt = _dropout(bt, dm.get("dropb"), training)
     d = bt
     for lvl, skip in ((4, c4), (3, c3), (2, c2), (1, c1)):
         u = _deconv_block(d, f"up{lvl}", params, training, new_stats, taps)
         cat = torch.cat([skip, u], dim=1)                         # [skip, up]  UNet/model.py:117
-        d = _conv_block(_conv_block(cat, f"dec{lvl}a", params, training, new_stats, taps), f"dec{lvl}b", params, training, new_stats, taps)
-    logits = _conv_block(d, "head", params, training, new_stats, taps)   # 1x1 + ReLU + BN (Q1)
+        d = _conv_block(_conv_block(cat, f"dec{lvl}a", params, training, new_stats, taps, relu_masks), f"dec{lvl}b", params, training, new_stats, taps, relu_masks)
+    logits = _conv_block(d, "head", params, training, new_stats, taps, relu_masks)   # 1x1 + ReLU + BN (Q1)
     logits = logits.permute(0, 2, 3, 1)
     return torch.softmax(logits, dim=-1), logits
 
@@ -182,7 +199,8 @@ def loss_and_accuracy(logits_nhwc, labels_onehot, global_batch_size):
     return loss, acc
 
 
-def train_step_grads(params, x, labels_onehot, global_batch_size, dropout_masks=None, taps=None):
+def train_step_grads(params, x, labels_onehot, global_batch_size, dropout_masks=None, taps=None, relu_masks=None,
+                     pool_idx=None):
     """fwd(training=True) + loss + grads of every trainable tensor (UNet/model.py:204-221).
 
     Returns dict(loss, acc, softmax, logits, grads{name: tensor}, new_stats{...}).
@@ -192,11 +210,15 @@ def train_step_grads(params, x, labels_onehot, global_batch_size, dropout_masks=
     for k, v in params.items():
         leaves[k] = v.detach().clone().requires_grad_(k in names)
     new_stats = {}
-    sm, logits = forward(leaves, x, True, dropout_masks, new_stats, taps)
+    sm, logits = forward(leaves, x, True, dropout_masks, new_stats, taps, relu_masks, pool_idx)
     loss, acc = loss_and_accuracy(logits, labels_onehot, global_batch_size)
-    grads = torch.autograd.grad(loss, [leaves[k] for k in names])
-    return dict(loss=loss.detach(), acc=acc, softmax=sm.detach(), logits=logits.detach(),
-                grads=OrderedDict(zip(names, grads)), new_stats=new_stats)
+    tap_keys = list(taps.keys()) if taps is not None else []
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names] + [taps[k] for k in tap_keys])
+    out = dict(loss=loss.detach(), acc=acc, softmax=sm.detach(), logits=logits.detach(),
+               grads=OrderedDict(zip(names, grads[:len(names)])), new_stats=new_stats)
+    if taps is not None:      # dL/d(activation) and dL/d(BN output) of every layer, for per-layer debugging
+        out["tap_grads"] = OrderedDict(zip(tap_keys, grads[len(names):]))
+    return out
 
 
 def test_step(params, x, labels_onehot, global_batch_size):

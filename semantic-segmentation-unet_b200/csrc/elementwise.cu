@@ -97,20 +97,40 @@ __global__ void __launch_bounds__(TPB) bn_stats_kernel(const T* __restrict__ a, 
   block_channel_reduce<2>(acc, C, partial);
 }
 
+// Row-parallel column sums: a block owns 32 columns; thread (lane = column, ry = row lane) sums rows ry, ry+8, ... in
+// fp64, the 8 row lanes are combined through shared memory in a fixed order (deterministic).
+constexpr int RED_ROWLANES = 8;
+__device__ __forceinline__ double block_rows_sum(double v, double (*sh)[32]) {
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  __syncthreads();
+  sh[ry][lane] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int r = 0; r < RED_ROWLANES; ++r) t += sh[r][lane];
+  return t;
+}
+
 // partial[rows][2][ncols]; channel c gathers columns g*C + c for g < groups.  Biased variance normalises (training),
 // the unbiased one feeds the moving average.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, int ncols, int groups, double count,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ moving_mean,
-                                   float* __restrict__ moving_var, float momentum, float eps) {
+__global__ void __launch_bounds__(32 * RED_ROWLANES) bn_finalize_kernel(const float* __restrict__ partial, int rows, int ncols, int groups,
+                                                                        double count, float* __restrict__ mean, float* __restrict__ rstd,
+                                                                        float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                                                        float momentum, float eps) {
+  __shared__ double sh[RED_ROWLANES][32];
   const int C = ncols / groups;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
-  for (int r = 0; r < rows; ++r)
-    for (int g = 0; g < groups; ++g) {
-      s += (double)partial[((size_t)r * 2 + 0) * ncols + g * C + c];
-      q += (double)partial[((size_t)r * 2 + 1) * ncols + g * C + c];
-    }
+  if (c < C)
+    for (int r = ry; r < rows; r += RED_ROWLANES)
+      for (int g = 0; g < groups; ++g) {
+        s += (double)partial[((size_t)r * 2 + 0) * ncols + g * C + c];
+        q += (double)partial[((size_t)r * 2 + 1) * ncols + g * C + c];
+      }
+  s = block_rows_sum(s, sh);
+  q = block_rows_sum(q, sh);
+  if (ry != 0 || c >= C) return;
   const double mu = s / count;
   double var = q / count - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -124,12 +144,16 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int rows, 
 }
 
 // out[c] = scale * sum_rows partial[r * row_stride + c],  c < ncols
-__global__ void reduce_rows_kernel(const float* __restrict__ partial, int rows, int row_stride, int ncols, float* __restrict__ out, float scale) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
+__global__ void __launch_bounds__(32 * RED_ROWLANES) reduce_rows_kernel(const float* __restrict__ partial, int rows, int row_stride, int ncols,
+                                                                        float* __restrict__ out, float scale) {
+  __shared__ double sh[RED_ROWLANES][32];
+  const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int r = 0; r < rows; ++r) s += (double)partial[(size_t)r * row_stride + c];
-  out[c] = (float)(s * (double)scale);
+  if (c < ncols)
+    for (int r = ry; r < rows; r += RED_ROWLANES) s += (double)partial[(size_t)r * row_stride + c];
+  s = block_rows_sum(s, sh);
+  if (ry == 0 && c < ncols) out[c] = (float)(s * (double)scale);
 }
 
 __global__ void rsqrt_eps_kernel(const float* __restrict__ v, float* __restrict__ out, int n, float eps) {
@@ -328,11 +352,9 @@ __global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const T* __restrict__
       float v = ga[i] * (d[i] - db[i] - xh * dg[i]);
       if (relu && !(f[i] > 0.f)) v = 0.f;
       d[i] = v;
+      acc[0][i] += v;   // bias gradient from the fp32 value (the reference is fp32; a deconv bias gradient is analytically 0)
     }
     V8<T>::store(dz + px * C + g * 8, d);
-    // accumulate what the consumers (wgrad / dgrad) will read
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[0][i] += storage_round<T>(d[i]);
   }
   block_channel_reduce<1>(acc, C, partial);
 }
@@ -520,15 +542,15 @@ int ub_bn_finalize(const float* partial, int ncols, int groups, long long count,
                    float* moving_var, float momentum, float eps, cudaStream_t stream) {
   UB_CHECK_ARG(partial && mean && rstd && groups > 0 && ncols % groups == 0 && count > 0, "bn_finalize: bad args");
   const int C = ncols / groups;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, UB_STATS_ROWS, ncols, groups, (double)count, mean, rstd, moving_mean,
-                                                         moving_var, momentum, eps);
+  bn_finalize_kernel<<<(C + 31) / 32, 32 * RED_ROWLANES, 0, stream>>>(partial, UB_STATS_ROWS, ncols, groups, (double)count, mean, rstd,
+                                                                     moving_mean, moving_var, momentum, eps);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
 
 int ub_reduce_rows(const float* partial, int rows, int row_stride, int ncols, float* out, float scale, cudaStream_t stream) {
   UB_CHECK_ARG(partial && out && rows > 0 && ncols > 0 && row_stride >= ncols, "reduce_rows: bad args");
-  reduce_rows_kernel<<<(ncols + 127) / 128, 128, 0, stream>>>(partial, rows, row_stride, ncols, out, scale);
+  reduce_rows_kernel<<<(ncols + 31) / 32, 32 * RED_ROWLANES, 0, stream>>>(partial, rows, row_stride, ncols, out, scale);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

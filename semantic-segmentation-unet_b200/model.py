@@ -67,6 +67,7 @@ class UNet:
         self.step_count = 0
         self.launches = 0
         self.profile = None
+        self._cur = ""                    # layer the current launches belong to (profiling tag)
         self._buf = {}
         self._inference_stale = True
         self._build_layout()
@@ -83,7 +84,7 @@ class UNet:
             a.record()
             rc = _raw_call(name, *args, self._stream())
             b.record()
-            self.profile.append((name, a, b))
+            self.profile.append((name, self._cur, a, b))
             return rc
         return _raw_call(name, *args, self._stream())
 
@@ -249,6 +250,23 @@ class UNet:
     def export_grads(self):
         return self.export_flat(self.G)
 
+    def export_activation_pattern(self, N, H, W):
+        """({layer: bool NCHW [a > 0]}, {"pool<l>": uint8 NCHW window slot 2*dy+dx}) of the last training forward.
+        Parity tests hand these to the oracle so that both sides differentiate the same piecewise-linear branch."""
+        relu, pool = {}, {}
+        for n, L in self.layers.items():
+            if L.kind == "deconv":
+                continue
+            h, w = self._dims(H, W, L.level)
+            a = self._b("a:" + n)[:N * h * w * L.cout].view(N, h, w, L.cout)
+            relu[n] = (a > 0).permute(0, 3, 1, 2).contiguous().cpu()
+        for lvl in (1, 2, 3, 4):
+            h, w = self._dims(H, W, lvl + 1)
+            C = self._BASELINE_FEATURE_DEPTH << (lvl - 1)
+            idx = self._b(f"idx{lvl}")[:N * h * w * C].view(N, h, w, C)
+            pool[f"pool{lvl}"] = idx.permute(0, 3, 1, 2).contiguous().cpu()
+        return relu, pool
+
     # reference API ------------------------------------------------------------------------------------
     def get_optimizer(self):
         return self
@@ -330,6 +348,7 @@ class UNet:
 
     def _conv_fwd(self, L, x0, c0, x1, c1, N, h, w, training):
         """conv3x3 + bias + relu -> a:<name>; batch statistics -> mean/rstd (training)"""
+        self._cur = L.name
         a = self._b("a:" + L.name)
         bias = self.P[L.off_b:L.off_b + L.cout]
         L.c0, L.c1 = c0, c1
@@ -345,6 +364,7 @@ class UNet:
         return a
 
     def _bn_apply(self, L, N, h, w, training, drop=None, pool_lvl=None):
+        self._cur = L.name
         a, y = self._b("a:" + L.name), self._b("y:" + L.name)
         mean, rstd = self._bn_vectors(L, training)
         gamma, beta = self._affine(L)
@@ -367,6 +387,7 @@ class UNet:
         dm = drop_masks or {}
         # ---- encoder
         L = Ls["enc1a"]
+        self._cur = "enc1a"
         self._call("ub_conv_first_fwd", x, self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], self._b("a:enc1a"),
                    self.partial if training else None, N, H, W, self.number_channels, self.act_code)
         if training:
@@ -393,6 +414,7 @@ class UNet:
             hi, wi = self._dims(H, W, lvl + 1)
             h, w = self._dims(H, W, lvl)
             Lu = Ls[f"up{lvl}"]
+            self._cur = Lu.name
             z = self._b("a:" + Lu.name)
             bias = self.P[Lu.off_b:Lu.off_b + Lu.cout]
             if self.precision == "bf16":
@@ -416,6 +438,7 @@ class UNet:
 
     def _head_forward(self, N, H, W, training):
         L = self.layers["head"]
+        self._cur = "head"
         K = self.number_classes
         P = N * H * W
         a = self._b("a:head")
@@ -442,6 +465,7 @@ class UNet:
     # ------------------------------------------------------------------------------------------------ backward
     def _bn_bwd(self, L, N, h, w, relu):
         """g:<name> holds dL/dy on entry and dL/dz (pre-activation gradient) on exit; fills dgamma/dbeta/dbias in G"""
+        self._cur = L.name
         g, a = self._b("g:" + L.name), self._b("a:" + L.name)
         mean, rstd = self._bn_vectors(L, True)
         C, M = L.cout, N * h * w
@@ -477,6 +501,7 @@ class UNet:
         done = on_layer_done or (lambda name: None)
         # ---- head: BN backward + relu mask + 1x1 dgrad/wgrad
         L = Ls["head"]
+        self._cur = "head"
         mean, rstd = self._bn_vectors(L, True)
         dl, a = self._b("dlogits"), self._b("a:head")
         self._call("ub_head_bwd_reduce", dl, a, mean, rstd, self.partial, P, K)
@@ -538,6 +563,7 @@ class UNet:
 
     # ------------------------------------------------------------------------------------------------ optimizer
     def _adam(self, lo=0, hi=None):
+        self._cur = "optimizer"
         hi = self.n_flat if hi is None else hi
         t = self.step_count
         lr_t = self.learning_rate * math.sqrt(1.0 - ADAM_B2 ** t) / (1.0 - ADAM_B1 ** t)
@@ -588,7 +614,7 @@ class UNet:
         return out
 
     # ------------------------------------------------------------------------------------------------ steps
-    def train_step(self, inputs, labels=None, *, dropout_masks=None, apply_update=True):
+    def train_step(self, inputs, labels=None, *, dropout_masks=None, apply_update=True, keep_softmax=False):
         """UNet/model.py:204-228.  Accepts the reference tuple (images, labels, loss_metric, accuracy_metric) or
         (images, labels).  Returns the loss as a 0-d device tensor (no host sync).
         dropout_masks: None -> fresh Philox masks; {} / False -> no dropout; dict of NCHW {0,1} arrays -> injected."""
@@ -612,7 +638,7 @@ class UNet:
             dm = self._import_drop_masks(dropout_masks)
         self._forward(x, N, H, W, True, dm)
         self._head_forward(N, H, W, True)
-        self._head_loss(N, H, W, True, lab, False, True)
+        self._head_loss(N, H, W, True, lab, keep_softmax, True)
         if self.dist is not None and self.dist.world_size > 1:
             self.dist.begin_step(self)
             self._backward(x, N, H, W, dm, on_layer_done=lambda name: self.dist.layer_done(self, name))

@@ -57,6 +57,7 @@ def host_case():
 
 
 if __name__ == "__main__":
-    graph_case("graph_c1_k2", N=2, C=1, H=32, W=48, K=2, seed=11, gb=2)
-    graph_case("graph_c3_k8", N=1, C=3, H=32, W=32, K=8, seed=12, gb=4)
+    # sizes chosen so that the bottleneck BatchNorm still sees >= 48 samples per channel (well-conditioned statistics)
+    graph_case("graph_c1_k2", N=2, C=1, H=96, W=64, K=2, seed=11, gb=2)
+    graph_case("graph_c3_k8", N=1, C=3, H=112, W=112, K=8, seed=12, gb=4)
     host_case()

@@ -1,7 +1,18 @@
-"""Whole-graph parity: the CUDA train step (through unetb200.model.UNet -> C ABI) against the oracle and the committed
-golden fixtures.  Error metric everywhere: max|got-ref| / max|ref| per tensor (relative to the tensor's largest
-magnitude; gradients that are analytically zero -- deconv biases feeding straight into BN -- are judged against the
-largest gradient magnitude of the layer's kernel instead)."""
+"""Whole-graph parity: the CUDA train step / inference forward (unetb200.model.UNet -> C ABI) against the oracle
+(oracle/unet_oracle.py, fp64) and the committed golden fixtures (tests/golden/, generated from the oracle).
+
+Error metric: max|got - ref| / max|ref| per tensor (north_star: <= 1e-2 bf16, <= 1e-4 fp32 check mode).
+
+Gradients are compared CONDITIONED on the activation pattern of the implementation under test: the oracle is re-run
+with the CUDA path's ReLU masks [a > 0] and max-pool argmax slots injected (oracle/unet_oracle.py `relu_masks`,
+`pool_idx`).  The U-Net is piecewise linear in its activations; a pre-activation within rounding distance of zero
+flips its mask between ANY two implementations (torch fp32 vs torch fp64 already differ by 5-10 % in max-norm on these
+shapes because of 1-3 such flips, see DESIGN.md "Parity methodology"), which says nothing about kernel correctness.
+The forward quantities (softmax, loss, accuracy, BN statistics) are compared against the UNCONDITIONED oracle, and
+the unconditioned gradient error is reported too (`e_grad_uncond`, bounded loosely).
+Analytically-zero gradients (deconv biases feed straight into BatchNorm) are judged against the layer's kernel
+gradient magnitude.
+"""
 from __future__ import annotations
 
 import os
@@ -19,14 +30,120 @@ from oracle import unet_oracle as O  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 # tolerances (north_star): bf16 storage <= 1e-2, fp32 check mode <= 1e-4
-TOL = {"bf16": dict(softmax=1e-2, loss=1e-2, grad=3e-2, stat=1e-2),
-       "fp32": dict(softmax=1e-4, loss=1e-4, grad=1e-4, stat=1e-4)}
+TOL = {"bf16": dict(softmax=1e-2, loss=1e-2, grad=1e-2, stat=1e-2, uncond=0.25, agree=0.99),
+       "fp32": dict(softmax=1e-4, loss=1e-4, grad=1e-4, stat=1e-4, uncond=0.25, agree=0.9995)}
 
 
 def rel(got, ref, floor=0.0):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
     return float(np.abs(got - ref).max() / max(np.abs(ref).max(), floor, 1e-30))
+
+
+def grad_errors(got, ref):
+    """per-tensor max-norm relative error; deconv biases (analytically zero) relative to the kernel gradient"""
+    out = {}
+    for n, gref in ref.items():
+        gref = gref.numpy() if hasattr(gref, "numpy") else np.asarray(gref)
+        layer = n.split("/")[0]
+        floor = 0.0
+        if layer.startswith("up") and n.endswith("/bias"):
+            k = ref[layer + "/kernel"]
+            floor = float(np.abs(k.numpy() if hasattr(k, "numpy") else k).max())
+        out[n] = rel(got[n], gref, floor)
+    return out
+
+
+def make_inputs(N, C, H, W, K, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.normal(size=(N, C, H, W)).astype(np.float32)
+    lab = rng.integers(0, K, size=(N, H, W)).astype(np.uint8)
+    dm = {"drop4": rng.integers(0, 2, size=(N, 512, H // 8, W // 8)).astype(np.uint8),
+          "dropb": rng.integers(0, 2, size=(N, 1024, H // 16, W // 16)).astype(np.uint8)}
+    return x, lab, dm
+
+
+def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None):
+    """one training step: softmax / loss / accuracy / BN moving statistics vs the oracle; all 92 gradients vs the
+    oracle conditioned on the CUDA path's activation pattern"""
+    from unetb200.model import UNet
+    tol = TOL[precision]
+    gb = gb or N
+    p = O.init_params(C, K, seed=seed, base=64, randomize_affine=True)
+    x, lab, dm = make_inputs(N, C, H, W, K, seed)
+    oh = np.eye(K, dtype=np.int32)[lab]
+    m = UNet(K, gb, C, learning_rate=1e-3, precision=precision, seed=0)
+    m.load_oracle_params({k: v.numpy() for k, v in p.items()})
+    m.train_step(torch.tensor(x), torch.tensor(oh), dropout_masks=dm, apply_update=False, keep_softmax=True)   # one-hot label contract
+    torch.cuda.synchronize()
+    met = m.metrics.cpu().numpy()
+    sm = m._b("softmax")[:N * H * W * K].view(N, H, W, K).cpu().numpy()
+    grads = m.export_grads()
+    stats = m.export_params()
+    relu, pool = m.export_activation_pattern(N, H, W)
+
+    xt, oht = torch.tensor(x, dtype=torch.float64), torch.tensor(oh)
+    dmt = {k: torch.tensor(v) for k, v in dm.items()}
+    ref = O.train_step_grads(p, xt, oht, gb, dmt)
+    refc = O.train_step_grads(p, xt, oht, gb, dmt, relu_masks=relu, pool_idx=pool)
+
+    r = {}
+    r["e_softmax"] = rel(sm, ref["softmax"].numpy())
+    r["argmax_agree"] = float((sm.argmax(-1) == ref["softmax"].numpy().argmax(-1)).mean())
+    r["e_loss"] = abs(float(met[0]) - float(ref["loss"])) / abs(float(ref["loss"]))
+    r["e_acc"] = abs(float(met[1]) - float(ref["acc"]))
+    r["e_stat"] = max(rel(stats[k], v.numpy()) for k, v in ref["new_stats"].items())
+    ec = grad_errors(grads, refc["grads"])
+    eu = grad_errors(grads, ref["grads"])
+    wc = max(ec, key=ec.get)
+    wu = max(eu, key=eu.get)
+    r["e_grad"], r["worst_grad"] = ec[wc], wc
+    r["e_grad_uncond"], r["worst_uncond"] = eu[wu], wu
+    r["e_loss_cond"] = abs(float(refc["loss"]) - float(ref["loss"])) / abs(float(ref["loss"]))
+    fl = 0
+    t = {}
+    O.forward(p, xt, True, dmt, None, t)
+    for n, mk in relu.items():
+        fl += int(((t[n + "/act"] > 0) != mk).sum())
+    r["relu_flips"] = fl
+    if os.environ.get("UB_VERBOSE"):
+        r["grad_errs"] = {k: float(f"{v:.3g}") for k, v in ec.items()}
+    r["ok"] = bool(r["e_softmax"] < tol["softmax"] and r["e_loss"] < tol["loss"] and r["e_stat"] < tol["stat"]
+                   and r["e_grad"] < tol["grad"] and r["e_grad_uncond"] < tol["uncond"] and r["argmax_agree"] >= tol["agree"]
+                   and r["e_acc"] < 0.01 and r["e_loss_cond"] < 1e-3)
+    return r
+
+
+def case_curve(precision="bf16", N=4, C=1, H=64, W=64, K=2, steps=100, lr=1e-3, seed=33):
+    """north_star: "the loss curve tracking over the first steps": `steps` optimisation steps (Adam, BN moving stats,
+    dropout masks injected) on a fixed stream of batches, CUDA path vs oracle (fp32 torch-CPU); the curves must track
+    within a band (chaotic divergence of two non-identical float pipelines is expected to grow slowly)."""
+    from unetb200.model import UNet
+    p = O.init_params(C, K, seed=seed, base=64, dtype=torch.float32)
+    m = UNet(K, N, C, learning_rate=lr, precision=precision, seed=0)
+    m.load_oracle_params({k: v.numpy() for k, v in p.items()})
+    opt = O.KerasAdam(p, lr)
+    rng = np.random.default_rng(seed)
+    # a learnable task: label = smoothed-noise field thresholded; images carry the field plus noise
+    from scipy.ndimage import gaussian_filter
+    got, ref = [], []
+    for s in range(steps):
+        f = gaussian_filter(rng.normal(size=(N, H, W)), sigma=(0, 3, 3))
+        lab = (f > 0).astype(np.uint8)
+        x = (f[:, None] * 8 + rng.normal(size=(N, C, H, W)) * 0.5).astype(np.float32)
+        dm = {"drop4": rng.integers(0, 2, size=(N, 512, H // 8, W // 8)).astype(np.uint8),
+              "dropb": rng.integers(0, 2, size=(N, 1024, H // 16, W // 16)).astype(np.uint8)}
+        oh = np.eye(K, dtype=np.int32)[lab]
+        r = O.train_step(p, opt, torch.tensor(x), torch.tensor(oh), N, {k: torch.tensor(v) for k, v in dm.items()})
+        ref.append(float(r["loss"]))
+        got.append(float(m.train_step(torch.tensor(x), torch.tensor(lab), dropout_masks=dm).item()))
+    got, ref = np.array(got), np.array(ref)
+    dev = np.abs(got - ref) / ref
+    out = dict(loss_first=float(ref[0]), loss_last_ref=float(ref[-1]), loss_last=float(got[-1]), dev_max=float(dev.max()),
+               dev_mean=float(dev.mean()), dev_first10=float(dev[:10].max()), steps=steps)
+    out["ok"] = bool(out["dev_first10"] < 2e-2 and out["dev_mean"] < 5e-2 and out["dev_max"] < 0.25 and ref[-1] < 0.8 * ref[0]
+                     and got[-1] < 0.8 * got[0])
+    return out
 
 
 def load_gold(name):
@@ -37,98 +154,40 @@ def load_gold(name):
     return g
 
 
-def run_model(g, precision):
+def case_golden(name, precision):
+    """committed fixture (oracle fp64 outputs): loss, accuracy, softmax and BN statistics tightly; gradients (64
+    samples + L2 norm per tensor, UNconditioned) within the loose bound that activation-pattern flips allow."""
     from unetb200.model import UNet
-    C, K = int(g["C"]), int(g["K"])
+    g = load_gold(name)
+    tol = TOL[precision]
+    N, C, H, W, K = int(g["N"]), int(g["C"]), int(g["H"]), int(g["W"]), int(g["K"])
     p = O.init_params(C, K, seed=int(g["seed"]), base=64, randomize_affine=True)
     m = UNet(K, int(g["gb"]), C, learning_rate=3e-4, precision=precision, seed=0)
     m.load_oracle_params({k: v.numpy() for k, v in p.items()})
     m.train_step(torch.tensor(g["x"]), torch.tensor(g["labels"]), dropout_masks={"drop4": g["drop4"], "dropb": g["dropb"]},
-                 apply_update=False)
+                 apply_update=False, keep_softmax=True)
     torch.cuda.synchronize()
-    return m, p
-
-
-def case_golden(name, precision):
-    g = load_gold(name)
-    m, _ = run_model(g, precision)
-    tol = TOL[precision]
     met = m.metrics.cpu().numpy()
+    sm = m._b("softmax")[:N * H * W * K].view(N, H, W, K).cpu().numpy()
     grads = m.export_grads()
-    r = dict(e_loss=abs(float(met[0]) - float(g["loss"])) / abs(float(g["loss"])), acc=float(met[1]), acc_ref=float(g["acc"]))
+    r = dict(e_loss=abs(float(met[0]) - float(g["loss"])) / abs(float(g["loss"])), e_acc=abs(float(met[1]) - float(g["acc"])),
+             e_softmax=rel(sm, g["softmax"]))
     worst, worst_name = 0.0, ""
     names = [str(n) for n in g["grad_names"]]
     for i, n in enumerate(names):
         flat = grads[n].reshape(-1)
         layer = n.split("/")[0]
-        floor = float(g["grad_absmax"][names.index(layer + "/kernel")]) * 1e-3
-        e = float(np.abs(flat[g["grad_sample_idx"][i]] - g["grad_sample_val"][i]).max() / max(float(g["grad_absmax"][i]), floor))
-        l2 = abs(float(np.linalg.norm(flat)) - float(g["grad_l2"][i])) / max(float(g["grad_l2"][i]), floor)
-        e = max(e, l2)
+        scale = float(g["grad_absmax"][i])
+        if layer.startswith("up") and n.endswith("/bias"):
+            scale = float(g["grad_absmax"][names.index(layer + "/kernel")])
+        e = float(np.abs(flat[g["grad_sample_idx"][i]] - g["grad_sample_val"][i]).max() / scale)
         if e > worst:
             worst, worst_name = e, n
-    r["e_grad_worst"] = worst
-    r["worst_grad"] = worst_name
+    r["e_grad_uncond"], r["worst_grad"] = worst, worst_name
     stats = m.export_params()
-    es = 0.0
-    for k in g:
-        if k.startswith("stat:"):
-            es = max(es, rel(stats[k[5:]], g[k]))
-    r["e_stat"] = es
-    # softmax through the public model call in training mode is covered by case_live; here compare loss/acc/grads
-    r["ok"] = bool(r["e_loss"] < tol["loss"] and worst < tol["grad"] and es < tol["stat"] and abs(r["acc"] - r["acc_ref"]) < 0.02)
-    return r
-
-
-def case_live(precision, N=2, C=1, H=48, W=32, K=2, seed=21, steps=2):
-    """oracle run live: softmax, loss, every gradient, then `steps` full optimisation steps (Adam + moving stats)"""
-    from unetb200.model import UNet
-    tol = TOL[precision]
-    p = O.init_params(C, K, seed=seed, base=64, randomize_affine=True)
-    rng = np.random.default_rng(seed)
-    m = UNet(K, N, C, learning_rate=1e-3, precision=precision, seed=0)
-    m.load_oracle_params({k: v.numpy() for k, v in p.items()})
-    opt = O.KerasAdam(p, 1e-3)
-    r = {}
-    for s in range(steps):
-        x = rng.normal(size=(N, C, H, W)).astype(np.float32)
-        lab = rng.integers(0, K, size=(N, H, W)).astype(np.uint8)
-        oh = np.eye(K, dtype=np.int32)[lab]
-        dm = {"drop4": rng.integers(0, 2, size=(N, 512, H // 8, W // 8)).astype(np.uint8),
-              "dropb": rng.integers(0, 2, size=(N, 1024, H // 16, W // 16)).astype(np.uint8)}
-        if s == 0:
-            sm = m.forward_softmax(torch.tensor(x), training=True, dropout_masks=dm).cpu().numpy()
-            # undo the moving-stat update of this extra forward so both sides see the same number of updates
-            m.load_oracle_params({k: v.numpy() for k, v in p.items()})
-        ref = O.train_step(p, opt, torch.tensor(x, dtype=torch.float64), torch.tensor(oh), N, {k: torch.tensor(v) for k, v in dm.items()})
-        m.train_step(torch.tensor(x), torch.tensor(oh), dropout_masks=dm)      # one-hot label contract
-        torch.cuda.synchronize()
-        met = m.metrics.cpu().numpy()
-        if s == 0:
-            r["e_softmax"] = rel(sm, ref["softmax"].numpy())
-            r["argmax_agree"] = float((sm.argmax(-1) == ref["softmax"].numpy().argmax(-1)).mean())
-            grads = m.export_grads()
-            worst, wn = 0.0, ""
-            for n, gref in ref["grads"].items():
-                layer = n.split("/")[0]
-                floor = float(ref["grads"][layer + "/kernel"].abs().max()) * 1e-3
-                e = rel(grads[n], gref.numpy(), floor)
-                if e > worst:
-                    worst, wn = e, n
-            r["e_grad_worst"], r["worst_grad"] = worst, wn
-        r[f"e_loss{s}"] = abs(float(met[0]) - float(ref["loss"])) / abs(float(ref["loss"]))
-    got = m.export_params()
-    ew, es = 0.0, 0.0
-    for k, v in p.items():
-        e = rel(got[k], v.numpy())
-        if "moving" in k:
-            es = max(es, e)
-        else:
-            ew = max(ew, e)
-    r["e_params_after"] = ew
-    r["e_moving_after"] = es
-    r["ok"] = bool(r["e_softmax"] < tol["softmax"] and r["e_grad_worst"] < tol["grad"] and all(r[f"e_loss{s}"] < tol["loss"] for s in range(steps))
-                   and es < tol["stat"] and ew < (2e-2 if precision == "bf16" else 1e-3) and r["argmax_agree"] > 0.999 - (0.02 if precision == "bf16" else 0))
+    r["e_stat"] = max(rel(stats[k[5:]], g[k]) for k in g if k.startswith("stat:"))
+    r["ok"] = bool(r["e_loss"] < tol["loss"] and r["e_softmax"] < tol["softmax"] and r["e_stat"] < tol["stat"] and r["e_acc"] < 0.01
+                   and worst < tol["uncond"])
     return r
 
 
@@ -158,12 +217,15 @@ def case_inference(precision):
 
 
 CASES = {
+    "live_fp32_c1k2": lambda: case_live("fp32", N=2, C=1, H=64, W=48, K=2, seed=21),
+    "live_fp32_c3k8": lambda: case_live("fp32", N=1, C=3, H=80, W=112, K=8, seed=22, gb=4),
+    "live_bf16_c1k2": lambda: case_live("bf16", N=2, C=1, H=128, W=96, K=2, seed=23),
+    "live_bf16_c3k8": lambda: case_live("bf16", N=1, C=3, H=144, W=176, K=8, seed=24, gb=8),
     "golden_c1_k2_fp32": lambda: case_golden("graph_c1_k2", "fp32"),
     "golden_c3_k8_fp32": lambda: case_golden("graph_c3_k8", "fp32"),
     "golden_c1_k2_bf16": lambda: case_golden("graph_c1_k2", "bf16"),
     "golden_c3_k8_bf16": lambda: case_golden("graph_c3_k8", "bf16"),
-    "live_fp32": lambda: case_live("fp32"),
-    "live_bf16": lambda: case_live("bf16"),
+    "curve_bf16": lambda: case_curve("bf16"),
     "inference_fp32": lambda: case_inference("fp32"),
     "inference_bf16": lambda: case_inference("bf16"),
 }
