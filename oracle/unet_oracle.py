@@ -94,8 +94,28 @@ def trainable_names(params):
     return [k for k in params if k.endswith(TRAINABLE_SUFFIXES)]
 
 
-def _bn(x, name, params, training, new_stats):
-    """BatchNormalization(axis=1), App. A.3: biased batch var to normalise, unbiased into the moving avg."""
+class _StorageRound(torch.autograd.Function):
+    """bf16-storage emulation (tests only): round the value where the CUDA path stores an activation in bf16 (forward)
+    and/or where it stores that activation's gradient in bf16 (backward).  Arithmetic stays in the oracle's dtype."""
+
+    @staticmethod
+    def forward(ctx, x, fwd, bwd):
+        ctx.bwd = bwd
+        return x.float().to(torch.bfloat16).to(x.dtype) if fwd else x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.float().to(torch.bfloat16).to(g.dtype) if ctx.bwd else g), None, None
+
+
+def _q(t, storage, fwd=True, bwd=True):
+    return t if storage is None else _StorageRound.apply(t, fwd, bwd)
+
+
+def _bn(x, name, params, training, new_stats, x_used=None):
+    """BatchNormalization(axis=1), App. A.3: biased batch var to normalise, unbiased into the moving avg.
+    x_used (bf16-storage emulation): the stored (rounded) activation that is normalised, while the statistics come
+    from the unrounded accumulator values `x` -- the data flow of the CUDA path."""
     g = params[name + "/gamma"].view(1, -1, 1, 1)
     b = params[name + "/beta"].view(1, -1, 1, 1)
     if training:
@@ -110,12 +130,17 @@ def _bn(x, name, params, training, new_stats):
     else:
         mean = params[name + "/moving_mean"]
         var = params[name + "/moving_var"]
-    return (x - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + BN_EPS) * g + b
+    xu = x if x_used is None else x_used
+    return (xu - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + BN_EPS) * g + b
 
 
-def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None):
+def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None, storage=None):
     w = params[name + "/kernel"].permute(3, 2, 0, 1)          # HWIO -> OIHW  (App. A.1)
-    z = F.conv2d(x, w, params[name + "/bias"], padding=w.shape[-1] // 2)
+    k = w.shape[-1]
+    tensor_core = storage is not None and k == 3 and w.shape[1] >= 64      # bf16 weight shadow; first layer/head stay fp32
+    if tensor_core:
+        w = _q(w, storage, True, False)
+    z = F.conv2d(x, w, params[name + "/bias"], padding=k // 2)
     if relu_masks is not None and name in relu_masks:
         # conditioned comparison (tests only): the activation pattern [z > 0] is taken from the implementation under
         # test, so that sign flips of pre-activations within rounding distance of 0 do not turn a 1e-7 forward
@@ -125,18 +150,27 @@ def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None):
         a = F.relu(z)
     if taps is not None:
         taps[name + "/act"] = a
-    y = _bn(a, name, params, training, new_stats)
+    head = (k == 1)
+    if storage is None or head:                               # the head keeps fp32 activations on the CUDA path
+        y = _bn(a, name, params, training, new_stats)
+    else:
+        y = _q(_bn(a, name, params, training, new_stats, x_used=_q(a, storage)), storage)
     if taps is not None:
         taps[name + "/out"] = y
     return y
 
 
-def _deconv_block(x, name, params, training, new_stats, taps):
+def _deconv_block(x, name, params, training, new_stats, taps, storage=None):
     w = params[name + "/kernel"].permute(3, 2, 0, 1)          # [kh,kw,Cout,Cin] -> [Cin,Cout,kh,kw] (App. A.2)
+    if storage is not None:
+        w = _q(w, storage, True, False)
     z = F.conv_transpose2d(x, w, params[name + "/bias"], stride=2)
     if taps is not None:
         taps[name + "/act"] = z
-    y = _bn(z, name, params, training, new_stats)
+    if storage is None:
+        y = _bn(z, name, params, training, new_stats)
+    else:
+        y = _q(_bn(z, name, params, training, new_stats, x_used=_q(z, storage)), storage)
     if taps is not None:
         taps[name + "/out"] = y
     return y
@@ -161,31 +195,42 @@ def _pool(x, idx=None):
     return torch.gather(win, -1, idx.long().unsqueeze(-1)).squeeze(-1)
 
 
-def forward(params, x, training, dropout_masks=None, new_stats=None, taps=None, relu_masks=None, pool_idx=None):
+def forward(params, x, training, dropout_masks=None, new_stats=None, taps=None, relu_masks=None, pool_idx=None, storage=None):
     """UNet/model.py:85-146.  x: [N,C,H,W].  Returns (softmax NHWC [N,H,W,K], logits NHWC).
 
     `logits` is what the Softmax layer consumes: the BN output of the ReLU'd 1x1 conv.
     dropout_masks: {'drop4': [N,8b,H/8,W/8], 'dropb': [N,16b,H/16,W/16]} of {0,1}; None => no dropout.
+    Test-only knobs: relu_masks / pool_idx (activation pattern of the implementation under test, see _conv_block /
+    _pool) and storage="bf16" (round activations, their gradients and the tensor-core weights where the CUDA path
+    stores bf16: gives the noise floor any bf16-storage implementation of this graph has against fp64).
     """
     dm = dropout_masks or {}
     pool_idx = pool_idx or {}
-    c1 = _conv_block(_conv_block(x, "enc1a", params, training, new_stats, taps, relu_masks), "enc1b", params, training, new_stats, taps, relu_masks)
-    p1 = _pool(c1, pool_idx.get("pool1"))
-    c2 = _conv_block(_conv_block(p1, "enc2a", params, training, new_stats, taps, relu_masks), "enc2b", params, training, new_stats, taps, relu_masks)
-    p2 = _pool(c2, pool_idx.get("pool2"))
-    c3 = _conv_block(_conv_block(p2, "enc3a", params, training, new_stats, taps, relu_masks), "enc3b", params, training, new_stats, taps, relu_masks)
-    p3 = _pool(c3, pool_idx.get("pool3"))
-    c4 = _conv_block(_conv_block(p3, "enc4a", params, training, new_stats, taps, relu_masks), "enc4b", params, training, new_stats, taps, relu_masks)
+    st = storage
+
+    def cb(t, name):
+        return _conv_block(t, name, params, training, new_stats, taps, relu_masks, st)
+
+    def fan(t):      # a tensor with two consumers: each branch's gradient is stored (rounded) before the sum
+        return _q(t, st, False, True)
+
+    c1 = cb(cb(x, "enc1a"), "enc1b")
+    p1 = _pool(fan(c1), pool_idx.get("pool1"))
+    c2 = cb(cb(p1, "enc2a"), "enc2b")
+    p2 = _pool(fan(c2), pool_idx.get("pool2"))
+    c3 = cb(cb(p2, "enc3a"), "enc3b")
+    p3 = _pool(fan(c3), pool_idx.get("pool3"))
+    c4 = cb(cb(p3, "enc4a"), "enc4b")
     c4 = _dropout(c4, dm.get("drop4"), training)                 # skip-4 carries the dropped tensor (Q2)
-    p4 = _pool(c4, pool_idx.get("pool4"))
-    bt = _conv_block(_conv_block(p4, "bota", params, training, new_stats, taps, relu_masks), "botb", params, training, new_stats, taps, relu_masks)
+    p4 = _pool(fan(c4), pool_idx.get("pool4"))
+    bt = cb(cb(p4, "bota"), "botb")
     bt = _dropout(bt, dm.get("dropb"), training)
     d = bt
     for lvl, skip in ((4, c4), (3, c3), (2, c2), (1, c1)):
-        u = _deconv_block(d, f"up{lvl}", params, training, new_stats, taps)
-        cat = torch.cat([skip, u], dim=1)                         # [skip, up]  UNet/model.py:117
-        d = _conv_block(_conv_block(cat, f"dec{lvl}a", params, training, new_stats, taps, relu_masks), f"dec{lvl}b", params, training, new_stats, taps, relu_masks)
-    logits = _conv_block(d, "head", params, training, new_stats, taps, relu_masks)   # 1x1 + ReLU + BN (Q1)
+        u = _deconv_block(d, f"up{lvl}", params, training, new_stats, taps, st)
+        cat = torch.cat([fan(skip), u], dim=1)                    # [skip, up]  UNet/model.py:117
+        d = cb(cb(cat, f"dec{lvl}a"), f"dec{lvl}b")
+    logits = cb(d, "head")                                        # 1x1 + ReLU + BN (Q1)
     logits = logits.permute(0, 2, 3, 1)
     return torch.softmax(logits, dim=-1), logits
 
@@ -200,7 +245,7 @@ def loss_and_accuracy(logits_nhwc, labels_onehot, global_batch_size):
 
 
 def train_step_grads(params, x, labels_onehot, global_batch_size, dropout_masks=None, taps=None, relu_masks=None,
-                     pool_idx=None):
+                     pool_idx=None, storage=None):
     """fwd(training=True) + loss + grads of every trainable tensor (UNet/model.py:204-221).
 
     Returns dict(loss, acc, softmax, logits, grads{name: tensor}, new_stats{...}).
@@ -210,7 +255,7 @@ def train_step_grads(params, x, labels_onehot, global_batch_size, dropout_masks=
     for k, v in params.items():
         leaves[k] = v.detach().clone().requires_grad_(k in names)
     new_stats = {}
-    sm, logits = forward(leaves, x, True, dropout_masks, new_stats, taps, relu_masks, pool_idx)
+    sm, logits = forward(leaves, x, True, dropout_masks, new_stats, taps, relu_masks, pool_idx, storage)
     loss, acc = loss_and_accuracy(logits, labels_onehot, global_batch_size)
     tap_keys = list(taps.keys()) if taps is not None else []
     grads = torch.autograd.grad(loss, [leaves[k] for k in names] + [taps[k] for k in tap_keys])

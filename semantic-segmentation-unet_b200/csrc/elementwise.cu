@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(TPB) bn_stats_kernel(const T* __restrict__ a, 
 
 // Row-parallel column sums: a block owns 32 columns; thread (lane = column, ry = row lane) sums rows ry, ry+8, ... in
 // fp64, the 8 row lanes are combined through shared memory in a fixed order (deterministic).
-constexpr int RED_ROWLANES = 8;
+constexpr int RED_ROWLANES = 32;
 __device__ __forceinline__ double block_rows_sum(double v, double (*sh)[32]) {
   const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
   __syncthreads();
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(32 * RED_ROWLANES) bn_finalize_kernel(const fl
   const int c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
   if (c < C)
+#pragma unroll 4
     for (int r = ry; r < rows; r += RED_ROWLANES)
       for (int g = 0; g < groups; ++g) {
         s += (double)partial[((size_t)r * 2 + 0) * ncols + g * C + c];
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(32 * RED_ROWLANES) reduce_rows_kernel(const fl
   const int c = blockIdx.x * 32 + lane;
   double s = 0.0;
   if (c < ncols)
+#pragma unroll 4
     for (int r = ry; r < rows; r += RED_ROWLANES) s += (double)partial[(size_t)r * row_stride + c];
   s = block_rows_sum(s, sh);
   if (ry == 0 && c < ncols) out[c] = (float)(s * (double)scale);
