@@ -14,6 +14,8 @@
 // from TMA out-of-bounds zero fill / store clipping.  K is walked in 64-channel blocks (one 128-byte swizzle row).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -354,6 +356,20 @@ int strided_map(CUtensorMap* m, const void* base, int C, int w, int h, int N, in
 
 }  // namespace
 
+// halo-patch kernels (igemm_conv3.cu)
+int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* post_scale,
+                      const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream);
+int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
+                        cudaStream_t stream);
+static bool legacy_conv3() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UB_CONV3_LEGACY");      // A/B switch for tools/bench_layers.py: one TMA box per filter tap
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 extern "C" {
 
 int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, void* out,
@@ -362,6 +378,7 @@ int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w
   UB_CHECK_SHAPE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0 && Cout % 64 == 0 && (C1 == 0 || x1),
                  "conv3x3_fwd: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
   UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0, "conv3x3_fwd: bad N/H/W");
+  if (!legacy_conv3()) return ub_conv3_halo_fwd(x0, C0, x1, C1, w, bias, nullptr, nullptr, out, stats, N, H, W, Cout, relu, stream);
   IgemmFwdParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -394,6 +411,7 @@ int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C
   UB_CHECK_ARG(dz && w_t && dx0, "conv3x3_dgrad: null pointer");
   UB_CHECK_SHAPE(Cout % 64 == 0 && C0 % 64 == 0 && C0 > 0 && (C1 == 0 || (C1 == C0 && dx1)),
                  "conv3x3_dgrad: channels must be multiples of 64 and split halves equal (Cout=%d C0=%d C1=%d)", Cout, C0, C1);
+  if (!legacy_conv3()) return ub_conv3_halo_dgrad(dz, Cout, w_t, dx0, C0, dx1, C1, N, H, W, stream);
   IgemmFwdParams p;
   memset(&p, 0, sizeof(p));
   int rc;

@@ -122,7 +122,8 @@ class UNet:
         soff = 0
         for name in reversed(list(self.layers)):       # head first: bucket order == backward order
             L = self.layers[name]
-            L.seg_begin = off
+            off = (off + 127) // 128 * 128      # kernel segments start 256-byte (bf16) / 512-byte (fp32) aligned: TMA rows of the
+            L.seg_begin = off                   # weight matrix then never straddle 128-byte lines
             L.off_w = off
             off += _pad8(L.n_w)
             L.off_b = off
