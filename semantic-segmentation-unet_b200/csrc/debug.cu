@@ -85,13 +85,13 @@ __global__ void __launch_bounds__(128, 1) desc_probe_kernel(const __grid_constan
 
 // Issue-rate probe: one CTA per SM issues `iters` x 4 MMAs (M = 128, K = 16 each) on operands that stay resident in shared
 // memory (contents irrelevant) and reports elapsed SM clocks: the tensor-pipe + smem-read ceiling per tile shape.
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int mn_major, long long* clocks) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int mn_major, int a_shift, int a_sbo, long long* clocks) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < (49152 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
@@ -106,14 +106,14 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int 
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) {
-    const uint32_t sa = smem_u32(smem), sb = sa + 16384;
+    const uint32_t sa = smem_u32(smem) + a_shift * 128, sb = smem_u32(smem) + 49152;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)mn_major << 15) | ((uint32_t)mn_major << 16) |
                            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint64_t ad = mn_major ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa, 16, 1024) + 2 * k;
+        const uint64_t ad = mn_major ? make_smem_desc(sa + k * 2048, 8192, a_sbo) : make_smem_desc(sa, 16, a_sbo) + 2 * k;
         const uint64_t bd = mn_major ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb, 16, 1024) + 2 * k;
         tc_mma_bf16(tmem_base, ad, bd, idesc, 1);
       }
@@ -133,15 +133,15 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int 
 
 }  // namespace
 
-extern "C" int ub_debug_mma_rate(int N, int iters, int mn_major, int nblocks, long long* clocks, cudaStream_t stream) {
+extern "C" int ub_debug_mma_rate(int N, int iters, int mn_major, int a_shift, int a_sbo, int nblocks, long long* clocks, cudaStream_t stream) {
   UB_CHECK_ARG(clocks && N >= 16 && N <= 256 && N % 16 == 0 && iters > 0 && nblocks > 0, "mma_rate: bad args");
-  const int smem = 16384 + 32768 + 1024;
+  const int smem = 49152 + 32768 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     UB_CUDA(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
-  mma_rate_kernel<<<nblocks, 128, smem, stream>>>(N, iters, mn_major, clocks);
+  mma_rate_kernel<<<nblocks, 128, smem, stream>>>(N, iters, mn_major, a_shift, a_sbo, clocks);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -124,76 +124,73 @@ __global__ void __launch_bounds__(192, 1) conv3_kernel(const __grid_constant__ C
   const bool resident = p.b_resident != 0;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int a_stage = 0, b_slot = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      bool first = true;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
-        const int img = m_tile / tiles_per_img;
-        const int rem = m_tile - img * tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * TH;
-        const int w0 = (rem % p.tiles_w) * TW;
-        int cbg = 0;
-        for (int src = 0; src < p.nsrc; ++src) {
-          for (int cb = 0; cb < p.cblk[src]; ++cb, ++cbg) {
-            mbar_wait(&aempty[a_stage], a_phase ^ 1);
-            mbar_expect_tx(&afull[a_stage], PATCH_BYTES);
-            tma_load_4d(smem + a_stage * PATCH_STRIDE, &p.a_map[src], &afull[a_stage], cb * 64, w0 - 1, h0 - 1, img);
-            if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
-            if (resident && !first) continue;
-            for (int tap = 0; tap < 9; ++tap) {
-              const int slot = resident ? cbg * 9 + tap : b_slot;
-              if (!resident) mbar_wait(&bempty[slot], b_phase ^ 1);
-              mbar_expect_tx(&bfull[slot], L::B_BYTES);
-              tma_load_2d(smem + L::OFF_B + slot * L::B_BYTES, &p.b_map, &bfull[slot], (tap * p.cblk_total + cbg) * 64, n_tile * BLOCK_N);
-              if (!resident && ++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
-            }
+    // ================= TMA producer (all lanes run the loop, one elected lane issues) =================
+    int a_stage = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * TH;
+      const int w0 = (rem % p.tiles_w) * TW;
+      int cbg = 0;
+      for (int src = 0; src < p.nsrc; ++src) {
+        for (int cb = 0; cb < p.cblk[src]; ++cb, ++cbg) {
+          mbar_wait(&aempty[a_stage], a_phase ^ 1);
+          mbar_expect_tx_e(&afull[a_stage], PATCH_BYTES);
+          tma_load_4d_e(smem + a_stage * PATCH_STRIDE, &p.a_map[src], &afull[a_stage], cb * 64, w0 - 1, h0 - 1, img);
+          if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
+          if (resident && !first) continue;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int slot = resident ? cbg * 9 + tap : b_slot;
+            if (!resident) mbar_wait(&bempty[slot], b_phase ^ 1);
+            mbar_expect_tx_e(&bfull[slot], L::B_BYTES);
+            tma_load_2d_e(smem + L::OFF_B + slot * L::B_BYTES, &p.b_map, &bfull[slot], (tap * p.cblk_total + cbg) * 64, n_tile * BLOCK_N);
+            if (!resident && ++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
           }
         }
-        first = false;
       }
+      first = false;
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
-      int a_stage = 0, b_slot = 0;
-      uint32_t a_phase = 0, b_phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int cbg = 0; cbg < p.cblk_total; ++cbg) {
-          mbar_wait(&afull[a_stage], a_phase);
-          tc_fence_after();
-          const uint32_t patch = smem_u32(smem + a_stage * PATCH_STRIDE);
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int slot = resident ? cbg * 9 + tap : b_slot;
-            mbar_wait(&bfull[slot], resident ? 0u : b_phase);
-            tc_fence_after();
-            const int dh = tap / 3, dw = tap - dh * 3;       // already offset by +1 (patch origin is pixel (-1, -1))
-            const uint64_t adesc = make_smem_desc(patch + (dh * PW + dw) * 128, 16, PW * 128);
-            const uint64_t bdesc = make_smem_desc(smem_u32(smem + L::OFF_B + slot * L::B_BYTES), 16, 1024);
+    // ================= MMA issuer (all lanes run the loop, one elected lane issues) =================
+    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    const uint32_t tmem_u = warp_uniform(tmem_base);
+    const uint32_t smem_base_u = warp_uniform(smem_u32(smem));
+    int a_stage = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + as * BLOCK_N;
+      for (int cbg = 0; cbg < p.cblk_total; ++cbg) {
+        mbar_wait(&afull[a_stage], a_phase);
+        const uint32_t patch = smem_base_u + a_stage * PATCH_STRIDE;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cbg | tap | k) != 0);
-            if (!resident) {
-              tc_commit(&bempty[slot]);
-              if (++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
-            }
+        for (int tap = 0; tap < 9; ++tap) {
+          const int slot = resident ? cbg * 9 + tap : b_slot;
+          mbar_wait(&bfull[slot], resident ? 0u : b_phase);
+          tc_fence_after();
+          const int dh = tap / 3, dw = tap % 3;           // already offset by +1 (patch origin is pixel (-1, -1))
+          const uint64_t adesc = make_smem_desc(patch + (dh * PW + dw) * 128, 16, PW * 128);
+          const uint64_t bdesc = make_smem_desc(smem_base_u + L::OFF_B + slot * L::B_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16_e(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cbg | tap | k) != 0);
+          if (!resident) {
+            tc_commit_e(&bempty[slot]);
+            if (++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
           }
-          tc_commit(&aempty[a_stage]);
-          if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
         }
-        tc_commit(&tfull[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        tc_commit_e(&aempty[a_stage]);
+        if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
       }
+      tc_commit_e(&tfull[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
     __syncwarp();
   } else {

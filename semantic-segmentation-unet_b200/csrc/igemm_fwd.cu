@@ -118,62 +118,60 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int img = m_tile / tiles_per_img;
-        const int rem = m_tile - img * tiles_per_img;
-        const int h0 = (rem / p.tiles_w) * TILE_H;
-        const int w0 = (rem % p.tiles_w) * TILE_W;
-        int kb = 0;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-          for (int src = 0; src < p.nsrc; ++src) {
-            for (int cb = 0; cb < p.cblk[src]; ++cb, ++kb) {
-              mbar_wait(&empty[stage], phase ^ 1);
-              uint8_t* sa = smem + stage * L::STAGE_BYTES;
-              mbar_expect_tx(&full[stage], L::STAGE_BYTES);
-              tma_load_4d(sa, &p.a_map[src], &full[stage], cb * 64, w0 + dw, h0 + dh, img);
-              tma_load_2d(sa + A_BYTES, &p.b_map, &full[stage], kb * 64, n_tile * BLOCK_N);
-              if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            }
+    // ================= TMA producer (all lanes run the loop, one elected lane issues) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * TILE_H;
+      const int w0 = (rem % p.tiles_w) * TILE_W;
+      int kb = 0;
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+        for (int src = 0; src < p.nsrc; ++src) {
+          for (int cb = 0; cb < p.cblk[src]; ++cb, ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            mbar_expect_tx_e(&full[stage], L::STAGE_BYTES);
+            tma_load_4d_e(sa, &p.a_map[src], &full[stage], cb * 64, w0 + dw, h0 + dh, img);
+            tma_load_2d_e(sa + A_BYTES, &p.b_map, &full[stage], kb * 64, n_tile * BLOCK_N);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
+    // ================= MMA issuer (all lanes run the loop, one elected lane issues) =================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+    const uint32_t tmem_u = warp_uniform(tmem_base);
+    const uint32_t smem_base_u = warp_uniform(smem_u32(smem));
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + as * BLOCK_N;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
-          const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, 1024);
+        const uint32_t sa = smem_base_u + stage * L::STAGE_BYTES;
+        const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+        const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 bytes) per 64-channel block
-            tc_mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          tc_commit(&empty[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit(&tfull[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 bytes) per 64-channel block
+          tc_mma_bf16_e(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        tc_commit_e(&empty[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      tc_commit_e(&tfull[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
     __syncwarp();
   } else {

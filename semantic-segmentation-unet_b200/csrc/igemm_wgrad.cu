@@ -100,58 +100,57 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // M side: two 64-row blocks (the second clamps to the last valid block when the block count is odd)
-      int amap[2], ac0[2], adh[2], adw[2];
-      for (int i = 0; i < 2; ++i) {
-        int blk = m_tile * 2 + i;
-        if (blk >= p.a.nblocks) blk = p.a.nblocks - 1;
-        decode_block(p.a, blk, amap[i], ac0[i], adh[i], adw[i]);
-      }
-      int bmap[BLOCK_N / 64], bc0[BLOCK_N / 64], bdh[BLOCK_N / 64], bdw[BLOCK_N / 64];
+    // TMA producer: all lanes run the loop, one elected lane issues (see common.cuh)
+    // M side: two 64-row blocks (the second clamps to the last valid block when the block count is odd)
+    int amap[2], ac0[2], adh[2], adw[2];
+    for (int i = 0; i < 2; ++i) {
+      int blk = m_tile * 2 + i;
+      if (blk >= p.a.nblocks) blk = p.a.nblocks - 1;
+      decode_block(p.a, blk, amap[i], ac0[i], adh[i], adw[i]);
+    }
+    int bmap[BLOCK_N / 64], bc0[BLOCK_N / 64], bdh[BLOCK_N / 64], bdw[BLOCK_N / 64];
 #pragma unroll
-      for (int j = 0; j < BLOCK_N / 64; ++j) decode_block(p.b, n_tile * (BLOCK_N / 64) + j, bmap[j], bc0[j], bdh[j], bdw[j]);
-      const int per_img = p.patches_w * p.patches_h;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int pt = p_begin; pt < p_end; ++pt) {
-        const int img = pt / per_img;
-        const int rem = pt - img * per_img;
-        const int h0 = (rem / p.patches_w) * PATCH_H;
-        const int w0 = (rem % p.patches_w) * PATCH_W;
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::STAGE_BYTES;
-        mbar_expect_tx(&full[stage], L::STAGE_BYTES);
+    for (int j = 0; j < BLOCK_N / 64; ++j) decode_block(p.b, n_tile * (BLOCK_N / 64) + j, bmap[j], bc0[j], bdh[j], bdw[j]);
+    const int per_img = p.patches_w * p.patches_h;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = p_begin; pt < p_end; ++pt) {
+      const int img = pt / per_img;
+      const int rem = pt - img * per_img;
+      const int h0 = (rem / p.patches_w) * PATCH_H;
+      const int w0 = (rem % p.patches_w) * PATCH_W;
+      mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* sa = smem + stage * L::STAGE_BYTES;
+      mbar_expect_tx_e(&full[stage], L::STAGE_BYTES);
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-          tma_load_4d(sa + i * BOX_BYTES, &p.a.map[amap[i]], &full[stage], ac0[i], w0 + adw[i], h0 + adh[i], img);
+      for (int i = 0; i < 2; ++i)
+        tma_load_4d_e(sa + i * BOX_BYTES, &p.a.map[amap[i]], &full[stage], ac0[i], w0 + adw[i], h0 + adh[i], img);
 #pragma unroll
-        for (int j = 0; j < BLOCK_N / 64; ++j)
-          tma_load_4d(sa + L::A_BYTES + j * BOX_BYTES, &p.b.map[bmap[j]], &full[stage], bc0[j], w0 + bdw[j], h0 + bdh[j], img);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
+      for (int j = 0; j < BLOCK_N / 64; ++j)
+        tma_load_4d_e(sa + L::A_BYTES + j * BOX_BYTES, &p.b.map[bmap[j]], &full[stage], bc0[j], w0 + bdw[j], h0 + bdh[j], img);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int pt = p_begin; pt < p_end; ++pt) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+    constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);  // both operands MN-major
+    const uint32_t tmem_u = warp_uniform(tmem_base);
+    const uint32_t smem_base_u = warp_uniform(smem_u32(smem));
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pt = p_begin; pt < p_end; ++pt) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      const uint32_t sa = smem_base_u + stage * L::STAGE_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels
-          const uint64_t adesc = make_smem_desc(sa + k * 2048, BOX_BYTES, 1024);
-          const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES + k * 2048, BOX_BYTES, 1024);
-          tc_mma_bf16(tmem_base, adesc, bdesc, idesc, (pt > p_begin) || (k > 0));
-        }
-        tc_commit(&empty[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels
+        const uint64_t adesc = make_smem_desc(sa + k * 2048, BOX_BYTES, 1024);
+        const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES + k * 2048, BOX_BYTES, 1024);
+        tc_mma_bf16_e(tmem_u, adesc, bdesc, idesc, (pt > p_begin) || (k > 0));
       }
-      tc_commit(tfull);
+      tc_commit_e(&empty[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
+    tc_commit_e(tfull);
     __syncwarp();
   } else {
     const int quad = warp & 3;

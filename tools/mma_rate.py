@@ -1,18 +1,19 @@
 #!/usr/bin/env python
-"""tcgen05.mma issue-rate ceiling per tile shape (operands resident in smem), see csrc/debug.cu."""
+"""tcgen05.mma issue-rate ceiling per tile shape (operands resident in smem), incl. A operands that start off the
+1024-byte swizzle atom / have a non-1024-multiple group stride (the halo-patch views), see csrc/debug.cu."""
 import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import unetb200._C as C  # noqa: E402
 dev = torch.device("cuda")
-for nblocks in (1, 148):
-    for mn in (0, 1):
-        for N in (32, 64, 128, 256):
+nblocks = 148
+for mn in (0, 1):
+    for (shift, sbo) in ((0, 1024), (1, 1024), (0, 1280), (11, 1280), (1, 2048), (17, 2048), (3, 2304)):
+        for N in (64, 128, 256):
             clk = torch.zeros(nblocks, dtype=torch.int64, device=dev)
             iters = 2000
-            C.call("ub_debug_mma_rate", N, iters, mn, nblocks, clk, torch.cuda.current_stream().cuda_stream)
+            C.call("ub_debug_mma_rate", N, iters, mn, shift, sbo, nblocks, clk, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             c = clk.float().mean().item() / (iters * 4)
-            print(json.dumps(dict(blocks=nblocks, mn_major=mn, N=N, clk_per_mma=round(c, 2), mac_per_clk=round(128 * N * 16 / c, 1),
-                                  smem_read_B_per_clk=round((128 * 32 + N * 32) / c, 1))), flush=True)
+            print(json.dumps(dict(mn_major=mn, a_shift=shift, a_sbo=sbo, N=N, clk_per_mma=round(c, 2), mac_per_clk=round(128 * N * 16 / c, 1))), flush=True)
