@@ -153,7 +153,9 @@ def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None, sto
     head = (k == 1)
     if storage is None or head:                               # the head keeps fp32 activations on the CUDA path
         y = _bn(a, name, params, training, new_stats)
-    else:
+    elif tensor_core:                                         # tcgen05 epilogue: statistics of the STORED (rounded) activations
+        y = _q(_bn(_q(a, storage), name, params, training, new_stats), storage)
+    else:                                                     # first layer: statistics from the fp32 values, stored rounded
         y = _q(_bn(a, name, params, training, new_stats, x_used=_q(a, storage)), storage)
     if taps is not None:
         taps[name + "/out"] = y
@@ -170,7 +172,7 @@ def _deconv_block(x, name, params, training, new_stats, taps, storage=None):
     if storage is None:
         y = _bn(z, name, params, training, new_stats)
     else:
-        y = _q(_bn(z, name, params, training, new_stats, x_used=_q(z, storage)), storage)
+        y = _q(_bn(_q(z, storage), name, params, training, new_stats), storage)
     if taps is not None:
         taps[name + "/out"] = y
     return y

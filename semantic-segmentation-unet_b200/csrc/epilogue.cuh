@@ -1,0 +1,180 @@
+// Shared epilogue of the implicit-GEMM kernels (sm_100a): 8 warps (two per TMEM lane quadrant, each taking half of the
+// tile's columns) drain a 128 x BLOCK_N fp32 accumulator stage:
+//   acc + bias -> ReLU -> optional folded inference BatchNorm -> bf16 -> SWIZZLE_128B staging tile -> TMA store,
+// and, for training, the per-channel sum / sum-of-squares of the STORED (bf16-rounded) activations for the BatchNorm
+// that follows (UNet/model.py:36, :47).  The statistics are column sums of the staging tile, read back with a
+// column-pair-per-thread mapping (conflict-free 4-byte reads, 4 accumulators per thread for the whole kernel) -- the
+// first version reduced the fp32 accumulators across lanes with a 31-shuffle butterfly per 32 columns, which made the
+// 64/128-column tiles epilogue-bound (profiles/r01_*).
+#pragma once
+#include "common.cuh"
+
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int EPI_OUT_BLK = 128 * 128;   // 128 pixels x 64 bf16
+
+struct EpiParams {
+  const float* bias;         // nullable, indexed (column % bias_mod)
+  int bias_mod;
+  const float* post_scale;   // nullable, same indexing: y = act(acc + bias) * post_scale + post_shift
+  const float* post_shift;
+  int relu;
+  float* stats;              // [UB_STATS_ROWS][2][ncols] or null
+  int ncols;
+  int H, W;                  // pixel space of the tile grid (for masking ragged tiles out of the statistics)
+};
+
+template <int BLOCK_N, int OUT_BUFS>
+struct EpiSmem {
+  static constexpr int OUT_BYTES = (BLOCK_N / 64) * EPI_OUT_BLK;
+  static constexpr int OFF_STAT = 0;                                  // float[row groups <= 8][2][BLOCK_N]: aliases staging buffer 0,
+                                                                      // only touched in finish() after every TMA store has drained
+  static constexpr int OFF_VEC = OUT_BUFS * OUT_BYTES;                // bias, scale, shift: float[3][BLOCK_N]
+  static constexpr int TOTAL = OFF_VEC + 3 * BLOCK_N * 4;
+  static_assert(8 * 2 * BLOCK_N * 4 <= OUT_BYTES, "statistics scratch must fit the staging buffer");
+};
+
+// TILE_W_: pixels per tile row (tile row r of accumulator row m: m / TILE_W_, column m % TILE_W_)
+template <int BLOCK_N, int OUT_BUFS, int TILE_W_>
+struct Epilogue {
+  using S = EpiSmem<BLOCK_N, OUT_BUFS>;
+  static constexpr int COLS_PER_THREAD = BLOCK_N / 2;          // this warp's half of the columns
+  static constexpr int NCHUNK = COLS_PER_THREAD / 32;
+  static constexpr int PAIRS = BLOCK_N / 2;                    // column pairs
+  static constexpr int ROW_GROUPS = EPI_THREADS / PAIRS;       // 8 / 4 / 2 for BLOCK_N 64 / 128 / 256
+  static constexpr int ROWS_PER_GROUP = 128 / ROW_GROUPS;
+
+  uint8_t* base;             // epilogue smem region (1024-aligned)
+  const EpiParams& ep;
+  uint32_t tmem_base;
+  uint64_t *tfull, *tempty;
+  int et, quad, lane, half, row;
+  int as = 0, buf = 0;
+  uint32_t aphase = 0;
+  bool post;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+
+  // epi_thread: 0 .. EPI_THREADS-1; hw_warp: warp index within the CTA (a warp may only touch TMEM lanes 32 * (hw_warp % 4) .. +31)
+  __device__ __forceinline__ Epilogue(uint8_t* smem_region, const EpiParams& e, uint32_t tmem, uint64_t* tf, uint64_t* te, int epi_thread,
+                                      int hw_warp)
+      : base(smem_region), ep(e), tmem_base(tmem), tfull(tf), tempty(te), et(epi_thread) {
+    lane = et & 31;
+    quad = hw_warp & 3;
+    half = (et >> 5) >> 2;     // the two warps sharing a quadrant split the columns
+    row = quad * 32 + lane;
+    post = ep.post_scale != nullptr;
+  }
+
+  __device__ __forceinline__ float* vec() const { return reinterpret_cast<float*>(base + S::OFF_VEC); }
+
+  // column-dependent vectors of this CTA's n_tile (call once, or when n_tile changes); ends with a barrier
+  __device__ __forceinline__ void load_vectors(int n_tile) {
+    float* v = vec();
+    for (int c = et; c < BLOCK_N; c += EPI_THREADS) {
+      const int col = (n_tile * BLOCK_N + c) % ep.bias_mod;
+      v[c] = ep.bias ? ep.bias[col] : 0.f;
+      v[BLOCK_N + c] = post ? ep.post_scale[col] : 1.f;
+      v[2 * BLOCK_N + c] = post ? ep.post_shift[col] : 0.f;
+    }
+    named_bar_sync(1, EPI_THREADS);
+  }
+
+  // store_fn(staging_block_ptr, block_index_within_tile) issues the TMA store(s) of one 64-column block (one thread calls it)
+  template <typename StoreFn>
+  __device__ __forceinline__ void tile(int h0, int w0, StoreFn&& store_fn) {
+    uint8_t* out_stage = base + buf * S::OUT_BYTES;
+    // the staging buffer we are about to overwrite must have been read by its TMA store (OUT_BUFS - 1 stores may be in flight)
+    if (et == 0) {
+      if (OUT_BUFS == 1) tma_store_wait_read0();
+      else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+    named_bar_sync(1, EPI_THREADS);      // also orders the previous tile's column-sum reads before these writes
+
+    mbar_wait(&tfull[as], aphase);
+    tc_fence_after();
+    const float* v = vec();
+    const uint32_t row_smem = smem_u32(out_stage) + row * 128;
+    const int rsw = row & 7;
+#pragma unroll
+    for (int ch = 0; ch < NCHUNK; ++ch) {
+      const int chunk = half * NCHUNK + ch;               // 32-column chunk index within the tile
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 32, r);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(r[j]) + v[chunk * 32 + j];
+        f[j] = ep.relu ? fmaxf(x, 0.f) : x;
+      }
+      if (post) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], v[BLOCK_N + chunk * 32 + j], v[2 * BLOCK_N + chunk * 32 + j]);
+      }
+      const uint32_t blk = row_smem + (chunk >> 1) * EPI_OUT_BLK;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c16 = (chunk & 1) * 4 + q;
+        st_shared_v4(blk + ((c16 ^ rsw) << 4), pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
+                     pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
+      }
+    }
+    // accumulator stage drained -> the MMA warp may reuse it
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[as]);
+    fence_proxy_async_smem();
+    named_bar_sync(1, EPI_THREADS);
+    if (et == 0) {
+#pragma unroll
+      for (int b = 0; b < BLOCK_N / 64; ++b) store_fn(out_stage + b * EPI_OUT_BLK, b);
+      tma_store_commit();
+    }
+    if (ep.stats) {
+      // column sums of the staged (rounded) tile: thread = (column pair, row group)
+      const int pair = et % PAIRS, grp = et / PAIRS;
+      const int c = 2 * pair;
+      const uint32_t colbase = smem_u32(out_stage) + (c >> 6) * EPI_OUT_BLK + ((c & 7) << 1);
+      const int c16 = (c & 63) >> 3;
+      const int r_begin = grp * ROWS_PER_GROUP;
+#pragma unroll 8
+      for (int rr = 0; rr < ROWS_PER_GROUP; ++rr) {
+        const int r_ = r_begin + rr;
+        if ((h0 + r_ / TILE_W_ < ep.H) && (w0 + r_ % TILE_W_ < ep.W)) {   // warp-uniform
+          uint32_t u;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(colbase + r_ * 128 + ((c16 ^ (r_ & 7)) << 4)));
+          const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
+          s0 += a;
+          s1 += b;
+          q0 = fmaf(a, a, q0);
+          q1 = fmaf(b, b, q1);
+        }
+      }
+    }
+    as ^= 1;
+    if (as == 0) aphase ^= 1;
+    if (OUT_BUFS > 1) buf = (buf + 1 == OUT_BUFS) ? 0 : buf + 1;
+  }
+
+  // after the last tile: drain stores, write this CTA's partial statistics row
+  __device__ __forceinline__ void finish(int n_tile, int stats_row) {
+    if (et == 0) tma_store_wait_all0();
+    if (ep.stats) {
+      float* st = reinterpret_cast<float*>(base + S::OFF_STAT);     // [ROW_GROUPS][2][BLOCK_N]
+      const int pair = et % PAIRS, grp = et / PAIRS;
+      named_bar_sync(1, EPI_THREADS);
+      st[(grp * 2 + 0) * BLOCK_N + 2 * pair] = s0;
+      st[(grp * 2 + 0) * BLOCK_N + 2 * pair + 1] = s1;
+      st[(grp * 2 + 1) * BLOCK_N + 2 * pair] = q0;
+      st[(grp * 2 + 1) * BLOCK_N + 2 * pair + 1] = q1;
+      named_bar_sync(1, EPI_THREADS);
+      for (int i = et; i < 2 * BLOCK_N; i += EPI_THREADS) {
+        const int which = i / BLOCK_N, c = i % BLOCK_N;
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < ROW_GROUPS; ++g) t += st[(g * 2 + which) * BLOCK_N + c];
+        ep.stats[((size_t)stats_row * 2 + which) * ep.ncols + n_tile * BLOCK_N + c] = t;
+      }
+    }
+  }
+};

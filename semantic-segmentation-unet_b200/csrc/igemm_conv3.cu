@@ -13,9 +13,10 @@
 //
 // Weights stream through a ring of per-(tap, channel-block) tiles; when the whole [BLOCK_N x 9 Cin] slice fits the
 // ring (the 64-channel level-1 layers) it is loaded once per CTA and stays resident.
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue (bias, ReLU, optional
-// folded inference BatchNorm, bf16 store through TMA, per-channel sum / sum-of-squares partials for training BN).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 = epilogue (epilogue.cuh: bias, ReLU,
+// optional folded inference BatchNorm, bf16 store through TMA, per-channel sum / sum-of-squares partials for training BN).
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace {
 
@@ -23,7 +24,6 @@ constexpr int TW = 8, TH = 16;
 constexpr int PW = TW + 2, PH = TH + 2;
 constexpr int PATCH_BYTES = PW * PH * 128;   // 23040
 constexpr int PATCH_STRIDE = 23 * 1024;      // ring pitch (1024-aligned)
-constexpr int OUT_BLK = 128 * 128;           // 128 pixels x 64 bf16
 
 struct Conv3Params {
   CUtensorMap a_map[2];
@@ -36,51 +36,28 @@ struct Conv3Params {
   int tiles_w, tiles_h;
   int n_tiles, total_tiles;
   int blocks_per_omap;
-  const float* bias;         // nullable
-  const float* post_scale;   // nullable: y = act(acc + bias) * post_scale + post_shift (inference BatchNorm folded)
-  const float* post_shift;
-  int relu;
-  float* stats;              // [UB_STATS_ROWS][2][ncols] or null
+  EpiParams ep;
   int ncols;
   int b_resident;
 };
 
-template <int BLOCK_N, int A_STAGES, int B_SLOTS>
+template <int BLOCK_N, int A_STAGES, int B_SLOTS, int OUT_BUFS>
 struct C3Smem {
+  using E = EpiSmem<BLOCK_N, OUT_BUFS>;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int OFF_B = A_STAGES * PATCH_STRIDE;
-  static constexpr int OFF_OUT = OFF_B + B_SLOTS * B_BYTES;
-  static constexpr int OUT_BYTES = (BLOCK_N / 64) * OUT_BLK;
-  static constexpr int OFF_STAT = OFF_OUT + OUT_BYTES;              // float[4][2][BLOCK_N]
-  static constexpr int OFF_VEC = OFF_STAT + 4 * 2 * BLOCK_N * 4;    // bias, scale, shift: float[3][BLOCK_N]
-  static constexpr int OFF_BAR = OFF_VEC + 3 * BLOCK_N * 4;
+  static constexpr int OFF_EPI = OFF_B + B_SLOTS * B_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + E::TOTAL;
   static constexpr int NBAR = 2 * A_STAGES + 2 * B_SLOTS + 4;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;
 };
 
-__device__ __forceinline__ float c3_col_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
-template <int BLOCK_N, int A_STAGES, int B_SLOTS>
-__global__ void __launch_bounds__(192, 1) conv3_kernel(const __grid_constant__ Conv3Params p) {
-  using L = C3Smem<BLOCK_N, A_STAGES, B_SLOTS>;
+template <int BLOCK_N, int A_STAGES, int B_SLOTS, int OUT_BUFS>
+__global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid_constant__ Conv3Params p) {
+  using L = C3Smem<BLOCK_N, A_STAGES, B_SLOTS, OUT_BUFS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_stage = smem + L::OFF_OUT;
-  float* stat_smem = reinterpret_cast<float*>(smem + L::OFF_STAT);
-  float* vec_smem = reinterpret_cast<float*>(smem + L::OFF_VEC);
   uint64_t* afull = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* aempty = afull + A_STAGES;
   uint64_t* bfull = aempty + A_STAGES;
@@ -106,7 +83,7 @@ __global__ void __launch_bounds__(192, 1) conv3_kernel(const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -194,111 +171,22 @@ __global__ void __launch_bounds__(192, 1) conv3_kernel(const __grid_constant__ C
     }
     __syncwarp();
   } else {
-    // ================= epilogue (4 warps, one TMEM lane quadrant each) =================
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int et = threadIdx.x - 64;          // 0..127
-    const bool store_thread = (et == 0);
-    const uint32_t row_smem = smem_u32(out_stage) + row * 128;
-    const int rsw = row & 7;
-    constexpr int NCHUNK = BLOCK_N / 32;
-    float acc_sum[NCHUNK], acc_sq[NCHUNK];
-#pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) acc_sum[c] = acc_sq[c] = 0.f;
-    const bool post = p.post_scale != nullptr;
-    for (int c = et; c < BLOCK_N; c += 128) {
-      const int col = n_tile * BLOCK_N + c;
-      vec_smem[c] = p.bias ? p.bias[col] : 0.f;
-      vec_smem[BLOCK_N + c] = post ? p.post_scale[col] : 1.f;
-      vec_smem[2 * BLOCK_N + c] = post ? p.post_shift[col] : 0.f;
-    }
-    named_bar_sync(1, 128);
-    int as = 0;
-    uint32_t aphase = 0;
+    // ================= epilogue (8 warps, epilogue.cuh) =================
+    Epilogue<BLOCK_N, OUT_BUFS, TW> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    epi.load_vectors(n_tile);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * TH;
       const int w0 = (rem % p.tiles_w) * TW;
-      const bool valid = (h0 + row / TW < p.H) && (w0 + row % TW < p.W);
-
-      // staging buffer must have been drained by the previous tile's TMA store
-      if (store_thread) tma_store_wait_read0();
-      named_bar_sync(1, 128);
-
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-#pragma unroll
-      for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 32, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + vec_smem[chunk * 32 + j];
-          f[j] = p.relu ? fmaxf(x, 0.f) : x;
-        }
-        if (post) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaf(f[j], vec_smem[BLOCK_N + chunk * 32 + j], vec_smem[2 * BLOCK_N + chunk * 32 + j]);
-        }
-        const uint32_t blk = row_smem + (chunk >> 1) * OUT_BLK;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c16 = (chunk & 1) * 4 + q;
-          st_shared_v4(blk + ((c16 ^ rsw) << 4), pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                       pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
-        }
-        if (p.stats) {
-          float s[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = valid ? f[j] : 0.f;
-            s[j] = f[j] * f[j];
-          }
-          acc_sum[chunk] += c3_col_reduce32(f, lane);
-          acc_sq[chunk] += c3_col_reduce32(s, lane);
-        }
-      }
-      // accumulator stage drained -> MMA warp may reuse it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      // staged tile -> global through TMA (clipped at the image edge)
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (store_thread) {
-#pragma unroll
-        for (int b = 0; b < BLOCK_N / 64; ++b) {
-          const int j = n_tile * (BLOCK_N / 64) + b;
-          const int map = j / p.blocks_per_omap;
-          const int c0 = (j - map * p.blocks_per_omap) * 64;
-          tma_store_4d(&p.o_map[map], out_stage + b * OUT_BLK, c0, w0, h0, img);
-        }
-        tma_store_commit();
-      }
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      epi.tile(h0, w0, [&](const uint8_t* blk, int b) {
+        const int j = n_tile * (BLOCK_N / 64) + b;
+        const int map = j / p.blocks_per_omap;
+        tma_store_4d(&p.o_map[map], blk, (j - map * p.blocks_per_omap) * 64, w0, h0, img);
+      });
     }
-    if (store_thread) tma_store_wait_all0();
-    if (p.stats) {
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        stat_smem[(quad * 2 + 0) * BLOCK_N + c * 32 + lane] = acc_sum[c];
-        stat_smem[(quad * 2 + 1) * BLOCK_N + c * 32 + lane] = acc_sq[c];
-      }
-      named_bar_sync(1, 128);
-      const int srow = blockIdx.x / p.n_tiles;
-      for (int i = et; i < 2 * BLOCK_N; i += 128) {
-        const int which = i / BLOCK_N, c = i % BLOCK_N;
-        float t = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) t += stat_smem[(q * 2 + which) * BLOCK_N + c];
-        p.stats[((size_t)srow * 2 + which) * p.ncols + n_tile * BLOCK_N + c] = t;
-      }
-    }
+    epi.finish(n_tile, blockIdx.x / p.n_tiles);
   }
 
   tc_fence_before();
@@ -309,11 +197,11 @@ __global__ void __launch_bounds__(192, 1) conv3_kernel(const __grid_constant__ C
   }
 }
 
-template <int BLOCK_N, int A_STAGES, int B_SLOTS>
+template <int BLOCK_N, int A_STAGES, int B_SLOTS, int OUT_BUFS>
 int launch_c3(Conv3Params& p, int n_img, cudaStream_t stream) {
-  using L = C3Smem<BLOCK_N, A_STAGES, B_SLOTS>;
+  using L = C3Smem<BLOCK_N, A_STAGES, B_SLOTS, OUT_BUFS>;
   static_assert(L::TOTAL <= 232448, "smem budget");
-  auto kern = conv3_kernel<BLOCK_N, A_STAGES, B_SLOTS>;
+  auto kern = conv3_kernel<BLOCK_N, A_STAGES, B_SLOTS, OUT_BUFS>;
   static bool attr_done = false;
   if (!attr_done) {
     UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -332,8 +220,8 @@ int launch_c3(Conv3Params& p, int n_img, cudaStream_t stream) {
   if (grid <= 0) grid = p.n_tiles;
   if (grid > total) grid = total;            // total is a multiple of n_tiles
   UB_CHECK_SHAPE(grid / p.n_tiles <= UB_STATS_ROWS, "conv3: stats rows");
-  if (p.stats) UB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
-  kern<<<(int)grid, 192, L::TOTAL, stream>>>(p);
+  if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  kern<<<(int)grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
@@ -342,9 +230,11 @@ int launch(Conv3Params& p, int n_img, cudaStream_t stream) {
   p.cblk_total = 0;
   for (int i = 0; i < p.nsrc; ++i) p.cblk_total += p.cblk[i];
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
-  if (p.ncols % 256 == 0) return launch_c3<256, 2, 3>(p, n_img, stream);
-  if (p.ncols % 128 == 0) return launch_c3<128, 3, 6>(p, n_img, stream);
-  return launch_c3<64, 2, 18>(p, n_img, stream);
+  p.ep.ncols = p.ncols;
+  p.ep.bias_mod = p.ncols;
+  if (p.ncols % 256 == 0) return launch_c3<256, 2, 3, 1>(p, n_img, stream);
+  if (p.ncols % 128 == 0) return launch_c3<128, 2, 6, 2>(p, n_img, stream);
+  return launch_c3<64, 2, 18, 2>(p, n_img, stream);
 }
 
 int in_map(CUtensorMap* m, const void* base, int C, int W, int H, int N) {
@@ -374,14 +264,14 @@ int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void
   const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   if ((rc = ub_tmap_mat2d(&p.b_map, w, Cout, 9ll * Cin, bn))) return rc;
   if ((rc = out_map(&p.o_map[0], out, Cout, W, H, N))) return rc;
-  p.H = H;
-  p.W = W;
+  p.H = p.ep.H = H;
+  p.W = p.ep.W = W;
   p.blocks_per_omap = Cout / 64;
-  p.bias = bias;
-  p.post_scale = post_scale;
-  p.post_shift = post_shift;
-  p.relu = relu;
-  p.stats = stats;
+  p.ep.bias = bias;
+  p.ep.post_scale = post_scale;
+  p.ep.post_shift = post_shift;
+  p.ep.relu = relu;
+  p.ep.stats = stats;
   p.ncols = Cout;
   return launch(p, N, stream);
 }
@@ -399,10 +289,9 @@ int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, in
   if ((rc = ub_tmap_mat2d(&p.b_map, w_t, Cin, 9ll * Cout, bn))) return rc;
   if ((rc = out_map(&p.o_map[0], dx0, C0, W, H, N))) return rc;
   if (C1 > 0 && (rc = out_map(&p.o_map[1], dx1, C1, W, H, N))) return rc;
-  p.H = H;
-  p.W = W;
+  p.H = p.ep.H = H;
+  p.W = p.ep.W = W;
   p.blocks_per_omap = C0 / 64;
-  p.relu = 0;
   p.ncols = Cin;
   return launch(p, N, stream);
 }

@@ -12,11 +12,12 @@
 //
 // M tile = 128 pixels = an 8x16 (h x w) patch of one image; the 'same' zero padding and ragged image edges come
 // from TMA out-of-bounds zero fill / store clipping.  K is walked in 64-channel blocks (one 128-byte swizzle row).
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 = epilogue (epilogue.cuh).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "epilogue.cuh"
 
 namespace {
 
@@ -40,49 +41,26 @@ struct IgemmFwdParams {
   int tiles_w, tiles_h;
   int n_tiles, total_tiles;
   int blocks_per_omap;
-  const float* bias;  // may be null
-  int bias_mod;       // bias index = column % bias_mod
-  int relu;
-  float* stats;       // [UB_STATS_ROWS][2][ncols] or null
+  EpiParams ep;       // bias (index = column % bias_mod), relu, stats [UB_STATS_ROWS][2][ncols]
   int ncols;
 };
 
 template <int BLOCK_N, int STAGES>
 struct SmemLayout {
+  using E = EpiSmem<BLOCK_N, 1>;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int OUT_BYTES = (BLOCK_N / 64) * A_BYTES;
-  static constexpr int OFF_OUT = STAGES * STAGE_BYTES;
-  static constexpr int OFF_STAT = OFF_OUT + OUT_BYTES;          // float[4][2][BLOCK_N]
-  static constexpr int OFF_BIAS = OFF_STAT + 4 * 2 * BLOCK_N * 4;  // float[BLOCK_N]
-  static constexpr int OFF_BAR = OFF_BIAS + BLOCK_N * 4;        // full[S], empty[S], tfull[2], tempty[2]
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + E::TOTAL;             // full[S], empty[S], tfull[2], tempty[2]
   static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 4) * 8;
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;            // + alignment slack
 };
 
-// Column sums over the 32 lanes of a warp for 32 columns held per lane: lane l returns sum_rows v[l].
-__device__ __forceinline__ float col_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant__ IgemmFwdParams p) {
+__global__ void __launch_bounds__(64 + EPI_THREADS, 1) igemm_fwd_kernel(const __grid_constant__ IgemmFwdParams p) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_stage = smem + L::OFF_OUT;
-  float* stat_smem = reinterpret_cast<float*>(smem + L::OFF_STAT);
-  float* bias_smem = reinterpret_cast<float*>(smem + L::OFF_BIAS);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
@@ -102,7 +80,7 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -175,108 +153,24 @@ __global__ void __launch_bounds__(192, 1) igemm_fwd_kernel(const __grid_constant
     }
     __syncwarp();
   } else {
-    // ================= epilogue (4 warps, one TMEM lane quadrant each) =================
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
-    const int et = threadIdx.x - 64;          // 0..127
-    const bool store_thread = (et == 0);
-    const uint32_t row_smem = smem_u32(out_stage) + row * 128;
-    const int rsw = row & 7;
-    constexpr int NCHUNK = BLOCK_N / 32;
-    float acc_sum[NCHUNK], acc_sq[NCHUNK];
-#pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) acc_sum[c] = acc_sq[c] = 0.f;
-    int as = 0;
-    uint32_t aphase = 0;
-    int last_n_tile = -1;
+    // ================= epilogue (8 warps, epilogue.cuh) =================
+    // host guarantees gridDim.x % n_tiles == 0, so this CTA's n_tile never changes
+    const int n_tile = blockIdx.x % p.n_tiles;
+    Epilogue<BLOCK_N, 1, TILE_W> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    epi.load_vectors(n_tile);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * TILE_H;
       const int w0 = (rem % p.tiles_w) * TILE_W;
-      const bool valid = (h0 + row / TILE_W < p.H) && (w0 + row % TILE_W < p.W);
-
-      // staging buffer must have been drained by the previous tile's TMA store; refresh the bias slice
-      if (store_thread) tma_store_wait_read0();
-      if (n_tile != last_n_tile) {
-        for (int c = et; c < BLOCK_N; c += 128)
-          bias_smem[c] = p.bias ? p.bias[(n_tile * BLOCK_N + c) % p.bias_mod] : 0.f;
-        last_n_tile = n_tile;
-      }
-      named_bar_sync(1, 128);
-
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-#pragma unroll
-      for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 32, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) + bias_smem[chunk * 32 + j];
-          f[j] = p.relu ? fmaxf(x, 0.f) : x;
-        }
-        const uint32_t blk = row_smem + (chunk >> 1) * A_BYTES;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int c16 = (chunk & 1) * 4 + q;
-          st_shared_v4(blk + ((c16 ^ rsw) << 4), pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]), pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]),
-                       pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
-        }
-        if (p.stats) {
-          float s[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            f[j] = valid ? f[j] : 0.f;
-            s[j] = f[j] * f[j];
-          }
-          acc_sum[chunk] += col_reduce32(f, lane);
-          acc_sq[chunk] += col_reduce32(s, lane);
-        }
-      }
-      // accumulator stage drained -> MMA warp may reuse it
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
-      // staged tile -> global through TMA (clipped at the image edge)
-      fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (store_thread) {
-#pragma unroll
-        for (int b = 0; b < BLOCK_N / 64; ++b) {
-          const int j = n_tile * (BLOCK_N / 64) + b;
-          const int map = j / p.blocks_per_omap;
-          const int c0 = (j - map * p.blocks_per_omap) * 64;
-          tma_store_4d(&p.o_map[map], out_stage + b * A_BYTES, c0, w0, h0, img);
-        }
-        tma_store_commit();
-      }
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      epi.tile(h0, w0, [&](const uint8_t* blk, int b) {
+        const int j = n_tile * (BLOCK_N / 64) + b;
+        const int map = j / p.blocks_per_omap;
+        tma_store_4d(&p.o_map[map], blk, (j - map * p.blocks_per_omap) * 64, w0, h0, img);
+      });
     }
-    if (store_thread) tma_store_wait_all0();
-    if (p.stats) {
-      // per-CTA partials: host guarantees gridDim.x % n_tiles == 0, so this CTA's n_tile never changes
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
-        stat_smem[(quad * 2 + 0) * BLOCK_N + c * 32 + lane] = acc_sum[c];
-        stat_smem[(quad * 2 + 1) * BLOCK_N + c * 32 + lane] = acc_sq[c];
-      }
-      named_bar_sync(1, 128);
-      const int n_tile = blockIdx.x % p.n_tiles;
-      const int srow = blockIdx.x / p.n_tiles;
-      for (int i = et; i < 2 * BLOCK_N; i += 128) {
-        const int which = i / BLOCK_N, c = i % BLOCK_N;
-        float t = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) t += stat_smem[(q * 2 + which) * BLOCK_N + c];
-        p.stats[((size_t)srow * 2 + which) * p.ncols + n_tile * BLOCK_N + c] = t;
-      }
-    }
+    epi.finish(n_tile, blockIdx.x / p.n_tiles);
   }
 
   tc_fence_before();
@@ -318,8 +212,8 @@ int launch_t(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
   if (grid <= 0) grid = p.n_tiles;
   if (grid > p.total_tiles) grid = p.total_tiles;
   UB_CHECK_SHAPE(grid / p.n_tiles <= UB_STATS_ROWS, "igemm: stats rows");
-  if (p.stats) UB_CUDA(cudaMemsetAsync(p.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
-  kern<<<grid, 192, L::TOTAL, stream>>>(p);
+  if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  kern<<<grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
@@ -328,6 +222,9 @@ int launch(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
   p.kb_per_tap = 0;
   for (int i = 0; i < p.nsrc; ++i) p.kb_per_tap += p.cblk[i];
   p.num_kb = p.kb_per_tap * p.ntaps;
+  p.ep.ncols = p.ncols;
+  p.ep.H = p.H;
+  p.ep.W = p.W;
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.num_kb > 0, "igemm: columns must be a multiple of 64");
   if (p.ncols % 256 == 0) return launch_t<256, 3>(p, n_img, stream);
   if (p.ncols % 128 == 0) return launch_t<128, 5>(p, n_img, stream);
@@ -396,10 +293,10 @@ int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w
   p.H = H;
   p.W = W;
   p.blocks_per_omap = Cout / 64;
-  p.bias = bias;
-  p.bias_mod = Cout;
-  p.relu = relu;
-  p.stats = stats;
+  p.ep.bias = bias;
+  p.ep.bias_mod = Cout;
+  p.ep.relu = relu;
+  p.ep.stats = stats;
   p.ncols = Cout;
   return launch(p, N, stream);
 }
@@ -425,10 +322,10 @@ int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C
   p.H = H;
   p.W = W;
   p.blocks_per_omap = C0 / 64;
-  p.bias = nullptr;
-  p.bias_mod = 1;
-  p.relu = 0;
-  p.stats = nullptr;
+  p.ep.bias = nullptr;
+  p.ep.bias_mod = 1;
+  p.ep.relu = 0;
+  p.ep.stats = nullptr;
   p.ncols = Cin;
   return launch(p, N, stream);
 }
@@ -451,10 +348,10 @@ int ub_deconv2x2_fwd(const void* x, int Cin, const void* w, const float* bias, v
   p.H = h;
   p.W = wd;
   p.blocks_per_omap = Cout / 64;
-  p.bias = bias;
-  p.bias_mod = Cout;
-  p.relu = 0;
-  p.stats = stats;
+  p.ep.bias = bias;
+  p.ep.bias_mod = Cout;
+  p.ep.relu = 0;
+  p.ep.stats = stats;
   p.ncols = ncols;
   return launch(p, N, stream);
 }
@@ -477,10 +374,10 @@ int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int 
   p.H = h;
   p.W = wd;
   p.blocks_per_omap = Cin / 64;
-  p.bias = nullptr;
-  p.bias_mod = 1;
-  p.relu = 0;
-  p.stats = nullptr;
+  p.ep.bias = nullptr;
+  p.ep.bias_mod = 1;
+  p.ep.relu = 0;
+  p.ep.stats = nullptr;
   p.ncols = Cin;
   return launch(p, N, stream);
 }
