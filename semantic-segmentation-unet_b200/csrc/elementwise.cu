@@ -170,57 +170,100 @@ __global__ void __launch_bounds__(TPB) bn_apply_kernel(const T* __restrict__ a, 
                                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const uint8_t* __restrict__ drop_mask,
                                                        long long total8, int C) {
+  // the grid stride (gridDim.x * TPB) is a multiple of the channel-group count G (G divides TPB), so a thread keeps
+  // its 8 channels for the whole loop and the folded affine lives in registers
   const int G = C >> 3;
-  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total8; i += (long long)gridDim.x * TPB) {
-    const int c0 = (int)(i % G) * 8;
-    float f[8], mu[8], rs[8], ga[8], be[8];
-    V8<T>::load(a + i * 8, f);
+  const long long i0 = (long long)blockIdx.x * TPB + threadIdx.x;
+  const long long stride = (long long)gridDim.x * TPB;
+  const int c0 = (int)(i0 % G) * 8;
+  float sc[8], sh[8];
+  {
+    float mu[8], rs[8], ga[8], be[8];
     load8f(mean + c0, mu); load8f(rstd + c0, rs); load8f(gamma + c0, ga); load8f(beta + c0, be);
-    uint2 dm = make_uint2(0x01010101u, 0x01010101u);
-    if (drop_mask) dm = __ldg(reinterpret_cast<const uint2*>(drop_mask + i * 8));
-    const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dm);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float sc = ga[k] * rs[k];
-      float v = (f[k] - mu[k]) * sc + be[k];
-      if (drop_mask) v = dmb[k] ? 2.f * v : 0.f;
+      sc[k] = ga[k] * rs[k];
+      sh[k] = be[k] - mu[k] * sc[k];
+    }
+  }
+  for (long long i = i0; i < total8; i += 2 * stride) {
+    const long long j = i + stride;
+    const bool two = j < total8;
+    float f[8], g[8];
+    uint2 dm0 = make_uint2(0x01010101u, 0x01010101u), dm1 = dm0;
+    V8<T>::load(a + i * 8, f);
+    if (two) V8<T>::load(a + j * 8, g);
+    if (drop_mask) {
+      dm0 = __ldg(reinterpret_cast<const uint2*>(drop_mask + i * 8));
+      if (two) dm1 = __ldg(reinterpret_cast<const uint2*>(drop_mask + j * 8));
+    }
+    const uint8_t* d0 = reinterpret_cast<const uint8_t*>(&dm0);
+    const uint8_t* d1 = reinterpret_cast<const uint8_t*>(&dm1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = fmaf(f[k], sc[k], sh[k]);
+      if (drop_mask) v = d0[k] ? 2.f * v : 0.f;
       f[k] = v;
     }
     V8<T>::store(y + i * 8, f);
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float v = fmaf(g[k], sc[k], sh[k]);
+        if (drop_mask) v = d1[k] ? 2.f * v : 0.f;
+        g[k] = v;
+      }
+      V8<T>::store(y + j * 8, g);
+    }
   }
 }
 
 // One thread = one 2x2 window x 8 channels: writes the 4 normalised pixels, the pooled max and its slot (2*dy+dx,
 // first max wins, matching argmax tie-breaking of the oracle).
 template <typename T>
-__global__ void __launch_bounds__(TPB) bn_apply_pool_kernel(const T* __restrict__ a, T* __restrict__ y, T* __restrict__ pooled,
+__global__ void __launch_bounds__(TPB, 3) bn_apply_pool_kernel(const T* __restrict__ a, T* __restrict__ y, T* __restrict__ pooled,
                                                             uint8_t* __restrict__ idx, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const uint8_t* __restrict__ drop_mask,
                                                             int N, int H, int W, int C) {
   const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * Ho * Wo * G;
+  // grid stride is a multiple of G (G divides TPB): the thread's channel group and folded affine are loop invariant
+  const int c0 = (int)(((long long)blockIdx.x * TPB + threadIdx.x) % G) * 8;
+  float sc[8], sh[8];
+  {
+    float mu[8], rs[8], ga[8], be[8];
+    load8f(mean + c0, mu); load8f(rstd + c0, rs); load8f(gamma + c0, ga); load8f(beta + c0, be);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = ga[k] * rs[k];
+      sh[k] = be[k] - mu[k] * sc[k];
+    }
+  }
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
-    const int g = (int)(i % G);
     long long t = i / G;
     const int wo = (int)(t % Wo); t /= Wo;
     const int ho = (int)(t % Ho);
     const int n = (int)(t / Ho);
-    const int c0 = g * 8;
-    float mu[8], rs[8], ga[8], be[8], best[8];
+    float best[8];
     int slot[8];
-    load8f(mean + c0, mu); load8f(rstd + c0, rs); load8f(gamma + c0, ga); load8f(beta + c0, be);
+    float fa[4][8];
+    uint2 dma[4];
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const long long off = (((long long)n * H + 2 * ho + (s >> 1)) * W + 2 * wo + (s & 1)) * C + c0;
-      float f[8];
-      V8<T>::load(a + off, f);
-      uint2 dm = make_uint2(0x01010101u, 0x01010101u);
-      if (drop_mask) dm = __ldg(reinterpret_cast<const uint2*>(drop_mask + off));
-      const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dm);
+      V8<T>::load(a + off, fa[s]);
+      dma[s] = make_uint2(0x01010101u, 0x01010101u);
+      if (drop_mask) dma[s] = __ldg(reinterpret_cast<const uint2*>(drop_mask + off));
+    }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const long long off = (((long long)n * H + 2 * ho + (s >> 1)) * W + 2 * wo + (s & 1)) * C + c0;
+      float (&f)[8] = fa[s];
+      const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dma[s]);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        float v = (f[k] - mu[k]) * (ga[k] * rs[k]) + be[k];
+        float v = fmaf(f[k], sc[k], sh[k]);
         if (drop_mask) v = dmb[k] ? 2.f * v : 0.f;
         f[k] = v;
       }
@@ -304,59 +347,98 @@ __global__ void __launch_bounds__(TPB) dropout_scale_kernel(const T* __restrict_
 // ------------------------------------------------------------------ BN backward
 // pass 1: partial[row][0][c] = sum dy, partial[row][1][c] = sum dy * xhat
 template <typename T>
-__global__ void __launch_bounds__(TPB) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
+__global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* __restrict__ partial, long long M, int C) {
   const int G = C >> 3, PL = TPB / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
-  float mu[8], rs[8];
+  float mu[8];
   load8f(mean + g * 8, mu);
-  load8f(rstd + g * 8, rs);
   float acc[2][8] = {};
-  for (long long px = (long long)blockIdx.x * PL + pl; px < M; px += (long long)gridDim.x * PL) {
-    float d[8], f[8];
+  const long long stride = (long long)gridDim.x * PL;
+  for (long long px = (long long)blockIdx.x * PL + pl; px < M; px += 2 * stride) {
+    const long long px2 = px + stride;
+    const bool two = px2 < M;
+    float d[8], f[8], d2[8] = {}, f2[8] = {};
     V8<T>::load(dy + px * C + g * 8, d);
     V8<T>::load(a + px * C + g * 8, f);
+    if (two) {
+      V8<T>::load(dy + px2 * C + g * 8, d2);
+      V8<T>::load(a + px2 * C + g * 8, f2);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[0][i] += d[i];
-      acc[1][i] += d[i] * (f[i] - mu[i]) * rs[i];
+      acc[1][i] = fmaf(d[i], f[i] - mu[i], acc[1][i]);
     }
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += d2[i];
+        acc[1][i] = fmaf(d2[i], f2[i] - mu[i], acc[1][i]);
+      }
+    }
+  }
+  {
+    float rs[8];
+    load8f(rstd + g * 8, rs);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[1][i] *= rs[i];      // sum dy * xhat = rstd * sum dy * (a - mean)
   }
   block_channel_reduce<2>(acc, C, partial);
 }
 
 // pass 2: dz = gamma*rstd*(dy - dbeta/M - xhat*dgamma/M) * [a > 0 if relu];  partial[row][0][c] = sum dz (bias gradient)
 template <typename T>
-__global__ void __launch_bounds__(TPB) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
+__global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ dbeta, const float* __restrict__ dgamma,
                                                            T* __restrict__ dz, float* __restrict__ partial, long long M, int C, int relu) {
   const int G = C >> 3, PL = TPB / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
-  float mu[8], rs[8], ga[8], db[8], dg[8];
-  load8f(mean + g * 8, mu); load8f(rstd + g * 8, rs); load8f(gamma + g * 8, ga);
-  load8f(dbeta + g * 8, db); load8f(dgamma + g * 8, dg);
-  const float invM = 1.f / (float)M;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    ga[i] *= rs[i];
-    db[i] *= invM;
-    dg[i] *= invM;
-  }
-  float acc[1][8] = {};
-  for (long long px = (long long)blockIdx.x * PL + pl; px < M; px += (long long)gridDim.x * PL) {
-    float d[8], f[8];
-    V8<T>::load(dy + px * C + g * 8, d);
-    V8<T>::load(a + px * C + g * 8, f);
+  // dz = gamma*rstd*(dy - dbeta/M - xhat*dgamma/M) = cA*dy + cB*a + cC  with xhat = (a - mean)*rstd
+  float cA[8], cB[8], cC[8];
+  {
+    float mu[8], rs[8], ga[8], db[8], dg[8];
+    load8f(mean + g * 8, mu); load8f(rstd + g * 8, rs); load8f(gamma + g * 8, ga);
+    load8f(dbeta + g * 8, db); load8f(dgamma + g * 8, dg);
+    const float invM = 1.f / (float)M;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float xh = (f[i] - mu[i]) * rs[i];
-      float v = ga[i] * (d[i] - db[i] - xh * dg[i]);
+      cA[i] = ga[i] * rs[i];
+      cB[i] = -cA[i] * rs[i] * dg[i] * invM;
+      cC[i] = -cA[i] * db[i] * invM - cB[i] * mu[i];
+    }
+  }
+  float acc[1][8] = {};
+  const long long stride = (long long)gridDim.x * PL;
+  for (long long px = (long long)blockIdx.x * PL + pl; px < M; px += 2 * stride) {
+    const long long px2 = px + stride;
+    const bool two = px2 < M;
+    float d[8], f[8], d2[8] = {}, f2[8] = {};
+    V8<T>::load(dy + px * C + g * 8, d);
+    V8<T>::load(a + px * C + g * 8, f);
+    if (two) {
+      V8<T>::load(dy + px2 * C + g * 8, d2);
+      V8<T>::load(a + px2 * C + g * 8, f2);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = fmaf(cA[i], d[i], fmaf(cB[i], f[i], cC[i]));
       if (relu && !(f[i] > 0.f)) v = 0.f;
       d[i] = v;
       acc[0][i] += v;   // bias gradient from the fp32 value (the reference is fp32; a deconv bias gradient is analytically 0)
     }
     V8<T>::store(dz + px * C + g * 8, d);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = fmaf(cA[i], d2[i], fmaf(cB[i], f2[i], cC[i]));
+        if (relu && !(f2[i] > 0.f)) v = 0.f;
+        d2[i] = v;
+        acc[0][i] += v;
+      }
+      V8<T>::store(dz + px2 * C + g * 8, d2);
+    }
   }
   block_channel_reduce<1>(acc, C, partial);
 }
@@ -567,7 +649,7 @@ int ub_bn_inference_rstd(const float* moving_var, float* rstd, int n, float eps,
 int ub_bn_apply(const void* a, void* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                 const unsigned char* drop_mask, long long M, int C, int dtype, cudaStream_t stream) {
   UB_CHECK_ARG(a && y && mean && rstd && gamma && beta && M > 0, "bn_apply: bad args");
-  UB_CHECK_SHAPE(C % 8 == 0, "bn_apply: C %% 8");
+  UB_CHECK_SHAPE(channels_ok(C), "bn_apply: C=%d must be a power of two in [64,2048]", C);
   const long long total8 = M * (C / 8);
   const int grid = grid_for(total8, TPB, ub_num_sms() * 16);
   UB_DISPATCH_T(dtype, (bn_apply_kernel<T><<<grid, TPB, 0, stream>>>((const T*)a, (T*)y, mean, rstd, gamma, beta, drop_mask, total8, C)));
@@ -579,9 +661,9 @@ int ub_bn_apply_pool(const void* a, void* y, void* pooled, unsigned char* idx, c
                      const float* gamma, const float* beta, const unsigned char* drop_mask, int N, int H, int W, int C, int dtype,
                      cudaStream_t stream) {
   UB_CHECK_ARG(a && y && pooled && idx && mean && rstd && gamma && beta, "bn_apply_pool: bad args");
-  UB_CHECK_SHAPE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "bn_apply_pool: C %% 8, even H/W");
+  UB_CHECK_SHAPE(channels_ok(C) && H % 2 == 0 && W % 2 == 0, "bn_apply_pool: C=%d must be a power of two in [64,2048], H/W even", C);
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
-  const int grid = grid_for(total, TPB, ub_num_sms() * 16);
+  const int grid = grid_for(total, TPB, ub_num_sms() * 12);
   UB_DISPATCH_T(dtype, (bn_apply_pool_kernel<T><<<grid, TPB, 0, stream>>>((const T*)a, (T*)y, (T*)pooled, idx, mean, rstd, gamma, beta,
                                                                          drop_mask, N, H, W, C)));
   UB_LAUNCH_CHECK();
@@ -613,7 +695,7 @@ int ub_bn_bwd_reduce(const void* dy, const void* a, const float* mean, const flo
   UB_CHECK_SHAPE(channels_ok(C), "bn_bwd_reduce: C=%d must be a power of two in [64,2048]", C);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * C, stream));
   const int PL = TPB / (C >> 3);
-  const int grid = grid_for(M, PL * 4, UB_STATS_ROWS);
+  const int grid = grid_for(M, PL * 4, ub_num_sms() * 3);      // one wave of 3 resident blocks per SM (<= UB_STATS_ROWS)
   UB_DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dy, (const T*)a, mean, rstd, partial, M, C)));
   UB_LAUNCH_CHECK();
   return UB_OK;
@@ -625,7 +707,7 @@ int ub_bn_bwd_apply(const void* dy, const void* a, const float* mean, const floa
   UB_CHECK_SHAPE(channels_ok(C), "bn_bwd_apply: C=%d must be a power of two in [64,2048]", C);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * C, stream));
   const int PL = TPB / (C >> 3);
-  const int grid = grid_for(M, PL * 4, UB_STATS_ROWS);
+  const int grid = grid_for(M, PL * 4, ub_num_sms() * 3);
   UB_DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dy, (const T*)a, mean, rstd, gamma, dbeta, dgamma, (T*)dz,
                                                                         partial, M, C, relu)));
   UB_LAUNCH_CHECK();

@@ -127,6 +127,150 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __rest
   }
 }
 
+// Strip-mined variants (W % 4 == 0): one thread = 4 consecutive pixels of a row x 8 output channels.  The 3 x 6 input
+// window is loaded once per strip (one 128-bit + two scalar loads per row) and the weights are read from shared memory
+// once per strip instead of once per pixel: ~2.5x fewer issued instructions per output than the per-pixel kernels,
+// which were issue-bound at 1/8 of the HBM roofline (profiles/r01a).
+template <typename T, int CIN>
+__global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, T* __restrict__ out,
+                                                                   float* __restrict__ partial, int N, int H, int W) {
+  __shared__ float ws[9 * CIN][64];
+  __shared__ float red[TPB * 8];
+  for (int i = threadIdx.x; i < 64 * 9 * CIN; i += TPB) {
+    const int co = i / (9 * CIN), k = i % (9 * CIN);     // w is [co][tap][ci]; k = tap * CIN + ci
+    ws[k][co] = w[i];
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = bias[sub * 8 + i];
+  float acc_s[8] = {}, acc_q[8] = {};
+  const int W4 = W >> 2;
+  const long long strips = (long long)N * H * W4;
+  const long long plane = (long long)H * W;
+  for (long long st = (long long)blockIdx.x * 32 + pl; st < strips; st += (long long)gridDim.x * 32) {
+    const int w0 = (int)(st % W4) * 4;
+    const long long t = st / W4;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float o[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[q][i] = b[i];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* xp = x + ((long long)n * CIN + ci) * plane;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = h + r - 1;
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (hh >= 0 && hh < H) {
+          const float* row = xp + (long long)hh * W + w0;
+          const float4 m = __ldg(reinterpret_cast<const float4*>(row));
+          v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w;
+          if (w0 > 0) v[0] = __ldg(row - 1);
+          if (w0 + 4 < W) v[5] = __ldg(row + 4);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int k = (r * 3 + c) * CIN + ci;
+          const float4 wa = *reinterpret_cast<const float4*>(&ws[k][sub * 8]);
+          const float4 wb = *reinterpret_cast<const float4*>(&ws[k][sub * 8 + 4]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float xv = v[q + c];
+            o[q][0] += xv * wa.x; o[q][1] += xv * wa.y; o[q][2] += xv * wa.z; o[q][3] += xv * wa.w;
+            o[q][4] += xv * wb.x; o[q][5] += xv * wb.y; o[q][6] += xv * wb.z; o[q][7] += xv * wb.w;
+          }
+        }
+      }
+    }
+    const long long px0 = ((long long)n * H + h) * W + w0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[q][i] = fmaxf(o[q][i], 0.f);
+        acc_s[i] += o[q][i];
+        acc_q[i] += o[q][i] * o[q][i];
+      }
+      st8<T>(out + (px0 + q) * 64 + sub * 8, o[q]);
+    }
+  }
+  if (partial) {
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[pl * 64 + sub * 8 + i] = comp ? acc_q[i] : acc_s[i];
+      __syncthreads();
+      if (threadIdx.x < 64) {
+        float t = 0.f;
+        for (int l = 0; l < 32; ++l) t += red[l * 64 + threadIdx.x];
+        partial[((size_t)blockIdx.x * 2 + comp) * 64 + threadIdx.x] = t;
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TPB) conv_first_wgrad_strip_kernel(const float* __restrict__ x, const T* __restrict__ dz,
+                                                                     float* __restrict__ partial, int N, int H, int W, int CIN) {
+  __shared__ float red[TPB * 8];
+  const int ci = blockIdx.y;
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float acc[9][8] = {};
+  const int W4 = W >> 2;
+  const long long strips = (long long)N * H * W4;
+  const long long plane = (long long)H * W;
+  for (long long st = (long long)blockIdx.x * 32 + pl; st < strips; st += (long long)gridDim.x * 32) {
+    const int w0 = (int)(st % W4) * 4;
+    const long long t = st / W4;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const long long px0 = ((long long)n * H + h) * W + w0;
+    float d[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ld8<T>(dz + (px0 + q) * 64 + sub * 8, d[q]);
+    const float* xp = x + ((long long)n * CIN + ci) * plane;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hh = h + r - 1;
+      float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (hh >= 0 && hh < H) {
+        const float* row = xp + (long long)hh * W + w0;
+        const float4 m = __ldg(reinterpret_cast<const float4*>(row));
+        v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w;
+        if (w0 > 0) v[0] = __ldg(row - 1);
+        if (w0 + 4 < W) v[5] = __ldg(row + 4);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float xv = v[q + c];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[r * 3 + c][i] += xv * d[q][i];
+        }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[pl * 64 + sub * 8 + i] = acc[t][i];
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      float s = 0.f;
+      for (int l = 0; l < 32; ++l) s += red[l * 64 + threadIdx.x];
+      partial[(((size_t)blockIdx.x * CIN + ci) * 9 + t) * 64 + threadIdx.x] = s;
+    }
+  }
+}
+
 // dW partial[row][ci][tap][64] = sum_p dz[p][co] * x[p + tap][ci]   (blockIdx.y = ci)
 template <typename T>
 __global__ void __launch_bounds__(TPB) conv_first_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dz, float* __restrict__ partial,
@@ -176,35 +320,44 @@ __global__ void conv_first_wgrad_finalize_kernel(const float* __restrict__ parti
 }
 
 // ------------------------------------------------------------------ head forward: a[P][K] = relu(x[P][64] . w[K][64] + b)
-template <typename T>
+// K is a template parameter (weights stay in registers); two pixels per thread per iteration keep two 16-byte loads in flight.
+template <typename T, int K>
 __global__ void __launch_bounds__(TPB) head_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                                       float* __restrict__ a_out, float* __restrict__ partial, long long P, int K) {
+                                                       float* __restrict__ a_out, float* __restrict__ partial, long long P) {
   __shared__ float sh[TPB / 32];
   const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  float wr[KMAX][8];
+  float wr[K][8], bk[K];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k)
+  for (int k = 0; k < K; ++k) {
+    bk[k] = b[k];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) wr[k][i] = (k < K) ? w[k * 64 + sub * 8 + i] : 0.f;
-  float s[KMAX] = {}, q[KMAX] = {};
-  const long long iters = (P + 31) / 32;
+    for (int i = 0; i < 8; ++i) wr[k][i] = w[k * 64 + sub * 8 + i];
+  }
+  float s[K] = {}, q[K] = {};
+  const long long iters = (P + 63) / 64;
   for (long long it = blockIdx.x; it < iters; it += gridDim.x) {
-    const long long px = it * 32 + pl;
-    const bool ok = px < P;
-    float f[8] = {};
-    if (ok) ld8<T>(x + px * 64 + sub * 8, f);
+    long long px[2];
+    bool ok[2];
+    float f[2][8] = {};
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
+    for (int u = 0; u < 2; ++u) {
+      px[u] = it * 64 + u * 32 + pl;
+      ok[u] = px[u] < P;
+      if (ok[u]) ld8<T>(x + px[u] * 64 + sub * 8, f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
         float d = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d += wr[k][i] * f[i];
+        for (int i = 0; i < 8; ++i) d += wr[k][i] * f[u][i];
         d += __shfl_xor_sync(0xffffffffu, d, 1);
         d += __shfl_xor_sync(0xffffffffu, d, 2);
         d += __shfl_xor_sync(0xffffffffu, d, 4);
-        const float a = fmaxf(d + b[k], 0.f);
-        if (ok && sub == (k & 7)) {
-          a_out[px * K + k] = a;
+        const float a = fmaxf(d + bk[k], 0.f);
+        if (ok[u] && sub == (k & 7)) {
+          a_out[px[u] * K + k] = a;
           s[k] += a;
           q[k] += a * a;
         }
@@ -213,14 +366,12 @@ __global__ void __launch_bounds__(TPB) head_fwd_kernel(const T* __restrict__ x, 
   }
   if (partial) {
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        const float ts = block_sum(s[k], sh);
-        const float tq = block_sum(q[k], sh);
-        if (threadIdx.x == 0) {
-          partial[((size_t)blockIdx.x * 2 + 0) * K + k] = ts;
-          partial[((size_t)blockIdx.x * 2 + 1) * K + k] = tq;
-        }
+    for (int k = 0; k < K; ++k) {
+      const float ts = block_sum(s[k], sh);
+      const float tq = block_sum(q[k], sh);
+      if (threadIdx.x == 0) {
+        partial[((size_t)blockIdx.x * 2 + 0) * K + k] = ts;
+        partial[((size_t)blockIdx.x * 2 + 1) * K + k] = tq;
       }
     }
   }
@@ -334,68 +485,83 @@ __global__ void __launch_bounds__(TPB) head_bwd_reduce_kernel(const float* __res
 
 // pass 2: dz_k = gamma_k rstd_k (dy_k - dbeta_k/P - xhat_k dgamma_k/P) [a_k > 0]
 //         dx[p][c] = sum_k w[k][c] dz_k   ;   partial[row] = { dW[k][c] (K*64), db[k] (K) }
-template <typename T>
+template <typename T, int K>
 __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ a, const T* __restrict__ x,
                                                              const float* __restrict__ w, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                              const float* __restrict__ dbeta, const float* __restrict__ dgamma,
-                                                             T* __restrict__ dx, float* __restrict__ partial, long long P, int K) {
-  __shared__ float red[TPB / 32][KMAX * 64 + KMAX];
+                                                             T* __restrict__ dx, float* __restrict__ partial, long long P) {
+  __shared__ float red[TPB / 32][K * 64 + K];
   const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float wr[KMAX][8], accw[KMAX][8] = {}, accb[KMAX] = {};
-  float g_rs[KMAX], mu[KMAX], rs[KMAX], db[KMAX], dg[KMAX];
+  float wr[K][8], accw[K][8] = {}, accb[K] = {};
+  float g_rs[K], mu[K], rs[K], db[K], dg[K];
   const float invP = 1.f / (float)P;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
+  for (int k = 0; k < K; ++k) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) wr[k][i] = (k < K) ? w[k * 64 + sub * 8 + i] : 0.f;
-    mu[k] = (k < K) ? mean[k] : 0.f;
-    rs[k] = (k < K) ? rstd[k] : 0.f;
-    g_rs[k] = (k < K) ? gamma[k] * rs[k] : 0.f;
-    db[k] = (k < K) ? dbeta[k] * invP : 0.f;
-    dg[k] = (k < K) ? dgamma[k] * invP : 0.f;
+    for (int i = 0; i < 8; ++i) wr[k][i] = w[k * 64 + sub * 8 + i];
+    mu[k] = mean[k];
+    rs[k] = rstd[k];
+    g_rs[k] = gamma[k] * rs[k];
+    db[k] = dbeta[k] * invP;
+    dg[k] = dgamma[k] * invP;
   }
-  const long long iters = (P + 31) / 32;
+  const long long iters = (P + 63) / 64;
   for (long long it = blockIdx.x; it < iters; it += gridDim.x) {
-    const long long px = it * 32 + pl;
-    if (px < P) {
-      float f[8], o[8] = {};
-      ld8<T>(x + px * 64 + sub * 8, f);
+    long long px[2];
+    bool ok[2];
+    float f[2][8] = {};
+    float av[2][K], dv[2][K];
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) {
-          const float av = a[px * K + k];
-          const float xh = (av - mu[k]) * rs[k];
-          float dz = g_rs[k] * (dy[px * K + k] - db[k] - xh * dg[k]);
-          if (!(av > 0.f)) dz = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      px[u] = it * 64 + u * 32 + pl;
+      ok[u] = px[u] < P;
+      if (ok[u]) {
+        ld8<T>(x + px[u] * 64 + sub * 8, f[u]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          av[u][k] = __ldg(a + px[u] * K + k);
+          dv[u][k] = __ldg(dy + px[u] * K + k);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (ok[u]) {
+        float o[8] = {};
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float xh = (av[u][k] - mu[k]) * rs[k];
+          float dz = g_rs[k] * (dv[u][k] - db[k] - xh * dg[k]);
+          if (!(av[u][k] > 0.f)) dz = 0.f;
           if (sub == 0) accb[k] += dz;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             o[i] += wr[k][i] * dz;
-            accw[k][i] += dz * f[i];
+            accw[k][i] += dz * f[u][i];
           }
         }
-      if (dx) st8<T>(dx + px * 64 + sub * 8, o);
+        if (dx) st8<T>(dx + px[u] * 64 + sub * 8, o);
+      }
     }
   }
   // reduce over the 4 pixels of each warp (lanes with equal sub), then over warps through smem
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k)
-    if (k < K) {
+  for (int k = 0; k < K; ++k) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float v = accw[k][i];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (lane < 8) red[warp][k * 64 + sub * 8 + i] = v;
-      }
-      float vb = accb[k];
-      vb = warp_sum(vb);
-      if (lane == 0) red[warp][K * 64 + k] = vb;
+    for (int i = 0; i < 8; ++i) {
+      float v = accw[k][i];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) red[warp][k * 64 + sub * 8 + i] = v;
     }
+    float vb = accb[k];
+    vb = warp_sum(vb);
+    if (lane == 0) red[warp][K * 64 + k] = vb;
+  }
   __syncthreads();
-  const int ncomp = K * 64 + K;
+  constexpr int ncomp = K * 64 + K;
   for (int i = threadIdx.x; i < ncomp; i += TPB) {
     float t = 0.f;
 #pragma unroll
@@ -481,6 +647,20 @@ inline int grid_for(long long work_items, int per_block, int cap) {
     else { ub_set_error("bad dtype %d", (int)(dtype)); return UB_ERR_INVALID_ARG; } \
   } while (0)
 
+#define UB_DISPATCH_K(kk, ...)                                      \
+  do {                                                              \
+    switch (kk) {                                                   \
+      case 1: { constexpr int KK = 1; __VA_ARGS__; } break;         \
+      case 2: { constexpr int KK = 2; __VA_ARGS__; } break;         \
+      case 3: { constexpr int KK = 3; __VA_ARGS__; } break;         \
+      case 4: { constexpr int KK = 4; __VA_ARGS__; } break;         \
+      case 5: { constexpr int KK = 5; __VA_ARGS__; } break;         \
+      case 6: { constexpr int KK = 6; __VA_ARGS__; } break;         \
+      case 7: { constexpr int KK = 7; __VA_ARGS__; } break;         \
+      default: { constexpr int KK = 8; __VA_ARGS__; } break;        \
+    }                                                               \
+  } while (0)
+
 #define UB_DISPATCH_CIN(cin, ...)                                   \
   do {                                                              \
     if ((cin) == 1) { constexpr int CIN = 1; __VA_ARGS__; }         \
@@ -496,9 +676,13 @@ int ub_conv_first_fwd(const float* x_nchw, const float* w, const float* bias, vo
   UB_CHECK_ARG(x_nchw && w && bias && out, "conv_first_fwd: null pointer");
   UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_fwd: Cin=%d must be in [1,4]", Cin);
   const long long P = (long long)N * H * W;
-  const int grid = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  const bool strip = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
+  const int grid = grid_for(strip ? P / 4 : P, 32 * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * 64, stream));
-  UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, (T*)out, partial, N, H, W))));
+  if (strip)
+    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_strip_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, (T*)out, partial, N, H, W))));
+  else
+    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, (T*)out, partial, N, H, W))));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
@@ -509,9 +693,13 @@ int ub_conv_first_wgrad(const float* x_nchw, const void* dz, float* dw, float* p
   UB_CHECK_ARG(x_nchw && dz && dw && partial, "conv_first_wgrad: null pointer");
   UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_wgrad: Cin=%d must be in [1,4]", Cin);
   const long long P = (long long)N * H * W;
-  const int rows = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  const bool strip = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
+  const int rows = grid_for(strip ? P / 4 : P, 32 * 4, UB_STATS_ROWS);
   dim3 grid(rows, Cin);
-  UB_DISPATCH_T(dtype, (conv_first_wgrad_kernel<T><<<grid, TPB, 0, stream>>>(x_nchw, (const T*)dz, partial, N, H, W, Cin)));
+  if (strip)
+    UB_DISPATCH_T(dtype, (conv_first_wgrad_strip_kernel<T><<<grid, TPB, 0, stream>>>(x_nchw, (const T*)dz, partial, N, H, W, Cin)));
+  else
+    UB_DISPATCH_T(dtype, (conv_first_wgrad_kernel<T><<<grid, TPB, 0, stream>>>(x_nchw, (const T*)dz, partial, N, H, W, Cin)));
   UB_LAUNCH_CHECK();
   conv_first_wgrad_finalize_kernel<<<(64 * 9 * Cin + 127) / 128, 128, 0, stream>>>(partial, dw, rows, Cin);
   UB_LAUNCH_CHECK();
@@ -522,9 +710,9 @@ int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, flo
                 cudaStream_t stream) {
   UB_CHECK_ARG(x && w && b && a_out && P > 0, "head_fwd: bad args");
   UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_fwd: number_classes=%d exceeds UB_MAX_CLASSES=%d", K, KMAX);
-  const int grid = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  const int grid = grid_for(P, 64 * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * K, stream));
-  UB_DISPATCH_T(dtype, (head_fwd_kernel<T><<<grid, TPB, 0, stream>>>((const T*)x, w, b, a_out, partial, P, K)));
+  UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_fwd_kernel<T, KK><<<grid, TPB, 0, stream>>>((const T*)x, w, b, a_out, partial, P))));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
@@ -565,10 +753,10 @@ int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const floa
                       cudaStream_t stream) {
   UB_CHECK_ARG(dy && a && x && w && mean && rstd && gamma && dbeta && dgamma && partial && P > 0, "head_bwd_apply: bad args");
   UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_bwd_apply: K");
-  const int grid = grid_for(P, 32 * 8, UB_STATS_ROWS);
+  const int grid = grid_for(P, 64 * 4, UB_STATS_ROWS);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * (K * 64 + K), stream));
-  UB_DISPATCH_T(dtype, (head_bwd_apply_kernel<T><<<grid, TPB, 0, stream>>>(dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx,
-                                                                          partial, P, K)));
+  UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_bwd_apply_kernel<T, KK><<<grid, TPB, 0, stream>>>(dy, a, (const T*)x, w, mean, rstd, gamma, dbeta,
+                                                                                              dgamma, (T*)dx, partial, P))));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -9,6 +9,8 @@
 // canonical MN-major layout (128-byte rows = 64 channels of one pixel, 8-pixel swizzle atoms).
 // Each CTA owns one 128 x BLOCK_N output tile and a contiguous range of 64-pixel patches (split-K); partial tiles go to
 // a fp32 workspace [split][m][n] and ub_wgrad_reduce sums them in a fixed order (deterministic) into dW[n][m].
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -319,9 +321,23 @@ int build_deconv(WgradParams& p, const void* x, int Cin, const void* dz, int Cou
 
 }  // namespace
 
+// halo-patch kernel (igemm_wgrad_halo.cu): the product path for conv3x3; this file's kernel serves the deconvs
+long long ub_wgrad_halo_workspace_bytes(int C0, int C1, int Cout, int N, int H, int W);
+int ub_wgrad_halo(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, void* workspace,
+                  long long workspace_bytes, int N, int H, int W, cudaStream_t stream);
+static bool legacy_wgrad() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UB_WGRAD_LEGACY");      // A/B switch for tools/bench_layers.py: one TMA box per (tap, channel block)
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 extern "C" {
 
 long long ub_conv3x3_wgrad_workspace_bytes(int C0, int C1, int Cout, int N, int H, int W) {
+  if (!legacy_wgrad()) return ub_wgrad_halo_workspace_bytes(C0, C1, Cout, N, H, W);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.a.nmaps = C1 > 0 ? 2 : 1;
@@ -340,6 +356,8 @@ int ub_conv3x3_wgrad(const void* x0, int C0, const void* x1, int C1, const void*
   UB_CHECK_ARG(x0 && dz && dw, "conv3x3_wgrad: null pointer");
   UB_CHECK_SHAPE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0 && Cout % 64 == 0 && (C1 == 0 || x1),
                  "conv3x3_wgrad: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0, "conv3x3_wgrad: bad N/H/W");
+  if (!legacy_wgrad()) return ub_wgrad_halo(x0, C0, x1, C1, dz, Cout, dw, workspace, workspace_bytes, N, H, W, stream);
   WgradParams p;
   int rc = build_conv(p, x0, C0, x1, C1, dz, Cout, N, H, W);
   if (rc) return rc;

@@ -1,0 +1,27 @@
+#!/bin/bash
+# One gpurun call: parity tests, bench, ncu launch list, ncu --set full captures of the dominant kernels.
+# usage: tools/gpu_round.sh <tag> [kernel regexes for --set full ...]
+# gpurun_out/ must stay under 64 MiB: the .ncu-rep of each capture is exported to CSV (raw page) on the box and only
+# a short one (-c 2) is kept per kernel for the source page.
+tag=${1:-r01}; shift
+kernels=${@:-"conv3_kernel wgrad_halo_kernel igemm_wgrad_kernel bn_bwd_apply bn_apply_kernel bn_bwd_reduce"}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$tag.log
+tail -5 gpurun_out/pytest_gpu_$tag.log
+python bench.py --layers gpurun_out/layers_$tag.json > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
+cat gpurun_out/bench_$tag.json
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain_$tag.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 400 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_$tag.log 2>&1
+for k in $kernels; do
+  $CMD > gpurun_out/plain_$tag.log 2>&1 &&
+  ncu --set full --clock-control none -k regex:$k -s 0 -c ${NCU_COUNT:-17} -f -o /tmp/prof_$k $CMD > gpurun_out/ncu_${tag}_$k.log 2>&1
+  ncu -i /tmp/prof_$k.ncu-rep --page raw --csv > gpurun_out/raw_${tag}_$k.csv 2>/dev/null
+  rm -f /tmp/prof_$k.ncu-rep
+done
+# source-level reports (small): two launches each of the two tensor-core kernels
+for k in conv3_kernel wgrad_halo_kernel; do
+  $CMD > gpurun_out/plain_$tag.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 2 -f -o gpurun_out/prof_${tag}_$k $CMD > /dev/null 2>&1
+done
+du -sh gpurun_out; ls -la gpurun_out | tail -30
