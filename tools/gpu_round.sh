@@ -15,7 +15,7 @@ $CMD > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1500 -c 400 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_$tag.log 2>&1
 for k in $kernels; do
   $CMD > gpurun_out/plain_$tag.log 2>&1 &&
-  ncu --set full --clock-control none -k regex:$k -s 0 -c ${NCU_COUNT:-17} -f -o /tmp/prof_$k $CMD > gpurun_out/ncu_${tag}_$k.log 2>&1
+  ncu --set full --clock-control none -k regex:$k -s 0 -c $( [[ $k == bn_* ]] && echo 6 || echo 17 ) -f -o /tmp/prof_$k $CMD > gpurun_out/ncu_${tag}_$k.log 2>&1
   ncu -i /tmp/prof_$k.ncu-rep --page raw --csv > gpurun_out/raw_${tag}_$k.csv 2>/dev/null
   rm -f /tmp/prof_$k.ncu-rep
 done
