@@ -92,10 +92,26 @@ int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const
 int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
                       const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K,
                       int dtype, cudaStream_t stream);
-/* Inference epilogue: argmax of the head written into the tile's zone of the mask -- UNet/inference.py:105-129. */
-int ub_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int h, int w_tile,
-                   int cy0, int cy1, int cx0, int cx1, int* mask, long long mask_ld, int dst_y, int dst_x, float* softmax_out,
-                   int dtype, cudaStream_t stream);
+/* Inference epilogue: argmax of the head written into each tile's zone of the uint8 mask -- UNet/inference.py:105-129.
+ * x: [ntiles][h][w][64]; geo: device int[ntiles][6] = {cy0, cy1, cx0, cx1, dst_y, dst_x} (crop box inside the tile, destination
+ * of its top-left corner in the mask); scale/shift: BatchNorm moving statistics of the head folded (gamma*rstd, beta-mean*scale);
+ * softmax_out (nullable) [ntiles][h][w][K] serves the model-call contract of inference.py:105. */
+int ub_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int ntiles, int h,
+                   int w_tile, const int* geo, unsigned char* mask, long long mask_ld, float* softmax_out, int dtype,
+                   cudaStream_t stream);
+
+/* ---- inference forms (training=False, UNet/model.py:240, inference.py:105): BatchNorm moving statistics folded into the
+ * producer's epilogue, y = act(conv + b) * scale + shift; plain max-pool */
+int ub_conv3x3_fwd_affine(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* scale,
+                          const float* shift, void* out, int N, int H, int W, int Cout, int relu, cudaStream_t stream);
+int ub_deconv2x2_fwd_affine(const void* x, int Cin, const void* w, const float* bias, const float* scale, const float* shift, void* out,
+                            int N, int h, int w_in, int Cout, cudaStream_t stream);
+int ub_conv_first_fwd_affine(const float* x_nchw, const float* w, const float* bias, const float* scale, const float* shift, void* out,
+                             int N, int H, int W, int Cin, int dtype, cudaStream_t stream);
+int ub_maxpool2x2_fwd(const void* y, void* pooled, int N, int H, int W, int C, int dtype, cudaStream_t stream);
+/* scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale */
+int ub_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var, float* scale, float* shift,
+               int n, float eps, cudaStream_t stream);
 
 /* ---- BatchNormalization(axis=1), eps 1e-3, momentum 0.99 -- UNet/model.py:36, :47 ------------------------------ */
 int ub_bn_stats(const void* a, float* partial, long long M, int C, int dtype, cudaStream_t stream);

@@ -158,6 +158,17 @@ __global__ void __launch_bounds__(32 * RED_ROWLANES) reduce_rows_kernel(const fl
   if (ry == 0 && c < ncols) out[c] = (float)(s * (double)scale);
 }
 
+// inference fold: scale = gamma / sqrt(var + eps), shift = beta - mean * scale
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, float* __restrict__ scale, float* __restrict__ shift, int n, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float sc = (float)((double)gamma[i] / sqrt((double)var[i] + (double)eps));
+    scale[i] = sc;
+    shift[i] = beta[i] - mean[i] * sc;
+  }
+}
+
 __global__ void rsqrt_eps_kernel(const float* __restrict__ v, float* __restrict__ out, int n, float eps) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)(1.0 / sqrt((double)v[i] + (double)eps));
@@ -642,6 +653,14 @@ int ub_reduce_rows(const float* partial, int rows, int row_stride, int ncols, fl
 int ub_bn_inference_rstd(const float* moving_var, float* rstd, int n, float eps, cudaStream_t stream) {
   UB_CHECK_ARG(moving_var && rstd && n > 0, "bn_inference_rstd: bad args");
   rsqrt_eps_kernel<<<(n + 255) / 256, 256, 0, stream>>>(moving_var, rstd, n, eps);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var, float* scale, float* shift, int n,
+               float eps, cudaStream_t stream) {
+  UB_CHECK_ARG(gamma && beta && moving_mean && moving_var && scale && shift && n > 0, "bn_fold: bad args");
+  bn_fold_kernel<<<(n + 255) / 256, 256, 0, stream>>>(gamma, beta, moving_mean, moving_var, scale, shift, n, eps);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

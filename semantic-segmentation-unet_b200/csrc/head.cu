@@ -68,6 +68,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh /*[TPB/32]*/) {
 // x: fp32 NCHW [N][CIN][H][W]; w: fp32 [64][9][CIN]; out: NHWC [P][64]; partial: [rows][2][64]
 template <typename T, int CIN>
 __global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                             const float* __restrict__ post_scale, const float* __restrict__ post_shift,
                                                              T* __restrict__ out, float* __restrict__ partial, int N, int H, int W) {
   __shared__ float ws[9 * CIN][64];
   __shared__ float red[TPB * 8];
@@ -77,9 +78,13 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __rest
   }
   __syncthreads();
   const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  float b[8];
+  float b[8], psc[8], psh[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = bias[sub * 8 + i];
+  for (int i = 0; i < 8; ++i) {
+    b[i] = bias[sub * 8 + i];
+    psc[i] = post_scale ? post_scale[sub * 8 + i] : 1.f;      // inference: BatchNorm moving statistics folded in
+    psh[i] = post_shift ? post_shift[sub * 8 + i] : 0.f;
+  }
   float acc_s[8] = {}, acc_q[8] = {};
   const long long P = (long long)N * H * W;
   const long long plane = (long long)H * W;
@@ -108,6 +113,7 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __rest
       o[i] = fmaxf(o[i], 0.f);
       acc_s[i] += o[i];
       acc_q[i] += o[i] * o[i];
+      o[i] = fmaf(o[i], psc[i], psh[i]);
     }
     st8<T>(out + px * 64 + sub * 8, o);
   }
@@ -133,7 +139,8 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __rest
 // which were issue-bound at 1/8 of the HBM roofline (profiles/r01a).
 template <typename T, int CIN>
 __global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                                   const float* __restrict__ bias, T* __restrict__ out,
+                                                                   const float* __restrict__ bias, const float* __restrict__ post_scale,
+                                                                   const float* __restrict__ post_shift, T* __restrict__ out,
                                                                    float* __restrict__ partial, int N, int H, int W) {
   __shared__ float ws[9 * CIN][64];
   __shared__ float red[TPB * 8];
@@ -143,9 +150,13 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* 
   }
   __syncthreads();
   const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  float b[8];
+  float b[8], psc[8], psh[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) b[i] = bias[sub * 8 + i];
+  for (int i = 0; i < 8; ++i) {
+    b[i] = bias[sub * 8 + i];
+    psc[i] = post_scale ? post_scale[sub * 8 + i] : 1.f;      // inference: BatchNorm moving statistics folded in
+    psh[i] = post_shift ? post_shift[sub * 8 + i] : 0.f;
+  }
   float acc_s[8] = {}, acc_q[8] = {};
   const int W4 = W >> 2;
   const long long strips = (long long)N * H * W4;
@@ -196,6 +207,7 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* 
         o[q][i] = fmaxf(o[q][i], 0.f);
         acc_s[i] += o[q][i];
         acc_q[i] += o[q][i] * o[q][i];
+        o[q][i] = fmaf(o[q][i], psc[i], psh[i]);
       }
       st8<T>(out + (px0 + q) * 64 + sub * 8, o[q]);
     }
@@ -572,62 +584,90 @@ __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __rest
 
 // ------------------------------------------------------------------ inference epilogue
 // logits_k = relu(x . w_k + b_k) * scale_k + shift_k (BN moving stats folded); argmax (first max) -> mask zone.
-// Tile pixel (ty, tx) of an h x w tile is written iff it lies in the crop box [cy0,cy1) x [cx0,cx1); destination is
-// mask[(dst_y + ty - cy0) * mask_ld + dst_x + tx - cx0].
-template <typename T>
+// A batch of `ntiles` equal-sized h x w tiles (x = [ntiles][h][w][64]); tile t writes its crop box
+// [cy0,cy1) x [cx0,cx1) to mask[(dst_y + ty - cy0) * mask_ld + dst_x + tx - cx0]  (geo[t] = {cy0,cy1,cx0,cx1,dst_y,dst_x}).
+struct TileGeo {
+  int cy0, cy1, cx0, cx1, dst_y, dst_x;
+};
+template <typename T, int K>
 __global__ void __launch_bounds__(TPB) head_argmax_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                                          const float* __restrict__ scale, const float* __restrict__ shift, int K, int h, int wd,
-                                                          int cy0, int cy1, int cx0, int cx1, int* __restrict__ mask, long long mask_ld, int dst_y,
-                                                          int dst_x, float* __restrict__ softmax_out) {
+                                                          const float* __restrict__ scale, const float* __restrict__ shift, int h, int wd,
+                                                          const TileGeo* __restrict__ geo, uint8_t* __restrict__ mask, long long mask_ld,
+                                                          float* __restrict__ softmax_out) {
   const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  float wr[KMAX][8];
+  float wr[K][8], bk[K], sc[K], sf[K];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k)
+  for (int k = 0; k < K; ++k) {
+    bk[k] = b[k];
+    sc[k] = scale[k];
+    sf[k] = shift[k];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) wr[k][i] = (k < K) ? w[k * 64 + sub * 8 + i] : 0.f;
+    for (int i = 0; i < 8; ++i) wr[k][i] = w[k * 64 + sub * 8 + i];
+  }
+  const int tile = blockIdx.y;
+  const TileGeo g = geo ? geo[tile] : TileGeo{0, h, 0, wd, 0, 0};
   const long long P = (long long)h * wd;
+  const T* xt = x + (long long)tile * P * 64;
   const long long iters = (P + 31) / 32;
   for (long long it = blockIdx.x; it < iters; it += gridDim.x) {
     const long long px = it * 32 + pl;
     const bool ok = px < P;
     float f[8] = {};
-    if (ok) ld8<T>(x + px * 64 + sub * 8, f);
-    float y[KMAX];
+    if (ok) ld8<T>(xt + px * 64 + sub * 8, f);
+    float y[K];
     float mx = -INFINITY;
     int am = 0;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k)
-      if (k < K) {
-        float d = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float d = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d += wr[k][i] * f[i];
-        d += __shfl_xor_sync(0xffffffffu, d, 1);
-        d += __shfl_xor_sync(0xffffffffu, d, 2);
-        d += __shfl_xor_sync(0xffffffffu, d, 4);
-        y[k] = fmaxf(d + b[k], 0.f) * scale[k] + shift[k];
-        if (y[k] > mx) {
-          mx = y[k];
-          am = k;
-        }
+      for (int i = 0; i < 8; ++i) d += wr[k][i] * f[i];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      y[k] = fmaxf(d + bk[k], 0.f) * sc[k] + sf[k];
+      if (y[k] > mx) {
+        mx = y[k];
+        am = k;
       }
+    }
     if (ok && sub == 0) {
       const int ty = (int)(px / wd), tx = (int)(px % wd);
-      if (mask && ty >= cy0 && ty < cy1 && tx >= cx0 && tx < cx1)
-        mask[(long long)(dst_y + ty - cy0) * mask_ld + dst_x + tx - cx0] = am;
+      if (mask && ty >= g.cy0 && ty < g.cy1 && tx >= g.cx0 && tx < g.cx1)
+        mask[(long long)(g.dst_y + ty - g.cy0) * mask_ld + g.dst_x + tx - g.cx0] = (uint8_t)am;
       if (softmax_out) {
         float se = 0.f;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-          if (k < K) {
-            y[k] = __expf(y[k] - mx);
-            se += y[k];
-          }
+        for (int k = 0; k < K; ++k) {
+          y[k] = __expf(y[k] - mx);
+          se += y[k];
+        }
         const float inv = 1.f / se;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-          if (k < K) softmax_out[px * K + k] = y[k] * inv;
+        for (int k = 0; k < K; ++k) softmax_out[((long long)tile * P + px) * K + k] = y[k] * inv;
       }
     }
+  }
+}
+
+// plain 2x2 max-pool (inference: the BatchNorm is already folded into the producer), 8 channels per thread
+template <typename T>
+__global__ void __launch_bounds__(TPB) maxpool_fwd_kernel(const T* __restrict__ y, T* __restrict__ pooled, int N, int H, int W, int C) {
+  const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * G;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int c0 = (int)(i % G) * 8;
+    long long t = i / G;
+    const int wo = (int)(t % Wo); t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8], f[4][8];
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4)
+      ld8<T>(y + (((long long)n * H + 2 * ho + (s4 >> 1)) * W + 2 * wo + (s4 & 1)) * C + c0, f[s4]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) best[k] = fmaxf(fmaxf(f[0][k], f[1][k]), fmaxf(f[2][k], f[3][k]));
+    st8<T>(pooled + (((long long)n * Ho + ho) * Wo + wo) * C + c0, best);
   }
 }
 
@@ -671,8 +711,22 @@ inline int grid_for(long long work_items, int per_block, int cap) {
 
 extern "C" {
 
+static int conv_first_impl(const float* x_nchw, const float* w, const float* bias, const float* post_scale, const float* post_shift, void* out,
+                           float* partial, int N, int H, int W, int Cin, int dtype, cudaStream_t stream);
+
 int ub_conv_first_fwd(const float* x_nchw, const float* w, const float* bias, void* out, float* partial, int N, int H, int W, int Cin,
                       int dtype, cudaStream_t stream) {
+  return conv_first_impl(x_nchw, w, bias, nullptr, nullptr, out, partial, N, H, W, Cin, dtype, stream);
+}
+
+int ub_conv_first_fwd_affine(const float* x_nchw, const float* w, const float* bias, const float* scale, const float* shift, void* out,
+                             int N, int H, int W, int Cin, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(scale && shift, "conv_first_fwd_affine: null pointer");
+  return conv_first_impl(x_nchw, w, bias, scale, shift, out, nullptr, N, H, W, Cin, dtype, stream);
+}
+
+static int conv_first_impl(const float* x_nchw, const float* w, const float* bias, const float* post_scale, const float* post_shift, void* out,
+                           float* partial, int N, int H, int W, int Cin, int dtype, cudaStream_t stream) {
   UB_CHECK_ARG(x_nchw && w && bias && out, "conv_first_fwd: null pointer");
   UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_fwd: Cin=%d must be in [1,4]", Cin);
   const long long P = (long long)N * H * W;
@@ -680,9 +734,9 @@ int ub_conv_first_fwd(const float* x_nchw, const float* w, const float* bias, vo
   const int grid = grid_for(strip ? P / 4 : P, 32 * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * 64, stream));
   if (strip)
-    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_strip_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, (T*)out, partial, N, H, W))));
+    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_strip_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, post_scale, post_shift, (T*)out, partial, N, H, W))));
   else
-    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, (T*)out, partial, N, H, W))));
+    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, post_scale, post_shift, (T*)out, partial, N, H, W))));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
@@ -761,15 +815,27 @@ int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const floa
   return UB_OK;
 }
 
-int ub_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int h, int wd, int cy0,
-                   int cy1, int cx0, int cx1, int* mask, long long mask_ld, int dst_y, int dst_x, float* softmax_out, int dtype,
-                   cudaStream_t stream) {
-  UB_CHECK_ARG(x && w && b && scale && shift && (mask || softmax_out), "head_argmax: bad args");
+int ub_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int ntiles, int h, int wd,
+                   const int* geo, unsigned char* mask, long long mask_ld, float* softmax_out, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(x && w && b && scale && shift && (mask || softmax_out) && ntiles > 0 && h > 0 && wd > 0, "head_argmax: bad args");
+  UB_CHECK_ARG(!mask || geo, "head_argmax: a mask needs the tile geometry");
   UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_argmax: K");
   const long long P = (long long)h * wd;
-  const int grid = grid_for(P, 32 * 4, ub_num_sms() * 8);
-  UB_DISPATCH_T(dtype, (head_argmax_kernel<T><<<grid, TPB, 0, stream>>>((const T*)x, w, b, scale, shift, K, h, wd, cy0, cy1, cx0, cx1, mask,
-                                                                       mask_ld, dst_y, dst_x, softmax_out)));
+  int gx = grid_for(P, 32 * 4, ub_num_sms() * 8 / (ntiles < 8 ? ntiles : 8));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, ntiles);
+  UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_argmax_kernel<T, KK><<<grid, TPB, 0, stream>>>((const T*)x, w, b, scale, shift, h, wd,
+                                                                                           reinterpret_cast<const TileGeo*>(geo), mask,
+                                                                                           mask_ld, softmax_out))));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_maxpool2x2_fwd(const void* y, void* pooled, int N, int H, int W, int C, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(y && pooled && N > 0, "maxpool2x2_fwd: bad args");
+  UB_CHECK_SHAPE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_fwd: C %% 8, even H/W");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  UB_DISPATCH_T(dtype, (maxpool_fwd_kernel<T><<<grid_for(total, TPB, ub_num_sms() * 16), TPB, 0, stream>>>((const T*)y, (T*)pooled, N, H, W, C)));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -301,6 +301,17 @@ int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w
   return launch(p, N, stream);
 }
 
+// Inference form: y = relu(conv + b) * scale + shift with the BatchNorm moving statistics folded into scale/shift
+// (training=False, UNet/model.py:240 / inference.py:105): no separate normalisation pass.
+int ub_conv3x3_fwd_affine(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* scale,
+                          const float* shift, void* out, int N, int H, int W, int Cout, int relu, cudaStream_t stream) {
+  UB_CHECK_ARG(x0 && w && out && scale && shift, "conv3x3_fwd_affine: null pointer");
+  UB_CHECK_SHAPE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0 && Cout % 64 == 0 && (C1 == 0 || x1),
+                 "conv3x3_fwd_affine: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0, "conv3x3_fwd_affine: bad N/H/W");
+  return ub_conv3_halo_fwd(x0, C0, x1, C1, w, bias, scale, shift, out, nullptr, N, H, W, Cout, relu, stream);
+}
+
 int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H,
                      int W, cudaStream_t stream) {
   UB_CHECK_ARG(dz && w_t && dx0, "conv3x3_dgrad: null pointer");
@@ -330,8 +341,22 @@ int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C
   return launch(p, N, stream);
 }
 
+static int deconv_fwd_impl(const void* x, int Cin, const void* w, const float* bias, const float* scale, const float* shift, void* out,
+                           float* stats, int N, int h, int wd, int Cout, cudaStream_t stream);
+
 int ub_deconv2x2_fwd(const void* x, int Cin, const void* w, const float* bias, void* out, float* stats, int N, int h,
                      int wd, int Cout, cudaStream_t stream) {
+  return deconv_fwd_impl(x, Cin, w, bias, nullptr, nullptr, out, stats, N, h, wd, Cout, stream);
+}
+
+int ub_deconv2x2_fwd_affine(const void* x, int Cin, const void* w, const float* bias, const float* scale, const float* shift, void* out,
+                            int N, int h, int wd, int Cout, cudaStream_t stream) {
+  UB_CHECK_ARG(scale && shift, "deconv2x2_fwd_affine: null pointer");
+  return deconv_fwd_impl(x, Cin, w, bias, scale, shift, out, nullptr, N, h, wd, Cout, stream);
+}
+
+static int deconv_fwd_impl(const void* x, int Cin, const void* w, const float* bias, const float* scale, const float* shift, void* out,
+                           float* stats, int N, int h, int wd, int Cout, cudaStream_t stream) {
   UB_CHECK_ARG(x && w && out, "deconv2x2_fwd: null pointer");
   UB_CHECK_SHAPE(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "deconv2x2_fwd: channels must be multiples of 64");
   IgemmFwdParams p;
@@ -350,6 +375,8 @@ int ub_deconv2x2_fwd(const void* x, int Cin, const void* w, const float* bias, v
   p.blocks_per_omap = Cout / 64;
   p.ep.bias = bias;
   p.ep.bias_mod = Cout;
+  p.ep.post_scale = scale;
+  p.ep.post_shift = shift;
   p.ep.relu = 0;
   p.ep.stats = stats;
   p.ncols = ncols;

@@ -146,6 +146,8 @@ class UNet:
         self.MM = torch.zeros(soff, dtype=torch.float32, device=dev)      # moving_mean
         self.MV = torch.ones(soff, dtype=torch.float32, device=dev)       # moving_variance
         self.MR = torch.ones(soff, dtype=torch.float32, device=dev)       # 1/sqrt(moving_var + eps) for inference
+        self.FS = torch.ones(soff, dtype=torch.float32, device=dev)       # inference fold: gamma * MR
+        self.FB = torch.zeros(soff, dtype=torch.float32, device=dev)      #                 beta - moving_mean * FS
         self.mean = torch.zeros(soff, dtype=torch.float32, device=dev)    # batch statistics of the last training fwd
         self.rstd = torch.ones(soff, dtype=torch.float32, device=dev)
         wt_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
@@ -299,7 +301,8 @@ class UNet:
                 continue
             h, w = self._dims(H, W, L.level)
             numel = N * h * w * L.cout
-            self._ensure("a:" + n, numel, adt)
+            if training or self.precision != "bf16":
+                self._ensure("a:" + n, numel, adt)      # bf16 inference folds BN into the producer: only y is kept
             self._ensure("y:" + n, numel, adt)
             if training:
                 self._ensure("g:" + n, numel, adt)
@@ -307,7 +310,8 @@ class UNet:
             h, w = self._dims(H, W, lvl + 1)
             C = self._BASELINE_FEATURE_DEPTH << (lvl - 1)
             self._ensure(f"pool{lvl}", N * h * w * C, adt)
-            self._ensure(f"idx{lvl}", N * h * w * C, torch.uint8)
+            if training or self.precision != "bf16":
+                self._ensure(f"idx{lvl}", N * h * w * C, torch.uint8)
             if training:
                 self._ensure(f"gpool{lvl}", N * h * w * C, adt)
                 self._ensure(f"gskip{lvl}", N * 4 * h * w * C, adt)
@@ -383,7 +387,13 @@ class UNet:
         self._alloc(N, H, W, training)
         if not training and self._inference_stale:
             self._call("ub_bn_inference_rstd", self.MV, self.MR, self.n_stat, BN_EPS)
+            for L in self.layers.values():
+                o, c = L.off_stat, L.cout
+                gamma, beta = self._affine(L)
+                self._call("ub_bn_fold", gamma, beta, self.MM[o:o + c], self.MV[o:o + c], self.FS[o:o + c], self.FB[o:o + c], c, BN_EPS)
             self._inference_stale = False
+        if not training and self.precision == "bf16":
+            return self._forward_folded(x, N, H, W)
         Ls = self.layers
         dm = drop_masks or {}
         # ---- encoder
@@ -435,6 +445,53 @@ class UNet:
             cur = self._bn_apply(La, N, h, w, training)
             self._conv_fwd(Lb, cur, Lb.cin, None, 0, N, h, w, training)
             cur = self._bn_apply(Lb, N, h, w, training)
+        return cur
+
+    def _forward_folded(self, x, N, H, W):
+        """Inference forward of the bf16 path (training=False: UNet/model.py:240, inference.py:105): the BatchNorm moving
+        statistics are folded into each producer's epilogue (y = act(conv + b) * scale + shift), so every activation
+        is written once; max-pool is a plain pool.  Leaves y:dec1b ready for the head."""
+        Ls = self.layers
+
+        def fold(L):
+            o, c = L.off_stat, L.cout
+            return self.FS[o:o + c], self.FB[o:o + c]
+
+        def conv(L, x0, c0, x1, c1, h, w):
+            self._cur = L.name
+            sc, sh = fold(L)
+            y = self._b("y:" + L.name)
+            self._call("ub_conv3x3_fwd_affine", x0, c0, x1, c1, self._wptr(L), self.P[L.off_b:L.off_b + L.cout], sc, sh, y, N, h, w, L.cout, 1)
+            return y
+
+        L = Ls["enc1a"]
+        self._cur = "enc1a"
+        sc, sh = fold(L)
+        cur = self._b("y:enc1a")
+        self._call("ub_conv_first_fwd_affine", x, self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], sc, sh, cur,
+                   N, H, W, self.number_channels, self.act_code)
+        for lvl in (1, 2, 3, 4):
+            h, w = self._dims(H, W, lvl)
+            if lvl > 1:
+                La = Ls[f"enc{lvl}a"]
+                cur = conv(La, self._b(f"pool{lvl - 1}"), La.cin, None, 0, h, w)
+            Lb = Ls[f"enc{lvl}b"]
+            cur = conv(Lb, cur, Lb.cin, None, 0, h, w)
+            self._call("ub_maxpool2x2_fwd", cur, self._b(f"pool{lvl}"), N, h, w, Lb.cout, self.act_code)
+        h, w = self._dims(H, W, 5)
+        cur = conv(Ls["bota"], self._b("pool4"), Ls["bota"].cin, None, 0, h, w)
+        cur = conv(Ls["botb"], cur, Ls["botb"].cin, None, 0, h, w)
+        for lvl in (4, 3, 2, 1):
+            hi, wi = self._dims(H, W, lvl + 1)
+            h, w = self._dims(H, W, lvl)
+            Lu = Ls[f"up{lvl}"]
+            self._cur = Lu.name
+            sc, sh = fold(Lu)
+            u = self._b("y:" + Lu.name)
+            self._call("ub_deconv2x2_fwd_affine", cur, Lu.cin, self._wptr(Lu), self.P[Lu.off_b:Lu.off_b + Lu.cout], sc, sh, u, N, hi, wi, Lu.cout)
+            La, Lb = Ls[f"dec{lvl}a"], Ls[f"dec{lvl}b"]
+            cur = conv(La, self._b(f"y:enc{lvl}b"), Lu.cout, u, Lu.cout, h, w)       # concat [skip, up] (model.py:117)
+            cur = conv(Lb, cur, Lb.cin, None, 0, h, w)
         return cur
 
     def _head_forward(self, N, H, W, training):
@@ -704,23 +761,18 @@ class UNet:
         """get_keras_model()(batch) contract of UNet/inference.py:105: numpy in, array-like softmax out."""
         return self.forward_softmax(batch_data, training=False).cpu().numpy()
 
-    def predict_tile_into(self, x, mask, mask_ld, crop, dst):
-        """Inference fast path: forward one NCHW fp32 device tile and write the argmax of its zone of responsibility
-        straight into the device mask (UNet/inference.py:105-129 without the softmax round trip).
-        crop = (cy0, cy1, cx0, cx1) inside the tile, dst = (y, x) in the mask."""
+    def predict_tiles_into(self, x, geo, mask, mask_ld):
+        """Inference fast path: forward a batch of equal-sized NCHW fp32 device tiles and write the argmax of each
+        tile's zone of responsibility straight into the uint8 device mask (UNet/inference.py:105-129 without the
+        softmax round trip).  geo: int32 device tensor [N,6] = (cy0, cy1, cx0, cx1, dst_y, dst_x) per tile."""
         N, _, H, W = x.shape
-        assert N == 1
-        self._forward(x, 1, H, W, False)
+        self._forward(x, N, H, W, False)
         L = self.layers["head"]
         K = self.number_classes
-        gamma, beta = self._affine(L)
-        mm, mr = self._bn_vectors(L, False)
-        sc = self._ensure("head_scale", 2 * _C.UB_MAX_CLASSES, torch.float32)
-        # folded BN affine of the head: scale = gamma * rstd, shift = beta - mean * scale (tiny, K elements)
-        sc[:K] = gamma * mr
-        sc[K:2 * K] = beta - mm * sc[:K]
-        self._call("ub_head_argmax", self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K], sc[:K], sc[K:2 * K],
-                   K, H, W, crop[0], crop[1], crop[2], crop[3], mask, mask_ld, dst[0], dst[1], None, self.act_code)
+        o = L.off_stat
+        self._cur = "head"
+        self._call("ub_head_argmax", self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K],
+                   self.FS[o:o + K], self.FB[o:o + K], K, N, H, W, geo, mask, mask_ld, None, self.act_code)
 
     # ------------------------------------------------------------------------------------------------ checkpoint
     def state_dict(self):

@@ -283,7 +283,66 @@ def case_inference(precision):
     return r
 
 
+def case_tiled_inference(precision):
+    """unetb200.inference (device-resident, batched, disjoint zones, argmax written by the head kernel) against the
+    oracle's restatement of the UNet/inference.py tile loop wrapped around (a) the SAME CUDA model call -- checks
+    the tiling / composition logic exactly -- and (b) for fp32, the fp64 oracle model -- checks the numerics."""
+    import tempfile
+    from unetb200.model import UNet
+    import unetb200.inference as I
+    C, K = 1, 2
+    p = O.init_params(C, K, seed=7, base=64, randomize_affine=True)
+    rng = np.random.default_rng(7)
+    for k in p:
+        if k.endswith("moving_mean"):
+            p[k] = torch.tensor(rng.normal(0.3, 0.1, size=p[k].shape))
+        if k.endswith("moving_var"):
+            p[k] = torch.tensor(rng.uniform(0.5, 1.5, size=p[k].shape))
+    m = UNet(K, 1, C, precision=precision, seed=0)
+    m.load_oracle_params({k: v.numpy() for k, v in p.items()})
+    from scipy.ndimage import gaussian_filter
+    img = gaussian_filter(rng.normal(size=(400, 336)), 3).astype(np.float32)
+    img = (img / img.std()).astype(np.float32)
+    r = {}
+    got = I._inference_tiling(img, m, 288)
+    ref = O.inference_tiling(img, m.get_keras_model(), 288, 96)
+    r["tiling_agree"] = float((got == ref).mean())
+    r["shape_ok"] = bool(got.shape == ref.shape and got.dtype == np.int32)
+    ragged = img[:390, :330]                                   # not multiples of 16: reflect padding path
+    got2 = I._inference_tiling(ragged, m, 288)
+    ref2 = O.inference_tiling(ragged, m.get_keras_model(), 288, 96)
+    r["ragged_agree"] = float((got2 == ref2).mean())
+    got3 = I._inference(ragged, m)
+    ref3 = O.inference_whole(ragged, m.get_keras_model())
+    r["whole_agree"] = float((got3 == ref3).mean())
+    r["fg_fraction"] = float((ref == 1).mean())
+    ok = r["shape_ok"] and min(r["tiling_agree"], r["ragged_agree"], r["whole_agree"]) >= 0.999 and got2.shape == ragged.shape
+    if precision == "fp32":
+        ref64 = O.inference_tiling(img.astype(np.float64), O.make_model_fn(p), 288, 96)
+        r["oracle_agree"] = float((got == ref64).mean())
+        ok = ok and r["oracle_agree"] >= 0.999
+    # file path: uint16 TIFF -> GPU z-score -> mask, against the host z-score + oracle tiler around the CUDA model
+    raw = np.clip(np.round(3000 + 400 * img), 0, 65535).astype(np.uint16)
+    with tempfile.TemporaryDirectory() as d:
+        fp = os.path.join(d, "a.tif")
+        from PIL import Image
+        Image.fromarray(raw).save(fp)
+        old_tile = I.TILE_SIZE
+        I.TILE_SIZE = 288
+        try:
+            got4 = I.segment_file(fp, m)
+        finally:
+            I.TILE_SIZE = old_tile
+    ref4 = O.inference_tiling(O.zscore_normalize(raw.astype(np.float32)), m.get_keras_model(), 288, 96)
+    r["file_agree"] = float((got4 == ref4).mean())
+    ok = ok and r["file_agree"] >= 0.999 and got4.dtype == np.uint8
+    r["ok"] = bool(ok)
+    return r
+
+
 CASES = {
+    "tiled_inference_bf16": lambda: case_tiled_inference("bf16"),
+    "tiled_inference_fp32": lambda: case_tiled_inference("fp32"),
     "live_fp32_c1k2": lambda: case_live("fp32", N=2, C=1, H=64, W=48, K=2, seed=21),
     "live_fp32_c3k8": lambda: case_live("fp32", N=1, C=3, H=80, W=112, K=8, seed=22, gb=4),
     "live_bf16_c1k2": lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23),

@@ -489,6 +489,7 @@ CASES = {
     "pool_bwd": case_pool_bwd,
     "conv_first_c1": lambda: case_conv_first(1),
     "conv_first_c3": lambda: case_conv_first(3),
+    "conv_first_c2_oddw": lambda: case_conv_first(2, W=22),
     "head_k2": lambda: case_head(2),
     "head_k8_weighted": lambda: case_head(8, weighted=True),
     "adam": case_adam,
