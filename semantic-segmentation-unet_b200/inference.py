@@ -200,7 +200,7 @@ def segment_file(img_filepath, unet_model):
         raw = raw.view(np.int16)              # torch uploads the bits; ub_zscore reads them as uint16
     elif raw.dtype not in (np.uint8, np.float32):
         raw = raw.astype(np.float32)
-    chw = np.ascontiguousarray(raw.transpose((2, 0, 1)))
+    chw = np.array(raw.transpose((2, 0, 1)), order="C")      # writable copy (PIL hands out read-only buffers)
     t = torch.from_numpy(chw).pin_memory().to(dev, non_blocking=True)
     x = zscore_device(t, unet_model)          # statistics of the UNPADDED image, as the reference (inference.py:206)
     pad_y, pad_x = _pad_amounts(h0, w0)

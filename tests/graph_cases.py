@@ -340,7 +340,51 @@ def case_tiled_inference(precision):
     return r
 
 
+def case_train_driver():
+    """unetb200.train.train_model end to end on a small ImageMaskPair LMDB: raw uint16 tiles + uint8 labels -> GPU z-score
+    -> train / test steps -> checkpoint, test_loss.csv, tensorboard dirs; then unetb200.inference restores the checkpoint."""
+    import tempfile
+    from scipy.ndimage import gaussian_filter
+    import unetb200.imagereader as R
+    import unetb200.train as T
+    import unetb200.inference as I
+    from unetb200.model import UNet
+    rng = np.random.default_rng(11)
+
+    def pairs(n, tag):
+        out = []
+        for i in range(n):
+            f = gaussian_filter(rng.normal(size=(64, 64)), 3)
+            img = np.clip(3000 + 4000 * f + rng.normal(0, 30, size=f.shape), 0, 65535).astype(np.uint16)
+            out.append((f"{tag}{i:03d}.tif", img[..., None], (f > 0.02).astype(np.uint8)))
+        return out
+
+    r = {}
+    with tempfile.TemporaryDirectory() as d:
+        R.write_database(os.path.join(d, "train.lmdb"), pairs(48, "tr"))
+        R.write_database(os.path.join(d, "test.lmdb"), pairs(8, "te"))
+        out = os.path.join(d, "out")
+        test_loss = T.train_model(out, 8, 1, os.path.join(d, "train.lmdb"), os.path.join(d, "test.lmdb"), 0, 2, 0, 3e-3, 12, 10, max_epochs=4)
+        r["test_loss"] = [round(float(v), 4) for v in test_loss]
+        r["files"] = sorted(os.listdir(out))
+        r["ckpt"] = os.path.exists(os.path.join(out, "checkpoint", "ckpt"))
+        csv = open(os.path.join(out, "test_loss.csv")).read().split()
+        r["csv_rows"] = len(csv)
+        tb = [f for f in r["files"] if f.startswith("tensorboard-")]
+        r["tb"] = bool(tb) and sorted(os.listdir(os.path.join(out, tb[0]))) == ["test", "train"]
+        # inference restores the checkpoint (UNet/inference.py:191-192) and segments a held-out tile better than chance
+        m = UNet(2, 1, 1, 1e-4)
+        m.load_checkpoint(os.path.join(out, "checkpoint", "ckpt"))
+        name, img, mask = pairs(1, "x")[0]
+        pred = I._inference(R.zscore_normalize(img[..., 0].astype(np.float32)), m)
+        r["holdout_acc"] = float((pred == mask).mean())
+    r["ok"] = bool(r["ckpt"] and r["tb"] and r["csv_rows"] == len(test_loss) == 4 and "test_loss.csv" in r["files"]
+                   and min(test_loss[1:]) < test_loss[0] and r["holdout_acc"] > 0.8)
+    return r
+
+
 CASES = {
+    "train_driver": case_train_driver,
     "tiled_inference_bf16": lambda: case_tiled_inference("bf16"),
     "tiled_inference_fp32": lambda: case_tiled_inference("fp32"),
     "live_fp32_c1k2": lambda: case_live("fp32", N=2, C=1, H=64, W=48, K=2, seed=21),
