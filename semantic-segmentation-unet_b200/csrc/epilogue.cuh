@@ -80,8 +80,12 @@ struct Epilogue {
   }
 
   // store_fn(staging_block_ptr, block_index_within_tile) issues the TMA store(s) of one 64-column block (one thread calls it)
+  // One 128-pixel x BLOCK_N part of an accumulator stage.  A stage may hold several parts (the 256-pixel super-tiles of
+  // igemm_conv3.cu): `col_off` = the part's first TMEM column inside the stage, `stage_cols` = columns per stage,
+  // `first` waits for the stage's MMAs, `last` hands the stage back to the MMA warp.
   template <typename StoreFn>
-  __device__ __forceinline__ void tile(int h0, int w0, StoreFn&& store_fn) {
+  __device__ __forceinline__ void tile(int h0, int w0, StoreFn&& store_fn, int col_off = 0, bool first = true, bool last = true,
+                                       int stage_cols = BLOCK_N) {
     uint8_t* out_stage = base + buf * S::OUT_BYTES;
     // the staging buffer we are about to overwrite must have been read by its TMA store (OUT_BUFS - 1 stores may be in flight)
     if (et == 0) {
@@ -90,7 +94,7 @@ struct Epilogue {
     }
     named_bar_sync(1, EPI_THREADS);      // also orders the previous tile's column-sum reads before these writes
 
-    mbar_wait(&tfull[as], aphase);
+    if (first) mbar_wait(&tfull[as], aphase);
     tc_fence_after();
     const float* v = vec();
     const uint32_t row_smem = smem_u32(out_stage) + row * 128;
@@ -99,7 +103,7 @@ struct Epilogue {
     for (int ch = 0; ch < NCHUNK; ++ch) {
       const int chunk = half * NCHUNK + ch;               // 32-column chunk index within the tile
       uint32_t r[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * BLOCK_N + chunk * 32, r);
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * stage_cols + col_off + chunk * 32, r);
       tmem_ld_wait();
       float f[32];
 #pragma unroll
@@ -122,7 +126,7 @@ struct Epilogue {
     // accumulator stage drained -> the MMA warp may reuse it
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty[as]);
+    if (last && lane == 0) mbar_arrive(&tempty[as]);
     fence_proxy_async_smem();
     named_bar_sync(1, EPI_THREADS);
     if (et == 0) {
@@ -151,8 +155,10 @@ struct Epilogue {
         }
       }
     }
-    as ^= 1;
-    if (as == 0) aphase ^= 1;
+    if (last) {
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
     if (OUT_BUFS > 1) buf = (buf + 1 == OUT_BUFS) ? 0 : buf + 1;
   }
 

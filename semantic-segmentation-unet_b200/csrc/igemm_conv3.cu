@@ -11,19 +11,33 @@
 // shared-memory address for both the TMA write and the MMA read (measured: tools/desc_probe.py, csrc/debug.cu).
 // Compared with one TMA box per tap this cuts the activation bytes entering shared memory by 9 x 128 / 180 = 6.4x.
 //
+// CTA tile = MT horizontally adjacent 128-pixel tiles (MT = 2: a 16 x 16 super-tile, one {64, 18, 18} patch, two
+// accumulators) x BLOCK_N columns.  The activation operand is nearly free (one patch feeds 9 taps), so what the L2 has to
+// deliver per MMA clock is the WEIGHT tile: 8192 / (128 MT) bytes per clock per SM.  The first version (MT = 1, BLOCK_N =
+// 256) asked for 64 B/clk/SM and ran into the ~8.5 kB/clk chip-wide L2->SM plateau (profiles/r01_summary.md); MT = 2
+// with BLOCK_N = 128 halves that for the same 512 TMEM columns.
+//
 // Weights stream through a ring of per-(tap, channel-block) tiles; when the whole [BLOCK_N x 9 Cin] slice fits the
 // ring (the 64-channel level-1 layers) it is loaded once per CTA and stays resident.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-9 = epilogue (epilogue.cuh: bias, ReLU,
 // optional folded inference BatchNorm, bf16 store through TMA, per-channel sum / sum-of-squares partials for training BN).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 
 namespace {
 
-constexpr int TW = 8, TH = 16;
-constexpr int PW = TW + 2, PH = TH + 2;
-constexpr int PATCH_BYTES = PW * PH * 128;   // 23040
-constexpr int PATCH_STRIDE = 23 * 1024;      // ring pitch (1024-aligned)
+constexpr int TW = 8, TH = 16;           // one accumulator = 16 (h) x 8 (w) pixels
+constexpr int PH = TH + 2;
+
+template <int MT>
+struct Patch {
+  static constexpr int TWS = TW * MT;                          // CTA tile width in pixels
+  static constexpr int PW = TWS + 2;
+  static constexpr int BYTES = PW * PH * 128;                  // 23040 (MT = 1) / 41472 (MT = 2)
+  static constexpr int STRIDE = (BYTES + 1023) / 1024 * 1024;  // ring pitch (1024-aligned)
+};
 
 struct Conv3Params {
   CUtensorMap a_map[2];
@@ -39,23 +53,29 @@ struct Conv3Params {
   EpiParams ep;
   int ncols;
   int b_resident;
+  const void* w_base;        // host-side only: weight matrix [ncols][9 * Cin] for the tensor map
 };
 
-template <int BLOCK_N, int A_STAGES, int B_SLOTS, int OUT_BUFS>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS>
 struct C3Smem {
   using E = EpiSmem<BLOCK_N, OUT_BUFS>;
+  using P = Patch<MT>;
   static constexpr int B_BYTES = BLOCK_N * 128;
-  static constexpr int OFF_B = A_STAGES * PATCH_STRIDE;
+  static constexpr int OFF_B = A_STAGES * P::STRIDE;
   static constexpr int OFF_EPI = OFF_B + B_SLOTS * B_BYTES;
   static constexpr int OFF_BAR = OFF_EPI + E::TOTAL;
   static constexpr int NBAR = 2 * A_STAGES + 2 * B_SLOTS + 4;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;
+  static constexpr int STAGE_COLS = MT * BLOCK_N;              // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = 2 * STAGE_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
 };
 
-template <int BLOCK_N, int A_STAGES, int B_SLOTS, int OUT_BUFS>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS>
 __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid_constant__ Conv3Params p) {
-  using L = C3Smem<BLOCK_N, A_STAGES, B_SLOTS, OUT_BUFS>;
+  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS>;
+  using PT = Patch<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* afull = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -88,7 +108,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    tmem_alloc(tmem_slot, L::TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -110,13 +130,13 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * TH;
-      const int w0 = (rem % p.tiles_w) * TW;
+      const int w0 = (rem % p.tiles_w) * PT::TWS;
       int cbg = 0;
       for (int src = 0; src < p.nsrc; ++src) {
         for (int cb = 0; cb < p.cblk[src]; ++cb, ++cbg) {
           mbar_wait(&aempty[a_stage], a_phase ^ 1);
-          mbar_expect_tx_e(&afull[a_stage], PATCH_BYTES);
-          tma_load_4d_e(smem + a_stage * PATCH_STRIDE, &p.a_map[src], &afull[a_stage], cb * 64, w0 - 1, h0 - 1, img);
+          mbar_expect_tx_e(&afull[a_stage], PT::BYTES);
+          tma_load_4d_e(smem + a_stage * PT::STRIDE, &p.a_map[src], &afull[a_stage], cb * 64, w0 - 1, h0 - 1, img);
           if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
           if (resident && !first) continue;
           for (int tap = 0; tap < 9; ++tap) {
@@ -143,20 +163,23 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_u + as * BLOCK_N;
+      const uint32_t d_tmem = tmem_u + as * L::STAGE_COLS;
       for (int cbg = 0; cbg < p.cblk_total; ++cbg) {
         mbar_wait(&afull[a_stage], a_phase);
-        const uint32_t patch = smem_base_u + a_stage * PATCH_STRIDE;
+        const uint32_t patch = smem_base_u + a_stage * PT::STRIDE;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int slot = resident ? cbg * 9 + tap : b_slot;
           mbar_wait(&bfull[slot], resident ? 0u : b_phase);
           tc_fence_after();
           const int dh = tap / 3, dw = tap % 3;           // already offset by +1 (patch origin is pixel (-1, -1))
-          const uint64_t adesc = make_smem_desc(patch + (dh * PW + dw) * 128, 16, PW * 128);
           const uint64_t bdesc = make_smem_desc(smem_base_u + L::OFF_B + slot * L::B_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_bf16_e(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (cbg | tap | k) != 0);
+          for (int j = 0; j < MT; ++j) {                  // the MT 16x8 pixel tiles of the super-tile share this weight tile
+            const uint64_t adesc = make_smem_desc(patch + (dh * PT::PW + dw + j * TW) * 128, 16, PT::PW * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc_mma_bf16_e(d_tmem + j * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (cbg | tap | k) != 0);
+          }
           if (!resident) {
             tc_commit_e(&bempty[slot]);
             if (++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
@@ -179,12 +202,16 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
       const int img = m_tile / tiles_per_img;
       const int rem = m_tile - img * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * TH;
-      const int w0 = (rem % p.tiles_w) * TW;
-      epi.tile(h0, w0, [&](const uint8_t* blk, int b) {
-        const int j = n_tile * (BLOCK_N / 64) + b;
-        const int map = j / p.blocks_per_omap;
-        tma_store_4d(&p.o_map[map], blk, (j - map * p.blocks_per_omap) * 64, w0, h0, img);
-      });
+      const int w0 = (rem % p.tiles_w) * PT::TWS;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int wj = w0 + j * TW;
+        epi.tile(h0, wj, [&](const uint8_t* blk, int b) {
+          const int jb = n_tile * (BLOCK_N / 64) + b;
+          const int map = jb / p.blocks_per_omap;
+          tma_store_4d(&p.o_map[map], blk, (jb - map * p.blocks_per_omap) * 64, wj, h0, img);
+        }, j * BLOCK_N, j == 0, j == MT - 1, L::STAGE_COLS);
+      }
     }
     epi.finish(n_tile, blockIdx.x / p.n_tiles);
   }
@@ -193,22 +220,29 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
-template <int BLOCK_N, int A_STAGES, int B_SLOTS, int OUT_BUFS>
-int launch_c3(Conv3Params& p, int n_img, cudaStream_t stream) {
-  using L = C3Smem<BLOCK_N, A_STAGES, B_SLOTS, OUT_BUFS>;
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS>
+int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream) {
+  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS>;
+  using PT = Patch<MT>;
   static_assert(L::TOTAL <= 232448, "smem budget");
-  auto kern = conv3_kernel<BLOCK_N, A_STAGES, B_SLOTS, OUT_BUFS>;
+  auto kern = conv3_kernel<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS>;
   static bool attr_done = false;
   if (!attr_done) {
     UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     attr_done = true;
   }
+  int rc;
+  for (int i = 0; i < p.nsrc; ++i)
+    if ((rc = ub_tmap_act4d(&p.a_map[i], a_base[i], a_ch[i], p.W, p.H, n_img, (long long)a_ch[i] * 2, (long long)p.W * a_ch[i] * 2,
+                            (long long)p.H * p.W * a_ch[i] * 2, PT::PW, PH)))
+      return rc;
+  if ((rc = ub_tmap_mat2d(&p.b_map, p.w_base, p.ncols, 9ll * p.cblk_total * 64, BLOCK_N))) return rc;
   p.n_tiles = p.ncols / BLOCK_N;
-  p.tiles_w = (p.W + TW - 1) / TW;
+  p.tiles_w = (p.W + PT::TWS - 1) / PT::TWS;
   p.tiles_h = (p.H + TH - 1) / TH;
   const long long m_tiles = (long long)n_img * p.tiles_w * p.tiles_h;
   const long long total = m_tiles * p.n_tiles;
@@ -226,20 +260,27 @@ int launch_c3(Conv3Params& p, int n_img, cudaStream_t stream) {
   return UB_OK;
 }
 
-int launch(Conv3Params& p, int n_img, cudaStream_t stream) {
+int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream) {
   p.cblk_total = 0;
   for (int i = 0; i < p.nsrc; ++i) p.cblk_total += p.cblk[i];
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
-  if (p.ncols % 256 == 0) return launch_c3<256, 2, 3, 1>(p, n_img, stream);
-  if (p.ncols % 128 == 0) return launch_c3<128, 2, 6, 2>(p, n_img, stream);
-  return launch_c3<64, 2, 18, 2>(p, n_img, stream);
+  static int v1 = -1;
+  if (v1 < 0) {
+    const char* e = getenv("UB_CONV3_V1");       // A/B switch for tools/bench_layers.py: the round-1 128-pixel tiles
+    v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (v1) {
+    if (p.ncols % 256 == 0) return launch_c3<256, 1, 2, 3, 1>(p, a_base, a_ch, n_img, stream);
+    if (p.ncols % 128 == 0) return launch_c3<128, 1, 2, 6, 2>(p, a_base, a_ch, n_img, stream);
+    return launch_c3<64, 1, 2, 18, 2>(p, a_base, a_ch, n_img, stream);
+  }
+  if (p.ncols % 128 == 0) return launch_c3<128, 2, 2, 4, 2>(p, a_base, a_ch, n_img, stream);       // 256 pixels x 128 columns
+  if (p.cblk_total == 1) return launch_c3<64, 1, 5, 9, 2>(p, a_base, a_ch, n_img, stream);         // 64 -> 64: weights resident, 5-deep patches
+  return launch_c3<64, 1, 2, 18, 2>(p, a_base, a_ch, n_img, stream);                               // 128 -> 64 (dec1a): weights resident
 }
 
-int in_map(CUtensorMap* m, const void* base, int C, int W, int H, int N) {
-  return ub_tmap_act4d(m, base, C, W, H, N, (long long)C * 2, (long long)W * C * 2, (long long)H * W * C * 2, PW, PH);
-}
 int out_map(CUtensorMap* m, const void* base, int C, int W, int H, int N) {
   return ub_tmap_act4d(m, base, C, W, H, N, (long long)C * 2, (long long)W * C * 2, (long long)H * W * C * 2, TW, TH);
 }
@@ -252,17 +293,12 @@ int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void
   Conv3Params p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = in_map(&p.a_map[0], x0, C0, W, H, N))) return rc;
-  p.nsrc = 1;
+  const void* a_base[2] = {x0, x1};
+  const int a_ch[2] = {C0, C1};
+  p.nsrc = C1 > 0 ? 2 : 1;
   p.cblk[0] = C0 / 64;
-  if (C1 > 0) {
-    if ((rc = in_map(&p.a_map[1], x1, C1, W, H, N))) return rc;
-    p.nsrc = 2;
-    p.cblk[1] = C1 / 64;
-  }
-  const int Cin = C0 + C1;
-  const int bn = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
-  if ((rc = ub_tmap_mat2d(&p.b_map, w, Cout, 9ll * Cin, bn))) return rc;
+  p.cblk[1] = C1 / 64;
+  p.w_base = w;
   if ((rc = out_map(&p.o_map[0], out, Cout, W, H, N))) return rc;
   p.H = p.ep.H = H;
   p.W = p.ep.W = W;
@@ -273,7 +309,7 @@ int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void
   p.ep.relu = relu;
   p.ep.stats = stats;
   p.ncols = Cout;
-  return launch(p, N, stream);
+  return launch(p, a_base, a_ch, N, stream);
 }
 
 int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
@@ -281,17 +317,16 @@ int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, in
   Conv3Params p;
   memset(&p, 0, sizeof(p));
   int rc;
-  if ((rc = in_map(&p.a_map[0], dz, Cout, W, H, N))) return rc;
+  const void* a_base[2] = {dz, nullptr};
+  const int a_ch[2] = {Cout, 0};
   p.nsrc = 1;
   p.cblk[0] = Cout / 64;
-  const int Cin = C0 + C1;
-  const int bn = (Cin % 256 == 0) ? 256 : (Cin % 128 == 0 ? 128 : 64);
-  if ((rc = ub_tmap_mat2d(&p.b_map, w_t, Cin, 9ll * Cout, bn))) return rc;
+  p.w_base = w_t;
   if ((rc = out_map(&p.o_map[0], dx0, C0, W, H, N))) return rc;
   if (C1 > 0 && (rc = out_map(&p.o_map[1], dx1, C1, W, H, N))) return rc;
   p.H = p.ep.H = H;
   p.W = p.ep.W = W;
   p.blocks_per_omap = C0 / 64;
-  p.ncols = Cin;
-  return launch(p, N, stream);
+  p.ncols = C0 + C1;
+  return launch(p, a_base, a_ch, N, stream);
 }

