@@ -215,6 +215,26 @@ __device__ __forceinline__ void tc_mma_bf16_e(uint32_t d_tmem, uint64_t adesc, u
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four K = 16 steps of one 64-element K block (K-major operands: +32 bytes = +2 in the descriptor address field per step) with
+// ONE elect: the issuing warp's instruction stream, not the tensor pipe, bounds tiles with few columns (profiles/r01g: a
+// single warp sustains roughly one dependent instruction per 4-5 clocks; N = 64 MMAs retire every 48).
+__device__ __forceinline__ void tc_mma4_bf16_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+      "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+      "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
 // value known to be identical in all lanes -> tell the compiler (lets it keep descriptors / addresses in uniform registers)
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 

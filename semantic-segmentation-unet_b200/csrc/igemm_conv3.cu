@@ -153,35 +153,46 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer (all lanes run the loop, one elected lane issues) =================
+    // Kept lean on purpose: with 64-column tiles an MMA retires every 48 clocks and this warp's own instruction stream
+    // was the bottleneck (profiles/r01g): descriptors are base + compile-time offsets, one elect per four MMAs, and
+    // resident weights are waited for once (first tile) instead of once per tap.
     constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
     const uint32_t tmem_u = warp_uniform(tmem_base);
     const uint32_t smem_base_u = warp_uniform(smem_u32(smem));
+    const uint64_t bdesc0 = make_smem_desc(smem_base_u + L::OFF_B, 16, 1024);
     int a_stage = 0, b_slot = 0;
     uint32_t a_phase = 0, b_phase = 0;
     int as = 0;
     uint32_t aphase = 0;
+    bool first = true;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_u + as * L::STAGE_COLS;
       for (int cbg = 0; cbg < p.cblk_total; ++cbg) {
         mbar_wait(&afull[a_stage], a_phase);
-        const uint32_t patch = smem_base_u + a_stage * PT::STRIDE;
+        if (resident && first)
+          for (int tap = 0; tap < 9; ++tap) mbar_wait(&bfull[cbg * 9 + tap], 0u);
+        tc_fence_after();
+        const uint64_t adesc0 = make_smem_desc(smem_base_u + a_stage * PT::STRIDE, 16, PT::PW * 128);
+        const uint64_t bdesc_cb = bdesc0 + (uint64_t)((cbg * 9 * L::B_BYTES) >> 4);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int slot = resident ? cbg * 9 + tap : b_slot;
-          mbar_wait(&bfull[slot], resident ? 0u : b_phase);
-          tc_fence_after();
           const int dh = tap / 3, dw = tap % 3;           // already offset by +1 (patch origin is pixel (-1, -1))
-          const uint64_t bdesc = make_smem_desc(smem_base_u + L::OFF_B + slot * L::B_BYTES, 16, 1024);
-#pragma unroll
-          for (int j = 0; j < MT; ++j) {                  // the MT 16x8 pixel tiles of the super-tile share this weight tile
-            const uint64_t adesc = make_smem_desc(patch + (dh * PT::PW + dw + j * TW) * 128, 16, PT::PW * 128);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) tc_mma_bf16_e(d_tmem + j * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (cbg | tap | k) != 0);
+          uint64_t bdesc;
+          if (resident) {
+            bdesc = bdesc_cb + (uint64_t)((tap * L::B_BYTES) >> 4);
+          } else {
+            mbar_wait(&bfull[b_slot], b_phase);
+            tc_fence_after();
+            bdesc = bdesc0 + (uint64_t)((b_slot * L::B_BYTES) >> 4);
           }
+#pragma unroll
+          for (int j = 0; j < MT; ++j)                    // the MT 16x8 pixel tiles of the super-tile share this weight tile
+            tc_mma4_bf16_e(d_tmem + j * BLOCK_N, adesc0 + (uint64_t)(((dh * PT::PW + dw + j * TW) * 128) >> 4), bdesc, idesc,
+                           (cbg | tap) != 0);
           if (!resident) {
-            tc_commit_e(&bempty[slot]);
+            tc_commit_e(&bempty[b_slot]);
             if (++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
           }
         }
@@ -191,6 +202,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
       tc_commit_e(&tfull[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
+      first = false;
     }
     __syncwarp();
   } else {
@@ -277,7 +289,7 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
     return launch_c3<64, 1, 2, 18, 2>(p, a_base, a_ch, n_img, stream);
   }
   if (p.ncols % 128 == 0) return launch_c3<128, 2, 2, 4, 2>(p, a_base, a_ch, n_img, stream);       // 256 pixels x 128 columns
-  if (p.cblk_total == 1) return launch_c3<64, 1, 5, 9, 2>(p, a_base, a_ch, n_img, stream);         // 64 -> 64: weights resident, 5-deep patches
+  if (p.cblk_total == 1) return launch_c3<64, 2, 2, 9, 2>(p, a_base, a_ch, n_img, stream);         // 64 -> 64: weights resident, 256-pixel super-tiles
   return launch_c3<64, 1, 2, 18, 2>(p, a_base, a_ch, n_img, stream);                               // 128 -> 64 (dec1a): weights resident
 }
 
