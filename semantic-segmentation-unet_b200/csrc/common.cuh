@@ -235,6 +235,54 @@ __device__ __forceinline__ void tc_mma4_bf16_e(uint32_t d_tmem, uint64_t adesc, 
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
       : "memory");
 }
+// NK consecutive K = 16 steps with ONE elect; the operand descriptors advance by a_step / b_step (in descriptor address units of
+// 16 bytes) per step.  Used by the MN-major (weight-gradient) kernels, whose K steps are pixel rows.
+template <int NK>
+__device__ __forceinline__ void tc_mma_steps_bf16_e(uint32_t d_tmem, uint64_t adesc, uint64_t a_step, uint64_t bdesc, uint64_t b_step,
+                                                    uint32_t idesc, uint32_t accumulate_first) {
+  static_assert(NK == 4 || NK == 8, "NK");
+  if (NK == 8) {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n\t"
+        "add.s64 a, %1, %2;\n\tadd.s64 b, %3, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(a_step), "l"(bdesc), "l"(b_step), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t"
+        ".reg .b64 a, b;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.b32 t, 0, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %3, %5, p;\n\t"
+        "add.s64 a, %1, %2;\n\tadd.s64 b, %3, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t"
+        "add.s64 a, a, %2;\n\tadd.s64 b, b, %4;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %5, t;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(a_step), "l"(bdesc), "l"(b_step), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+  }
+}
 // value known to be identical in all lanes -> tell the compiler (lets it keep descriptors / addresses in uniform registers)
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 

@@ -141,9 +141,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) igemm_fwd_kernel(const __
         const uint32_t sa = smem_base_u + stage * L::STAGE_BYTES;
         const uint64_t adesc = make_smem_desc(sa, 16, 1024);
         const uint64_t bdesc = make_smem_desc(sa + A_BYTES, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 bytes) per 64-channel block
-          tc_mma_bf16_e(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        tc_mma4_bf16_e(d_tmem, adesc, bdesc, idesc, kb != 0);   // 4 x (K = 16 bf16 = 32 bytes) per 64-channel block, one elect
         tc_commit_e(&empty[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }

@@ -143,12 +143,9 @@ __global__ void __launch_bounds__(192, 1) igemm_wgrad_kernel(const __grid_consta
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       const uint32_t sa = smem_base_u + stage * L::STAGE_BYTES;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {  // 4 x 16 pixels
-        const uint64_t adesc = make_smem_desc(sa + k * 2048, BOX_BYTES, 1024);
-        const uint64_t bdesc = make_smem_desc(sa + L::A_BYTES + k * 2048, BOX_BYTES, 1024);
-        tc_mma_bf16_e(tmem_u, adesc, bdesc, idesc, (pt > p_begin) || (k > 0));
-      }
+      // 4 x 16 pixels, one elected asm block
+      tc_mma_steps_bf16_e<4>(tmem_u, make_smem_desc(sa, BOX_BYTES, 1024), 2048 >> 4, make_smem_desc(sa + L::A_BYTES, BOX_BYTES, 1024), 2048 >> 4,
+                             idesc, pt > p_begin);
       tc_commit_e(&empty[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }

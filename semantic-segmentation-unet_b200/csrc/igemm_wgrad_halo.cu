@@ -169,25 +169,24 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       tc_fence_after();
       const uint32_t sa = smem_base_u + stage * L::STAGE_BYTES;
       const uint32_t acc_on = (t > t_begin) ? 1u : 0u;
+      // K = 16 pixels = two tile rows per MMA; 8 K steps per accumulator in one elected asm block (the issue stream of this
+      // warp, not the tensor pipe, was the limit with one elect per MMA)
+      const uint64_t bdesc = make_smem_desc(sa + L::OFF_DZ, DZ_BLK_BYTES, TW * 128);
+      constexpr uint64_t B_STEP = (2 * TW * 128) >> 4, A_STEP = (2 * PW * 128) >> 4;
+      if (MODE == 0) {
+        const uint64_t adesc0 = make_smem_desc(sa, C::PATCH_STRIDE, PW * 128);
 #pragma unroll
-      for (int ks = 0; ks < TH / 2; ++ks) {        // K = 16 pixels = two tile rows per MMA
-        const uint64_t bdesc = make_smem_desc(sa + L::OFF_DZ + ks * 2 * TW * 128, DZ_BLK_BYTES, TW * 128);
-        if (MODE == 0) {
+        for (int dw = 0; dw < 3; ++dw)
+          tc_mma_steps_bf16_e<8>(tmem_u + dw * C::BLOCK_N, adesc0 + (uint64_t)((dw * 128) >> 4), A_STEP, bdesc, B_STEP, idesc, acc_on);
+      } else {
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
-            const uint64_t adesc = make_smem_desc(sa + ((2 * ks) * PW + dw) * 128, C::PATCH_STRIDE, PW * 128);
-            tc_mma_bf16_e(tmem_u + dw * C::BLOCK_N, adesc, bdesc, idesc, acc_on | (uint32_t)(ks != 0));
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            // pairs (0,1) (3,4) (6,7): second view one pixel to the right (LBO 128 B); (2,5) (5,8): one patch row down (LBO 1280 B)
-            const int ta = (j < 3) ? 3 * j : (j == 3 ? 2 : 5);
-            const int adh = ta / 3, adw = ta % 3;
-            const uint32_t lbo = (j < 3) ? 128u : (uint32_t)(PW * 128);
-            const uint64_t adesc = make_smem_desc(sa + ((2 * ks + adh) * PW + adw) * 128, lbo, PW * 128);
-            tc_mma_bf16_e(tmem_u + j * C::BLOCK_N, adesc, bdesc, idesc, acc_on | (uint32_t)(ks != 0));
-          }
+        for (int j = 0; j < 5; ++j) {
+          // pairs (0,1) (3,4) (6,7): second view one pixel to the right (LBO 128 B); (2,5) (5,8): one patch row down (LBO 1280 B)
+          const int ta = (j < 3) ? 3 * j : (j == 3 ? 2 : 5);
+          const int adh = ta / 3, adw = ta % 3;
+          const uint32_t lbo = (j < 3) ? 128u : (uint32_t)(PW * 128);
+          const uint64_t adesc = make_smem_desc(sa + (adh * PW + adw) * 128, lbo, PW * 128);
+          tc_mma_steps_bf16_e<8>(tmem_u + j * C::BLOCK_N, adesc, A_STEP, bdesc, B_STEP, idesc, acc_on);
         }
       }
       tc_commit_e(&empty[stage]);
