@@ -264,9 +264,10 @@ def run_cuda(args):
     nprof = 2
     if rank == 0:
         model.profile = []
-        for i in range(nprof):
-            model.train_step(dx[i % nb], dl[i % nb])
-        torch.cuda.synchronize(dev)
+    for i in range(nprof):                      # every rank runs these steps (they contain the gradient all-reduce)
+        model.train_step(dx[i % nb], dl[i % nb])
+    torch.cuda.synchronize(dev)
+    if rank == 0:
         layer_ms = {}
         for name, layer, a, b in model.profile:
             t = a.elapsed_time(b)

@@ -52,6 +52,8 @@ class DataParallel:
             kw = {}
             if backend == "nccl":
                 kw["device_id"] = torch.device("cuda", torch.cuda.current_device())
+            import datetime
+            kw["timeout"] = datetime.timedelta(seconds=int(os.environ.get("UB_DIST_TIMEOUT_S", "180")))   # fail fast instead of hanging a GPU box
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world_size, **kw)
         self._comm_stream = None
         self._buckets = None
