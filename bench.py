@@ -187,6 +187,7 @@ def write_layer_table(path, layer_ms):
 
 # ---------------------------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
     import torch
     from unetb200.dist import DataParallel
     from unetb200.model import UNet
