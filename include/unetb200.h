@@ -52,6 +52,11 @@ int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w
  * Channels [0,C0) go to dx0 and [C0,C0+C1) to dx1 (gradient of the concat; C1 == 0 or C1 == C0). */
 int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H,
                      int W, cudaStream_t stream);
+/* Same, fused with the backward-BatchNorm reduction of the tensor whose gradient it writes (the LAST output: dx1 of a
+ * concat dgrad, else dx0): a = that tensor's saved pre-normalisation activation, mean/rstd its batch statistics;
+ * partial[UB_STATS_ROWS][2][C] = {sum dy, rstd * sum dy * (a - mean)} -- what ub_bn_bwd_reduce computes in a separate pass. */
+int ub_conv3x3_dgrad_bnred(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
+                           const void* a, const float* mean, const float* rstd, float* partial, cudaStream_t stream);
 /* Gradient w.r.t. the conv kernel: dw fp32 [Cout][9][C0+C1] -- UNet/model.py:219. */
 long long ub_conv3x3_wgrad_workspace_bytes(int C0, int C1, int Cout, int N, int H, int W);
 int ub_conv3x3_wgrad(const void* x0, int C0, const void* x1, int C1, const void* dz, int Cout, float* dw, void* workspace,

@@ -22,22 +22,33 @@ struct EpiParams {
   float* stats;              // [UB_STATS_ROWS][2][ncols] or null
   int ncols;
   int H, W;                  // pixel space of the tile grid (for masking ragged tiles out of the statistics)
+  // RED (dgrad only): the tile being written is dL/dy of a BatchNorm'd tensor whose saved activation `a` is read through
+  // red_map; the epilogue accumulates that BatchNorm's backward sums (the separate bn_bwd_reduce pass over dy and a):
+  //   red_out[row][0][c] = sum dy,  red_out[row][1][c] = rstd_c * sum dy * (a - mean_c)        (c relative to red_blk_begin * 64)
+  const float* red_mean;
+  const float* red_rstd;
+  float* red_out;            // [UB_STATS_ROWS][2][red_ncols]
+  int red_blk_begin;         // first 64-column block of the output that belongs to the BatchNorm'd tensor (concat dgrad: C0 / 64)
+  int red_ncols;
 };
 
-template <int BLOCK_N, int OUT_BUFS>
+// RED: 0 = off, 1 = one `a`-tile buffer (fetched at the start of its part), 2 = two buffers (fetched one part ahead)
+template <int BLOCK_N, int OUT_BUFS, int RED = 0>
 struct EpiSmem {
   static constexpr int OUT_BYTES = (BLOCK_N / 64) * EPI_OUT_BLK;
   static constexpr int OFF_STAT = 0;                                  // float[row groups <= 8][2][BLOCK_N]: aliases staging buffer 0,
                                                                       // only touched in finish() after every TMA store has drained
-  static constexpr int OFF_VEC = OUT_BUFS * OUT_BYTES;                // bias, scale, shift: float[3][BLOCK_N]
-  static constexpr int TOTAL = OFF_VEC + 3 * BLOCK_N * 4;
+  static constexpr int OFF_ABUF = OUT_BUFS * OUT_BYTES;               // RED: the `a` tile, same swizzled layout as the staging tile
+  static constexpr int OFF_VEC = OFF_ABUF + RED * OUT_BYTES;          // bias, scale, shift: float[3][BLOCK_N]
+  static constexpr int OFF_ABAR = OFF_VEC + 3 * BLOCK_N * 4;          // RED: mbarrier of the `a` tile load
+  static constexpr int TOTAL = OFF_ABAR + 16;
   static_assert(8 * 2 * BLOCK_N * 4 <= OUT_BYTES, "statistics scratch must fit the staging buffer");
 };
 
 // TILE_W_: pixels per tile row (tile row r of accumulator row m: m / TILE_W_, column m % TILE_W_)
-template <int BLOCK_N, int OUT_BUFS, int TILE_W_>
+template <int BLOCK_N, int OUT_BUFS, int TILE_W_, int RED = 0>
 struct Epilogue {
-  using S = EpiSmem<BLOCK_N, OUT_BUFS>;
+  using S = EpiSmem<BLOCK_N, OUT_BUFS, RED>;
   static constexpr int COLS_PER_THREAD = BLOCK_N / 2;          // this warp's half of the columns
   static constexpr int NCHUNK = COLS_PER_THREAD / 32;
   static constexpr int PAIRS = BLOCK_N / 2;                    // column pairs
@@ -53,6 +64,14 @@ struct Epilogue {
   uint32_t aphase = 0;
   bool post;
   float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  // RED state
+  const CUtensorMap* red_map = nullptr;
+  int red_nt = 0;            // this CTA's n_tile
+  float m0 = 0.f, m1 = 0.f;  // mean of this thread's column pair
+  uint32_t red_phase0 = 0, red_phase1 = 0;
+  int red_cur = 0;           // buffer holding the current part's `a` tile
+  bool red_primed = false;
+  bool red_mine = false;     // this thread's column pair belongs to the BatchNorm'd tensor
 
   // epi_thread: 0 .. EPI_THREADS-1; hw_warp: warp index within the CTA (a warp may only touch TMEM lanes 32 * (hw_warp % 4) .. +31)
   __device__ __forceinline__ Epilogue(uint8_t* smem_region, const EpiParams& e, uint32_t tmem, uint64_t* tf, uint64_t* te, int epi_thread,
@@ -76,7 +95,47 @@ struct Epilogue {
       v[BLOCK_N + c] = post ? ep.post_scale[col] : 1.f;
       v[2 * BLOCK_N + c] = post ? ep.post_shift[col] : 0.f;
     }
+    if (RED) {
+      red_nt = n_tile;
+      const int c = 2 * (et % PAIRS);
+      const int gcol = n_tile * BLOCK_N + c - ep.red_blk_begin * 64;
+      red_mine = gcol >= 0 && gcol < ep.red_ncols;
+      if (red_mine) {
+        m0 = ep.red_mean[gcol];
+        m1 = ep.red_mean[gcol + 1];
+      }
+      if (et == 0) {
+        mbar_init(abar(0), 1);
+        mbar_init(abar(1), 1);
+        mbar_fence_init();
+      }
+    }
     named_bar_sync(1, EPI_THREADS);
+  }
+  __device__ __forceinline__ uint64_t* abar(int i) const { return reinterpret_cast<uint64_t*>(base + S::OFF_ABAR) + i; }
+  __device__ __forceinline__ bool red_any() const {
+    bool any = false;
+#pragma unroll
+    for (int b = 0; b < BLOCK_N / 64; ++b) any |= red_block(b);
+    return any;
+  }
+  // one thread: fetch the tile of the saved activation matching the output part at (h0, w0, img) -- same box and swizzle as
+  // the staging tile -- into buffer `bi`
+  __device__ __forceinline__ void red_issue(int bi, int h0, int w0, int img) {
+    uint32_t bytes = 0;
+#pragma unroll
+    for (int b = 0; b < BLOCK_N / 64; ++b) bytes += red_block(b) ? EPI_OUT_BLK : 0;
+    if (!bytes) return;
+    mbar_expect_tx(abar(bi), bytes);
+#pragma unroll
+    for (int b = 0; b < BLOCK_N / 64; ++b)
+      if (red_block(b))
+        tma_load_4d(base + S::OFF_ABUF + bi * S::OUT_BYTES + b * EPI_OUT_BLK, red_map, abar(bi),
+                    (red_nt * (BLOCK_N / 64) + b - ep.red_blk_begin) * 64, w0, h0, img);
+  }
+  __device__ __forceinline__ bool red_block(int b) const {
+    const int jb = red_nt * (BLOCK_N / 64) + b - ep.red_blk_begin;
+    return jb >= 0 && jb * 64 < ep.red_ncols;
   }
 
   // store_fn(staging_block_ptr, block_index_within_tile) issues the TMA store(s) of one 64-column block (one thread calls it)
@@ -85,7 +144,7 @@ struct Epilogue {
   // `first` waits for the stage's MMAs, `last` hands the stage back to the MMA warp.
   template <typename StoreFn>
   __device__ __forceinline__ void tile(int h0, int w0, StoreFn&& store_fn, int col_off = 0, bool first = true, bool last = true,
-                                       int stage_cols = BLOCK_N) {
+                                       int stage_cols = BLOCK_N, int img = 0, bool has_next = false, int nh0 = 0, int nw0 = 0, int nimg = 0) {
     uint8_t* out_stage = base + buf * S::OUT_BYTES;
     // the staging buffer we are about to overwrite must have been read by its TMA store (OUT_BUFS - 1 stores may be in flight)
     if (et == 0) {
@@ -93,6 +152,14 @@ struct Epilogue {
       else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     }
     named_bar_sync(1, EPI_THREADS);      // also orders the previous tile's column-sum reads before these writes
+    if (RED) {
+      // the buffer not holding the current part was last read one part ago (ordered by the barrier above)
+      if (et == 0) {
+        if (RED == 1 || !red_primed) red_issue(red_cur, h0, w0, img);
+        if (RED == 2 && has_next) red_issue(red_cur ^ 1, nh0, nw0, nimg);
+      }
+      red_primed = true;
+    }
 
     if (first) mbar_wait(&tfull[as], aphase);
     tc_fence_after();
@@ -155,6 +222,43 @@ struct Epilogue {
         }
       }
     }
+    if (RED) {
+      if (red_any()) {                             // uniform over the CTA
+        if (red_cur == 0) {
+          mbar_wait(abar(0), red_phase0);
+          red_phase0 ^= 1;
+        } else {
+          mbar_wait(abar(1), red_phase1);
+          red_phase1 ^= 1;
+        }
+        if (red_mine) {
+          const int pair = et % PAIRS, grp = et / PAIRS;
+          const int c = 2 * pair;
+          const uint32_t off0 = (c >> 6) * EPI_OUT_BLK + ((c & 7) << 1);
+          const uint32_t dybase = smem_u32(out_stage) + off0;
+          const uint32_t abase = smem_u32(base + S::OFF_ABUF + red_cur * S::OUT_BYTES) + off0;
+          const int c16 = (c & 63) >> 3;
+          const int r_begin = grp * ROWS_PER_GROUP;
+#pragma unroll 8
+          for (int rr = 0; rr < ROWS_PER_GROUP; ++rr) {
+            const int r_ = r_begin + rr;
+            if ((h0 + r_ / TILE_W_ < ep.H) && (w0 + r_ % TILE_W_ < ep.W)) {   // warp-uniform
+              const uint32_t o = r_ * 128 + ((c16 ^ (r_ & 7)) << 4);
+              uint32_t u, v;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(dybase + o));
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(abase + o));
+              const float d0 = __uint_as_float(u << 16), d1 = __uint_as_float(u & 0xffff0000u);
+              const float a0 = __uint_as_float(v << 16), a1 = __uint_as_float(v & 0xffff0000u);
+              s0 += d0;
+              s1 += d1;
+              q0 = fmaf(d0, a0 - m0, q0);
+              q1 = fmaf(d1, a1 - m1, q1);
+            }
+          }
+        }
+      }
+      if (RED == 2) red_cur ^= 1;
+    }
     if (last) {
       as ^= 1;
       if (as == 0) aphase ^= 1;
@@ -165,6 +269,27 @@ struct Epilogue {
   // after the last tile: drain stores, write this CTA's partial statistics row
   __device__ __forceinline__ void finish(int n_tile, int stats_row) {
     if (et == 0) tma_store_wait_all0();
+    if (RED) {
+      float* st = reinterpret_cast<float*>(base + S::OFF_STAT);     // [ROW_GROUPS][2][BLOCK_N]
+      const int pair = et % PAIRS, grp = et / PAIRS;
+      named_bar_sync(1, EPI_THREADS);
+      st[(grp * 2 + 0) * BLOCK_N + 2 * pair] = s0;
+      st[(grp * 2 + 0) * BLOCK_N + 2 * pair + 1] = s1;
+      st[(grp * 2 + 1) * BLOCK_N + 2 * pair] = q0;
+      st[(grp * 2 + 1) * BLOCK_N + 2 * pair + 1] = q1;
+      named_bar_sync(1, EPI_THREADS);
+      for (int i = et; i < 2 * BLOCK_N; i += EPI_THREADS) {
+        const int which = i / BLOCK_N, c = i % BLOCK_N;
+        const int gcol = n_tile * BLOCK_N + c - ep.red_blk_begin * 64;
+        if (gcol < 0 || gcol >= ep.red_ncols) continue;
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < ROW_GROUPS; ++g) t += st[(g * 2 + which) * BLOCK_N + c];
+        if (which) t *= ep.red_rstd[gcol];
+        ep.red_out[((size_t)stats_row * 2 + which) * ep.red_ncols + gcol] = t;
+      }
+      return;
+    }
     if (ep.stats) {
       float* st = reinterpret_cast<float*>(base + S::OFF_STAT);     // [ROW_GROUPS][2][BLOCK_N]
       const int pair = et % PAIRS, grp = et / PAIRS;

@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(TPB) conv_first_wgrad_strip_kernel(const float* __restrict__ x, const T* __restrict__ dz,
+__global__ void __launch_bounds__(TPB, 2) conv_first_wgrad_strip_kernel(const float* __restrict__ x, const T* __restrict__ dz,
                                                                      float* __restrict__ partial, int N, int H, int W, int CIN) {
   __shared__ float red[TPB * 8];
   const int ci = blockIdx.y;

@@ -43,6 +43,7 @@ struct Conv3Params {
   CUtensorMap a_map[2];
   CUtensorMap b_map;
   CUtensorMap o_map[2];
+  CUtensorMap red_map;       // RED: saved activation `a` of the BatchNorm'd tensor this dgrad writes the gradient of
   int nsrc;
   int cblk[2];
   int cblk_total;
@@ -56,9 +57,9 @@ struct Conv3Params {
   const void* w_base;        // host-side only: weight matrix [ncols][9 * Cin] for the tensor map
 };
 
-template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED>
 struct C3Smem {
-  using E = EpiSmem<BLOCK_N, OUT_BUFS>;
+  using E = EpiSmem<BLOCK_N, OUT_BUFS, RED>;
   using P = Patch<MT>;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int OFF_B = A_STAGES * P::STRIDE;
@@ -72,9 +73,9 @@ struct C3Smem {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
 };
 
-template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED>
 __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid_constant__ Conv3Params p) {
-  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS>;
+  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED>;
   using PT = Patch<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
     tma_prefetch_desc(&p.o_map[0]);
+    if (RED) tma_prefetch_desc(&p.red_map);
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(&afull[s], 1);
       mbar_init(&aempty[s], 1);
@@ -207,7 +209,8 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
     __syncwarp();
   } else {
     // ================= epilogue (8 warps, epilogue.cuh) =================
-    Epilogue<BLOCK_N, OUT_BUFS, TW> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    Epilogue<BLOCK_N, OUT_BUFS, TW, RED> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    epi.red_map = &p.red_map;
     epi.load_vectors(n_tile);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
@@ -218,11 +221,26 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < MT; ++j) {
         const int wj = w0 + j * TW;
+        // RED == 2: the part after this one (its `a` tile is prefetched now)
+        bool has_next = false;
+        int nh0 = h0, nw0 = wj + TW, nimg = img;
+        if (RED == 2) {
+          if (j + 1 < MT) {
+            has_next = true;
+          } else if (tile + (int)gridDim.x < p.total_tiles) {
+            const int nm = (tile + (int)gridDim.x) / p.n_tiles;
+            nimg = nm / tiles_per_img;
+            const int nrem = nm - nimg * tiles_per_img;
+            nh0 = (nrem / p.tiles_w) * TH;
+            nw0 = (nrem % p.tiles_w) * PT::TWS;
+            has_next = true;
+          }
+        }
         epi.tile(h0, wj, [&](const uint8_t* blk, int b) {
           const int jb = n_tile * (BLOCK_N / 64) + b;
           const int map = jb / p.blocks_per_omap;
           tma_store_4d(&p.o_map[map], blk, (jb - map * p.blocks_per_omap) * 64, wj, h0, img);
-        }, j * BLOCK_N, j == 0, j == MT - 1, L::STAGE_COLS);
+        }, j * BLOCK_N, j == 0, j == MT - 1, L::STAGE_COLS, img, has_next, nh0, nw0, nimg);
       }
     }
     epi.finish(n_tile, blockIdx.x / p.n_tiles);
@@ -236,12 +254,12 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
   }
 }
 
-template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED = 0>
 int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream) {
-  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS>;
+  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED>;
   using PT = Patch<MT>;
   static_assert(L::TOTAL <= 232448, "smem budget");
-  auto kern = conv3_kernel<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS>;
+  auto kern = conv3_kernel<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED>;
   static bool attr_done = false;
   if (!attr_done) {
     UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -267,6 +285,7 @@ int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_
   if (grid > total) grid = total;            // total is a multiple of n_tiles
   UB_CHECK_SHAPE(grid / p.n_tiles <= UB_STATS_ROWS, "conv3: stats rows");
   if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  if (RED) UB_CUDA(cudaMemsetAsync(p.ep.red_out, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ep.red_ncols, stream));
   kern<<<(int)grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);
   UB_LAUNCH_CHECK();
   return UB_OK;
@@ -287,6 +306,11 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
     if (p.ncols % 256 == 0) return launch_c3<256, 1, 2, 3, 1>(p, a_base, a_ch, n_img, stream);
     if (p.ncols % 128 == 0) return launch_c3<128, 1, 2, 6, 2>(p, a_base, a_ch, n_img, stream);
     return launch_c3<64, 1, 2, 18, 2>(p, a_base, a_ch, n_img, stream);
+  }
+  if (p.ep.red_out) {          // dgrad fused with the backward-BatchNorm reduction of the tensor it differentiates
+    if (p.ncols % 128 == 0) return launch_c3<128, 2, 2, 4, 1, 1>(p, a_base, a_ch, n_img, stream);
+    if (p.cblk_total == 1) return launch_c3<64, 2, 2, 9, 2, 2>(p, a_base, a_ch, n_img, stream);       // room for two `a` buffers: prefetch
+    return launch_c3<64, 1, 2, 18, 1, 1>(p, a_base, a_ch, n_img, stream);
   }
   if (p.ncols % 128 == 0) return launch_c3<128, 2, 2, 4, 2>(p, a_base, a_ch, n_img, stream);       // 256 pixels x 128 columns
   if (p.cblk_total == 1) return launch_c3<64, 2, 2, 9, 2>(p, a_base, a_ch, n_img, stream);         // 64 -> 64: weights resident, 256-pixel super-tiles
@@ -325,7 +349,7 @@ int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void
 }
 
 int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
-                        cudaStream_t stream) {
+                        const void* red_a, const float* red_mean, const float* red_rstd, float* red_partial, cudaStream_t stream) {
   Conv3Params p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -340,5 +364,15 @@ int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, in
   p.W = p.ep.W = W;
   p.blocks_per_omap = C0 / 64;
   p.ncols = C0 + C1;
+  if (red_partial) {
+    // the BatchNorm'd tensor is the LAST output (dx1 of a concat dgrad, else dx0)
+    const int cred = C1 > 0 ? C1 : C0;
+    if ((rc = out_map(&p.red_map, red_a, cred, W, H, N))) return rc;
+    p.ep.red_mean = red_mean;
+    p.ep.red_rstd = red_rstd;
+    p.ep.red_out = red_partial;
+    p.ep.red_blk_begin = C1 > 0 ? C0 / 64 : 0;
+    p.ep.red_ncols = cred;
+  }
   return launch(p, a_base, a_ch, N, stream);
 }

@@ -253,7 +253,7 @@ int strided_map(CUtensorMap* m, const void* base, int C, int w, int h, int N, in
 int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* post_scale,
                       const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream);
 int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
-                        cudaStream_t stream);
+                        const void* red_a, const float* red_mean, const float* red_rstd, float* red_partial, cudaStream_t stream);
 static bool legacy_conv3() {
   static int v = -1;
   if (v < 0) {
@@ -315,7 +315,7 @@ int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C
   UB_CHECK_ARG(dz && w_t && dx0, "conv3x3_dgrad: null pointer");
   UB_CHECK_SHAPE(Cout % 64 == 0 && C0 % 64 == 0 && C0 > 0 && (C1 == 0 || (C1 == C0 && dx1)),
                  "conv3x3_dgrad: channels must be multiples of 64 and split halves equal (Cout=%d C0=%d C1=%d)", Cout, C0, C1);
-  if (!legacy_conv3()) return ub_conv3_halo_dgrad(dz, Cout, w_t, dx0, C0, dx1, C1, N, H, W, stream);
+  if (!legacy_conv3()) return ub_conv3_halo_dgrad(dz, Cout, w_t, dx0, C0, dx1, C1, N, H, W, nullptr, nullptr, nullptr, nullptr, stream);
   IgemmFwdParams p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -341,6 +341,16 @@ int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C
 
 static int deconv_fwd_impl(const void* x, int Cin, const void* w, const float* bias, const float* scale, const float* shift, void* out,
                            float* stats, int N, int h, int wd, int Cout, cudaStream_t stream);
+
+/* dgrad fused with the backward-BatchNorm reduction of the tensor whose gradient it writes (the last output: dx1 of a
+ * concat dgrad, else dx0): partial[UB_STATS_ROWS][2][C] = {sum dy, rstd * sum dy * (a - mean)} -- replaces ub_bn_bwd_reduce */
+int ub_conv3x3_dgrad_bnred(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
+                           const void* a, const float* mean, const float* rstd, float* partial, cudaStream_t stream) {
+  UB_CHECK_ARG(dz && w_t && dx0 && a && mean && rstd && partial, "conv3x3_dgrad_bnred: null pointer");
+  UB_CHECK_SHAPE(Cout % 64 == 0 && C0 % 64 == 0 && C0 > 0 && (C1 == 0 || (C1 == C0 && dx1)),
+                 "conv3x3_dgrad_bnred: channels must be multiples of 64 and split halves equal (Cout=%d C0=%d C1=%d)", Cout, C0, C1);
+  return ub_conv3_halo_dgrad(dz, Cout, w_t, dx0, C0, dx1, C1, N, H, W, a, mean, rstd, partial, stream);
+}
 
 int ub_deconv2x2_fwd(const void* x, int Cin, const void* w, const float* bias, void* out, float* stats, int N, int h,
                      int wd, int Cout, cudaStream_t stream) {

@@ -70,6 +70,7 @@ class UNet:
         self._cur = ""                    # layer the current launches belong to (profiling tag)
         self._buf = {}
         self._inference_stale = True
+        self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
         self._build_layout()
         self.class_weights = None
         if class_weights is not None:
@@ -154,6 +155,8 @@ class UNet:
         self.WT = {n: torch.zeros(L.n_w, dtype=wt_dtype, device=dev) for n, L in self.layers.items() if L.kind in ("conv", "deconv")}
         self.metrics = torch.zeros(2, dtype=torch.float32, device=dev)    # [loss, accuracy] of the last step
         self.partial = torch.zeros(_C.UB_STATS_ROWS * 2 * 2048, dtype=torch.float32, device=dev)
+        self.partial_red = torch.zeros(_C.UB_STATS_ROWS * 2 * 1024, dtype=torch.float32, device=dev)   # BN-backward sums produced by a fused dgrad
+        self._red_ready = None                                                                          # layer whose sums partial_red holds
         self.red = torch.zeros(4096, dtype=torch.float32, device=dev)
 
     def trainable_count(self):
@@ -527,24 +530,38 @@ class UNet:
         g, a = self._b("g:" + L.name), self._b("a:" + L.name)
         mean, rstd = self._bn_vectors(L, True)
         C, M = L.cout, N * h * w
-        self._call("ub_bn_bwd_reduce", g, a, mean, rstd, self.partial, M, C, self.act_code)
+        if self._red_ready == L.name:          # the dgrad that produced g already accumulated [sum dy | sum dy*xhat]
+            src = self.partial_red
+        else:
+            self._call("ub_bn_bwd_reduce", g, a, mean, rstd, self.partial, M, C, self.act_code)
+            src = self.partial
+        self._red_ready = None
         # [sum dy | sum dy*xhat] lands directly in the flat gradient buffer: beta and gamma segments are adjacent
         assert L.off_gamma == L.off_beta + C
-        self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2 * C, 2 * C, self.G[L.off_beta:L.off_beta + 2 * C], 1.0)
+        self._call("ub_reduce_rows", src, _C.UB_STATS_ROWS, 2 * C, 2 * C, self.G[L.off_beta:L.off_beta + 2 * C], 1.0)
         dbeta, dgamma = self.G[L.off_beta:L.off_beta + C], self.G[L.off_gamma:L.off_gamma + C]
         self._call("ub_bn_bwd_apply", g, a, mean, rstd, self.P[L.off_gamma:L.off_gamma + C], dbeta, dgamma, g, self.partial, M, C,
                    relu, self.act_code)
         self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, C, C, self.G[L.off_b:L.off_b + C], 1.0)
         return g
 
-    def _conv_bwd(self, L, x0, x1, N, h, w, dx0, dx1):
+    def _conv_bwd(self, L, x0, x1, N, h, w, dx0, dx1, red=None):
+        """red: the BatchNorm'd layer whose dL/dy this conv's dgrad writes last (dx1 of a concat, else dx0): its backward
+        sums are accumulated in the dgrad epilogue instead of a separate pass over dy and a (bf16 path)"""
         dz = self._bn_bwd(L, N, h, w, 1)
         dw = self.G[L.off_w:L.off_w + L.n_w]
         c0, c1 = L.c0, L.c1
         if self.precision == "bf16":
             ws = self._b("wgrad_ws")
             self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
-            if dx0 is not None:
+            # worth it only where the K loop is long enough to hide the longer epilogue (measured: 64-output-channel layers,
+            # whose dgrad has a single 64-channel K block, lose more in the dgrad than the separate reduction pass costs)
+            if dx0 is not None and red is not None and self.fuse_bn_reduce and L.cout >= 128:
+                rm, rr = self._bn_vectors(red, True)
+                self._call("ub_conv3x3_dgrad_bnred", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w, self._b("a:" + red.name), rm, rr,
+                           self.partial_red)
+                self._red_ready = red.name
+            elif dx0 is not None:
                 self._call("ub_conv3x3_dgrad", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w)
         else:
             self._call("ub_check_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, N, h, w)
@@ -577,9 +594,9 @@ class UNet:
             h, w = self._dims(H, W, lvl)
             hi, wi = self._dims(H, W, lvl + 1)
             La, Lb, Lu = Ls[f"dec{lvl}a"], Ls[f"dec{lvl}b"], Ls[f"up{lvl}"]
-            self._conv_bwd(Lb, self._b("y:" + La.name), None, N, h, w, self._b("g:" + La.name), None)
+            self._conv_bwd(Lb, self._b("y:" + La.name), None, N, h, w, self._b("g:" + La.name), None, red=La)
             done(Lb.name)
-            self._conv_bwd(La, self._b(f"y:enc{lvl}b"), self._b("y:" + Lu.name), N, h, w, self._b(f"gskip{lvl}"), self._b("g:" + Lu.name))
+            self._conv_bwd(La, self._b(f"y:enc{lvl}b"), self._b("y:" + Lu.name), N, h, w, self._b(f"gskip{lvl}"), self._b("g:" + Lu.name), red=Lu)
             done(La.name)
             prev = Ls[f"dec{lvl + 1}b"] if lvl < 4 else Ls["botb"]
             dz = self._bn_bwd(Lu, N, h, w, 0)
@@ -599,7 +616,7 @@ class UNet:
         if "dropb" in dm:
             g = self._b("g:botb")
             self._call("ub_dropout_bwd", g, dm["dropb"], g, N * h * w * Lb.cout, self.act_code)
-        self._conv_bwd(Lb, self._b("y:bota"), None, N, h, w, self._b("g:bota"), None)
+        self._conv_bwd(Lb, self._b("y:bota"), None, N, h, w, self._b("g:bota"), None, red=La)
         done("botb")
         self._conv_bwd(La, self._b("pool4"), None, N, h, w, self._b("gpool4"), None)
         done("bota")
@@ -609,7 +626,7 @@ class UNet:
             La, Lb = Ls[f"enc{lvl}a"], Ls[f"enc{lvl}b"]
             self._call("ub_maxpool2x2_bwd_add", self._b(f"gpool{lvl}"), self._b(f"idx{lvl}"), self._b(f"gskip{lvl}"),
                        dm.get("drop4") if lvl == 4 else None, self._b("g:" + Lb.name), N, h, w, Lb.cout, self.act_code)
-            self._conv_bwd(Lb, self._b("y:" + La.name), None, N, h, w, self._b("g:" + La.name), None)
+            self._conv_bwd(Lb, self._b("y:" + La.name), None, N, h, w, self._b("g:" + La.name), None, red=La)
             done(Lb.name)
             if lvl > 1:
                 self._conv_bwd(La, self._b(f"pool{lvl - 1}"), None, N, h, w, self._b(f"gpool{lvl - 1}"), None)

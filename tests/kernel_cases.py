@@ -105,6 +105,39 @@ def case_conv3x3_dgrad(Cout=64, C0=64, C1=0, N=2, H=24, W=40, seed=1):
     return dict(err=e, ok=bool(e < 1e-2 and np.isfinite(got).all()))
 
 
+def case_conv3x3_dgrad_bnred(Cout=64, C0=64, C1=0, N=2, H=24, W=40, seed=12):
+    """dgrad fused with the backward-BatchNorm reduction of its (last) output against the numpy oracle's bn_bwd sums"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    Cin = C0 + C1
+    Cr = C1 if C1 else C0
+    dz = bf16_round(rng.normal(size=(N, H, W, Cout)))
+    w = bf16_round(rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cout))
+    a = bf16_round(np.maximum(rng.normal(0.3, 1.0, size=(N, H, W, Cr)), 0))
+    mean = a.mean((0, 1, 2)).astype(np.float32)
+    rstd = (1.0 / np.sqrt(a.var((0, 1, 2)) + 1e-3)).astype(np.float32)
+    ref = ON.conv_dgrad(dz, w)
+    wp = dev(pack_conv(w), torch.float32)
+    wt = torch.empty(Cin * 9 * Cout, dtype=torch.bfloat16, device="cuda")
+    C.call("ub_transpose_pack", wp, wt, Cout, 9, Cin, 1, 0, C.UB_BF16, stream())
+    dx0 = torch.full((N, H, W, C0), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dx1 = torch.full((N, H, W, C1), float("nan"), dtype=torch.bfloat16, device="cuda") if C1 else None
+    partial = torch.full((C.UB_STATS_ROWS * 2 * Cr,), float("nan"), dtype=torch.float32, device="cuda")
+    C.call("ub_conv3x3_dgrad_bnred", dev(dz, torch.bfloat16), Cout, wt, dx0, C0, dx1, C1, N, H, W, dev(a, torch.bfloat16), dev(mean, torch.float32),
+           dev(rstd, torch.float32), partial, stream())
+    torch.cuda.synchronize()
+    got = dx0.double().cpu().numpy()
+    if C1:
+        got = np.concatenate([got, dx1.double().cpu().numpy()], -1)
+    e = rel_err(got, ref)
+    dy = got[..., Cin - Cr:]                                  # the stored (bf16) gradient, as bn_bwd_apply will read it
+    s, q = stats_from_partial(partial, Cr)
+    s_ref = dy.sum((0, 1, 2))
+    q_ref = (dy * (a - mean.astype(np.float64))).sum((0, 1, 2)) * rstd.astype(np.float64)
+    es, eq = rel_err(s, s_ref), rel_err(q, q_ref)
+    return dict(err=e, err_sum=es, err_q=eq, ok=bool(e < 1e-2 and es < 1e-4 and eq < 1e-4 and np.isfinite(got).all()))
+
+
 def case_conv3x3_wgrad(C0=64, C1=0, Cout=64, N=2, H=24, W=40, seed=2):
     C = _C()
     rng = np.random.default_rng(seed)
@@ -467,6 +500,12 @@ CASES = {
     "conv_dgrad_64_64": lambda: case_conv3x3_dgrad(64, 64, 0),
     "conv_dgrad_split_128": lambda: case_conv3x3_dgrad(128, 64, 64),
     "conv_dgrad_256_512": lambda: case_conv3x3_dgrad(256, 512, 0, H=8, W=16),
+    "conv_dgrad_bnred_64_64": lambda: case_conv3x3_dgrad_bnred(64, 64, 0),
+    "conv_dgrad_bnred_128_64": lambda: case_conv3x3_dgrad_bnred(128, 64, 0, H=20, W=13),
+    "conv_dgrad_bnred_128_128": lambda: case_conv3x3_dgrad_bnred(128, 128, 0, N=1, H=40, W=24),
+    "conv_dgrad_bnred_256_512": lambda: case_conv3x3_dgrad_bnred(256, 512, 0, N=1, H=8, W=16),
+    "conv_dgrad_bnred_cat_64+64": lambda: case_conv3x3_dgrad_bnred(64, 64, 64, H=18, W=20),
+    "conv_dgrad_bnred_cat_128+128": lambda: case_conv3x3_dgrad_bnred(128, 128, 128, N=1, H=16, W=32),
     "conv_wgrad_64_64": lambda: case_conv3x3_wgrad(64, 0, 64),
     "conv_wgrad_cat_64+64_128": lambda: case_conv3x3_wgrad(64, 64, 128),
     "conv_wgrad_128_256": lambda: case_conv3x3_wgrad(128, 0, 256, H=16, W=16),
