@@ -25,11 +25,27 @@ sys.path.insert(0, ROOT)
 BATCH, CH, HW, CLASSES = 16, 1, 512, 2
 METRIC = "unet512_train_images_per_sec"
 WORKLOAD = "config2: UNet synthetic 1ch 512x512, 2 classes, batch 16/GPU, fwd+bwd+Adam"
+CLASS_WEIGHTS = None
+
+
+def select_workload(name):
+    """config2 (default, the metric's configuration) or config4 (BASELINE.json configs[3]: 3-channel uint8-like 1024x1024 tiles,
+    8 classes, class-weighted softmax-CE, 4 images per GPU = the same pixels per step)"""
+    global BATCH, CH, HW, CLASSES, METRIC, WORKLOAD, CLASS_WEIGHTS
+    if name == "config4":
+        BATCH, CH, HW, CLASSES = 4, 3, 1024, 8
+        METRIC = "unet1024_train_images_per_sec"
+        WORKLOAD = "config4: UNet synthetic 3ch 1024x1024, 8 classes, class-weighted CE, batch 4/GPU, fwd+bwd+Adam"
+        CLASS_WEIGHTS = [0.5, 1.0, 1.5, 2.0, 0.75, 1.25, 1.75, 0.9]
 
 
 # ---------------------------------------------------------------------------------------------- algorithmic work
-def layer_flops(nc=CH, K=CLASSES, H=HW, W=HW, b=64):
+def layer_flops(nc=None, K=None, H=None, W=None, b=64):
     """per-image dense-MAC FLOPs per layer: name -> (kind, fwd_flops)"""
+    nc = CH if nc is None else nc
+    K = CLASSES if K is None else K
+    H = HW if H is None else H
+    W = HW if W is None else W
     out = {}
     lv = lambda l: (H >> (l - 1)) * (W >> (l - 1))
     enc = [("enc1a", nc, b, 1), ("enc1b", b, b, 1), ("enc2a", b, 2 * b, 2), ("enc2b", 2 * b, 2 * b, 2), ("enc3a", 2 * b, 4 * b, 3),
@@ -45,7 +61,8 @@ def layer_flops(nc=CH, K=CLASSES, H=HW, W=HW, b=64):
     return out
 
 
-def step_flops(batch=BATCH, **kw):
+def step_flops(batch=None, **kw):
+    batch = BATCH if batch is None else batch
     fl = layer_flops(**kw)
     fwd = sum(v for _, v in fl.values())
     train = 3 * fwd - fl["enc1a"][1]            # no dgrad for the first layer
@@ -56,7 +73,7 @@ def step_flops(batch=BATCH, **kw):
     return batch * fwd, batch * train, fam
 
 
-FAMILY = {"ub_conv3x3_fwd": "igemm_fwd", "ub_conv3x3_dgrad": "igemm_fwd", "ub_deconv2x2_fwd": "igemm_fwd", "ub_deconv2x2_dgrad": "igemm_fwd",
+FAMILY = {"ub_conv3x3_fwd": "igemm_fwd", "ub_conv3x3_dgrad": "igemm_fwd", "ub_conv3x3_dgrad_bnred": "igemm_fwd", "ub_deconv2x2_fwd": "igemm_fwd", "ub_deconv2x2_dgrad": "igemm_fwd",
           "ub_conv3x3_wgrad": "igemm_wgrad", "ub_deconv2x2_wgrad": "igemm_wgrad"}
 
 
@@ -114,8 +131,12 @@ def synthetic_host_batches(nbatches, seed):
         mu = img.mean(axis=(2, 3), keepdims=True)
         sd = img.std(axis=(2, 3), keepdims=True)
         xs.append(((img - mu) / np.where(sd <= 1.0, 1.0, sd)).astype(np.float32))
-        f = gaussian_filter(rng.normal(size=(BATCH, HW, HW)).astype(np.float32), sigma=(0, 4, 4))
-        ls.append((f > np.quantile(f, 0.71)).astype(np.uint8))
+        if CLASSES == 2:
+            f = gaussian_filter(rng.normal(size=(BATCH, HW, HW)).astype(np.float32), sigma=(0, 4, 4))
+            ls.append((f > np.quantile(f, 0.71)).astype(np.uint8))
+        else:          # argmax of K smoothed noise fields
+            f = gaussian_filter(rng.normal(size=(BATCH, CLASSES, HW, HW)).astype(np.float32), sigma=(0, 0, 4, 4))
+            ls.append(f.argmax(1).astype(np.uint8))
     return xs, ls
 
 
@@ -198,7 +219,8 @@ def run_cuda(args):
     local = dp.local_rank if dp else 0
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    model = UNet(CLASSES, BATCH * world, CH, learning_rate=3e-4 / 10, precision="bf16", seed=0, dist=dp)   # warm-up LR (train.py:129)
+    model = UNet(CLASSES, BATCH * world, CH, learning_rate=3e-4 / 10, precision="bf16", seed=0, dist=dp,   # warm-up LR (train.py:129)
+                 class_weights=CLASS_WEIGHTS)
     if dp:
         dp.broadcast_params(model)
 
@@ -332,7 +354,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", default=None, help="write a per-layer / per-entry-point timing table (JSON) to this path")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4"])
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3
     if args.impl == "reference":
