@@ -208,7 +208,10 @@ def write_layer_table(path, layer_ms):
 
 # ---------------------------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from unetb200.dist import DataParallel
     from unetb200.model import UNet
@@ -341,7 +344,7 @@ def run_cuda(args):
         "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
         "final_loss": final_loss,
     }
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dp:
         dp.shutdown()
 

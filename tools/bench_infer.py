@@ -25,7 +25,9 @@ def main():
     ap.add_argument("--tile-batch", type=int, default=4)
     ap.add_argument("--classes", type=int, default=2)
     args = ap.parse_args()
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    json_fd = os.dup(1)          # stdout carries exactly one JSON line (NCCL prints its banner to fd 1)
+    os.dup2(2, 1)
     import torch
     import unetb200.inference as I
     from unetb200.dist import DataParallel
@@ -78,10 +80,10 @@ def main():
     if rank == 0:
         # forward FLOPs actually executed: tiles incl. halo (1.467776 MFLOP/pixel at Cin = 1, K = 2)
         px_exec = sum((tl["y1"] - tl["y0"]) * (tl["x1"] - tl["x0"]) for tl in I.tile_plan(S + pad_y, S + pad_x, I.TILE_SIZE, 96)) if S > I.TILE_SIZE else S * S
-        print(json.dumps({"metric": "unet_tiled_inference_mpix_per_sec", "value": S * S / secs / 1e6, "unit": "MPix/s", "n_gpus": world,
+        os.write(json_fd, (json.dumps({"metric": "unet_tiled_inference_mpix_per_sec", "value": S * S / secs / 1e6, "unit": "MPix/s", "n_gpus": world,
                           "image": [S, S], "tiles": ntiles, "tile_batch": args.tile_batch, "seconds": secs,
                           "exec_tflops": px_exec * 1.467776e6 / secs / 1e12, "foreground_fraction": float((out_host.numpy() == 1).mean()),
-                          "h2d_bytes": int(host.numel() * 2), "d2h_bytes": int(out_host.numel())}), flush=True)
+                          "h2d_bytes": int(host.numel() * 2), "d2h_bytes": int(out_host.numel())}) + "\n").encode())
     if dp:
         dp.shutdown()
 
