@@ -79,6 +79,8 @@ int ub_conv_first_fwd(const float* x_nchw, const float* w, const float* bias, vo
 /* partial scratch: UB_STATS_ROWS * Cin * 9 * 64 floats */
 int ub_conv_first_wgrad(const float* x_nchw, const void* dz, float* dw, float* partial, int N, int H, int W, int Cin, int dtype,
                         cudaStream_t stream);
+/* gradient w.r.t. the fp32 NCHW network input (tape.gradient(loss, img) of UNet.estimate_radius, UNet/model.py:186) */
+int ub_conv_first_dgrad(const void* dz, const float* w, float* dx_nchw, int N, int H, int W, int Cin, int dtype, cudaStream_t stream);
 /* 1x1 Conv2D(relu) 64 -> K classes -- UNet/model.py:136.  a_out fp32 [P][K]; partial [UB_STATS_ROWS][2][K]. */
 int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, float* partial, long long P, int K, int dtype,
                 cudaStream_t stream);

@@ -283,6 +283,34 @@ __global__ void __launch_bounds__(TPB, 2) conv_first_wgrad_strip_kernel(const fl
   }
 }
 
+// dx[n][ci][h][w] = sum_{tap, co} dz[(h, w) - shift(tap)][co] * w[co][tap][ci]   (gradient w.r.t. the network input; only
+// UNet.estimate_radius needs it -- training never differentiates the image).  One thread per input pixel and channel.
+template <typename T>
+__global__ void __launch_bounds__(TPB) conv_first_dgrad_kernel(const T* __restrict__ dz, const float* __restrict__ w, float* __restrict__ dx,
+                                                               int N, int H, int W, int CIN) {
+  const long long total = (long long)N * CIN * H * W;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
+    const int wv = (int)(i % W);
+    long long t = i / W;
+    const int h = (int)(t % H); t /= H;
+    const int ci = (int)(t % CIN);
+    const int n = (int)(t / CIN);
+    float acc = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h - (tap / 3 - 1), ww = wv - (tap % 3 - 1);       // output pixel that read this input through `tap`
+      if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+      const T* d = dz + (((long long)n * H + hh) * W + ww) * 64;
+      for (int c8 = 0; c8 < 8; ++c8) {
+        float f[8];
+        ld8<T>(d + c8 * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += f[k] * w[((c8 * 8 + k) * 9 + tap) * CIN + ci];
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
 // dW partial[row][ci][tap][64] = sum_p dz[p][co] * x[p + tap][ci]   (blockIdx.y = ci)
 template <typename T>
 __global__ void __launch_bounds__(TPB) conv_first_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dz, float* __restrict__ partial,
@@ -756,6 +784,15 @@ int ub_conv_first_wgrad(const float* x_nchw, const void* dz, float* dw, float* p
     UB_DISPATCH_T(dtype, (conv_first_wgrad_kernel<T><<<grid, TPB, 0, stream>>>(x_nchw, (const T*)dz, partial, N, H, W, Cin)));
   UB_LAUNCH_CHECK();
   conv_first_wgrad_finalize_kernel<<<(64 * 9 * Cin + 127) / 128, 128, 0, stream>>>(partial, dw, rows, Cin);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_conv_first_dgrad(const void* dz, const float* w, float* dx_nchw, int N, int H, int W, int Cin, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(dz && w && dx_nchw, "conv_first_dgrad: null pointer");
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4 && N > 0 && H > 0 && W > 0, "conv_first_dgrad: bad shape");
+  const long long total = (long long)N * Cin * H * W;
+  UB_DISPATCH_T(dtype, (conv_first_dgrad_kernel<T><<<grid_for(total, TPB, ub_num_sms() * 8), TPB, 0, stream>>>((const T*)dz, w, dx_nchw, N, H, W, Cin)));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

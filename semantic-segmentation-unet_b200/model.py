@@ -70,6 +70,7 @@ class UNet:
         self._cur = ""                    # layer the current launches belong to (profiling tag)
         self._buf = {}
         self._inference_stale = True
+        self._radius_cache = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
         self._build_layout()
         self.class_weights = None
@@ -195,6 +196,7 @@ class UNet:
             self._call("ub_cast_bf16", self.P, self.S, self.n_flat)
         self._repack_dgrad()
         self._inference_stale = True
+        self._radius_cache = None
 
     def _repack_dgrad(self):
         code = self.act_code
@@ -286,11 +288,73 @@ class UNet:
     def get_keras_model(self):                           # UNet/model.py:148-149
         return self._model_call
 
-    def estimate_radius(self):
-        """UNet/model.py:160-202 derives the halo from the empirical receptive field of a noise image and rounds it
-        up to a multiple of 16; structurally that is 96 for this topology, which is what is returned.
-        (Deviation: the reference recomputes it per image from unseeded noise; see DESIGN.md.)"""
-        return UNet.RADIUS
+    @staticmethod
+    def _round_radius(x):
+        return int(UNet.SIZE_FACTOR * math.ceil(float(x) / UNet.SIZE_FACTOR))
+
+    def input_gradient(self, images, dlogits_fn):
+        """dL/d(images) of the inference-mode graph (training=False: moving statistics, no dropout) for a loss whose
+        gradient w.r.t. the softmax INPUT (the head's BatchNorm output) is dlogits_fn(softmax [N,H,W,K] numpy) -> numpy.
+        Runs on a private fp32 (check-mode) copy of this model: the reference differentiates in fp32 and thresholds the
+        result at 1e-8 (UNet/model.py:165-202)."""
+        m = UNet(self.number_classes, 1, self.number_channels, self.learning_rate, precision="fp32", device=self.device, seed=0)
+        m.P.copy_(self.P)
+        m.MM.copy_(self.MM)
+        m.MV.copy_(self.MV)
+        m._weights_changed()
+        x = m._prep_images(images)
+        N, _, H, W = x.shape
+        sm = m.forward_softmax(x, training=False)
+        dl = torch.as_tensor(np.ascontiguousarray(dlogits_fn(sm.cpu().numpy()), dtype=np.float32)).to(m.device)
+        m._ensure("dlogits", N * H * W * m.number_classes, torch.float32)[:dl.numel()].copy_(dl.reshape(-1))
+        m._alloc(N, H, W, True)            # gradient buffers (forward_softmax allocated the inference set only)
+        m._bwd_inference = True
+        dx = torch.zeros_like(x)
+        m._backward(x, N, H, W, None, input_grad=dx)
+        return dx
+
+    def estimate_radius(self, noise=None):
+        """UNet/model.py:160-202: empirical receptive field -- gradient of a mean-absolute-error loss that is non-zero only
+        at the centre pixel of a 192 x 192 noise image w.r.t. that image; radius = half the extent where |grad| > 1e-8,
+        rounded up to a multiple of 16 (falls back to RADIUS = 96).  The reference draws unseeded noise and runs ten
+        redundant forward passes (only the last tape is used); one pass is run here, `noise` may be injected for tests."""
+        Nn = 2 * UNet.RADIUS
+        if noise is None:
+            if self._radius_cache is not None:      # same weights -> same receptive field: estimated once per weight state
+                return self._radius_cache           # (the reference re-estimates it for every image, inference.py:54)
+            noise = np.random.normal(size=(1, self.number_channels, Nn, Nn))
+            cache = True
+        else:
+            cache = False
+        mid = int(Nn / 2)
+        K = self.number_classes
+
+        def dlogits(sm):
+            # loss = sum_pixels mean_k |msk - sm|, msk = sm except 1 - sm at the centre: only the centre pixel contributes
+            p = sm[0, mid, mid].astype(np.float64)
+            dsm = -np.sign((1.0 - p) - p) / K                      # d loss / d softmax_k at the centre
+            dy = p * (dsm - float((dsm * p).sum()))                # through the softmax Jacobian
+            out = np.zeros(sm.shape, dtype=np.float32)
+            out[0, mid, mid] = dy
+            return out
+
+        g = self.input_gradient(np.asarray(noise, dtype=np.float32), dlogits)
+        grad_img = np.abs(g[0].cpu().numpy())
+        grad_img = np.average(grad_img, axis=0) if self.number_channels > 1 else grad_img.squeeze()
+        print('Theoretical RF: {}'.format(UNet.RADIUS))
+        vec = np.maximum(np.max(grad_img, axis=0).squeeze(), np.max(grad_img, axis=1).squeeze())
+        idx = np.nonzero(vec > 1e-8)[0]
+        if len(idx) < 2:
+            radius = UNet.RADIUS
+            print('ERF based radius detection failed, defaulting to theoretical radius: {}'.format(radius))
+        else:
+            erf = int((np.max(idx) - np.min(idx)) / 2)
+            radius = UNet._round_radius(erf)
+            print('computed radius : "{}"'.format(radius))
+        self._last_erf_grad = grad_img
+        if cache:
+            self._radius_cache = radius
+        return radius
 
     # ------------------------------------------------------------------------------------------------ shapes
     def _dims(self, H, W, level):
@@ -528,8 +592,16 @@ class UNet:
         """g:<name> holds dL/dy on entry and dL/dz (pre-activation gradient) on exit; fills dgamma/dbeta/dbias in G"""
         self._cur = L.name
         g, a = self._b("g:" + L.name), self._b("a:" + L.name)
-        mean, rstd = self._bn_vectors(L, True)
         C, M = L.cout, N * h * w
+        if getattr(self, "_bwd_inference", False):
+            # training=False: BatchNorm is a fixed affine map, dz = gamma * rstd_moving * dy * [a > 0] (zero batch-statistic terms)
+            mean, rstd = self._bn_vectors(L, False)
+            zero = self._ensure("zeros", 2048, torch.float32)
+            zero.zero_()
+            self._call("ub_bn_bwd_apply", g, a, mean, rstd, self.P[L.off_gamma:L.off_gamma + C], zero[:C], zero[:C], g, self.partial, M, C,
+                       relu, self.act_code)
+            return g
+        mean, rstd = self._bn_vectors(L, True)
         if self._red_ready == L.name:          # the dgrad that produced g already accumulated [sum dy | sum dy*xhat]
             src = self.partial_red
         else:
@@ -568,21 +640,26 @@ class UNet:
             if dx0 is not None:
                 self._call("ub_check_conv3x3", dz, L.cout, None, 0, self.WT[L.name], None, dx0, c0, dx1, c1, N, h, w, 0)
 
-    def _backward(self, x, N, H, W, drop_masks=None, on_layer_done=None):
+    def _backward(self, x, N, H, W, drop_masks=None, on_layer_done=None, input_grad=None):
         Ls = self.layers
         dm = drop_masks or {}
         K = self.number_classes
         P = N * H * W
         done = on_layer_done or (lambda name: None)
+        infer = getattr(self, "_bwd_inference", False)
         # ---- head: BN backward + relu mask + 1x1 dgrad/wgrad
         L = Ls["head"]
         self._cur = "head"
-        mean, rstd = self._bn_vectors(L, True)
+        mean, rstd = self._bn_vectors(L, not infer)
         dl, a = self._b("dlogits"), self._b("a:head")
-        self._call("ub_head_bwd_reduce", dl, a, mean, rstd, self.partial, P, K)
         dbeta, dgamma = self.G[L.off_beta:L.off_beta + K], self.G[L.off_gamma:L.off_gamma + K]
-        self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2 * K, K, dbeta, 1.0)
-        self._call("ub_reduce_rows", self.partial[K:], _C.UB_STATS_ROWS, 2 * K, K, dgamma, 1.0)
+        if infer:
+            dbeta.zero_()
+            dgamma.zero_()
+        else:
+            self._call("ub_head_bwd_reduce", dl, a, mean, rstd, self.partial, P, K)
+            self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2 * K, K, dbeta, 1.0)
+            self._call("ub_reduce_rows", self.partial[K:], _C.UB_STATS_ROWS, 2 * K, K, dgamma, 1.0)
         self._call("ub_head_bwd_apply", dl, a, self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
                    self.P[L.off_gamma:L.off_gamma + K], dbeta, dgamma, self._b("g:dec1b"), self.partial, P, K, self.act_code)
         ncomp = K * 64 + K
@@ -634,6 +711,9 @@ class UNet:
                 dz = self._bn_bwd(La, N, h, w, 1)
                 self._call("ub_conv_first_wgrad", x, dz, self.G[La.off_w:La.off_w + La.n_w], self._b("first_ws"), N, H, W,
                            self.number_channels, self.act_code)
+                if input_grad is not None:
+                    self._call("ub_conv_first_dgrad", dz, self.P[La.off_w:La.off_w + La.n_w], input_grad, N, H, W, self.number_channels,
+                               self.act_code)
             done(La.name)
 
     # ------------------------------------------------------------------------------------------------ optimizer
@@ -738,6 +818,7 @@ class UNet:
             self._adam()
             self._repack_dgrad()
             self._inference_stale = True
+            self._radius_cache = None
         loss = self.metrics[0]
         if loss_metric is not None:
             loss_metric.update_state(loss)

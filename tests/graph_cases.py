@@ -401,7 +401,35 @@ def case_train_driver():
     return r
 
 
+def case_estimate_radius(C=1, K=2, seed=41):
+    """UNet.estimate_radius (UNet/model.py:160-202): the input gradient of the inference-mode graph against the oracle's
+    autograd (fp64), and the radius derived from it"""
+    from unetb200.model import UNet
+    p = O.init_params(C, K, seed=seed, base=64, randomize_affine=True)
+    rng = np.random.default_rng(seed)
+    for k in p:
+        if k.endswith("moving_mean"):
+            p[k] = torch.tensor(rng.normal(0.2, 0.1, size=p[k].shape))
+        if k.endswith("moving_var"):
+            p[k] = torch.tensor(rng.uniform(0.5, 1.5, size=p[k].shape))
+    noise = rng.normal(size=(1, C, 192, 192))
+    m = UNet(K, 1, C, precision="bf16", seed=0)
+    m.load_oracle_params({k: v.numpy() for k, v in p.items()})
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        radius = m.estimate_radius(noise=noise)
+    ref_radius, ref_grad = O.estimate_radius(p, C, noise=noise)
+    got = m._last_erf_grad
+    r = dict(radius=int(radius), ref_radius=int(ref_radius), e_grad=rel(got, ref_grad),
+             support=[int((got.max(0) > 1e-8).sum()), int((ref_grad.max(0) > 1e-8).sum())])
+    r["ok"] = bool(radius == ref_radius and r["e_grad"] < 1e-3 and radius % 16 == 0)
+    return r
+
+
 CASES = {
+    "estimate_radius_c1": lambda: case_estimate_radius(1, 2, 41),
+    "estimate_radius_c3": lambda: case_estimate_radius(3, 4, 42),
     "train_driver": case_train_driver,
     "tiled_inference_bf16": lambda: case_tiled_inference("bf16"),
     "tiled_inference_fp32": lambda: case_tiled_inference("fp32"),
