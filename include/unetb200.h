@@ -151,6 +151,9 @@ int ub_dropout_mask(unsigned char* mask, long long n, unsigned long long seed, u
 /* Keras Adam (UNet/model.py:79, :223): theta -= lr_t * m / (sqrt(v) + eps); optional bf16 shadow copy of theta */
 int ub_adam(float* param, const float* grad, float* m, float* v, void* bf16_shadow, long long n, float lr_t, float beta1,
             float beta2, float eps, float grad_scale, cudaStream_t stream);
+/* same update with lr_t read from device memory at execution time (the step can then be replayed from a CUDA graph) */
+int ub_adam_dev(float* param, const float* grad, float* m, float* v, void* bf16_shadow, long long n, const float* lr_t_dev, float beta1,
+                float beta2, float eps, float grad_scale, cudaStream_t stream);
 /* dst[c][t'][r] = src(r,t,c) (t' = T-1-t when flip): builds the dgrad weight packs.
  * src_layout 0: src [R][T][C] (conv [Cout][tap][Cin]); 1: src [T][R][C] (deconv [(2a+b)][Cout][Cin]) */
 int ub_transpose_pack(const float* src, void* dst, int R, int T, int C, int flip, int src_layout, int dst_dtype,

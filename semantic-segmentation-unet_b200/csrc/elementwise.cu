@@ -456,8 +456,9 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(const T* __restric
 
 // ------------------------------------------------------------------ Adam (Keras formula)
 __global__ void __launch_bounds__(TPB) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                                   __nv_bfloat16* __restrict__ shadow, long long n, float lr_t, float b1, float b2, float eps,
-                                                   float gscale) {
+                                                   __nv_bfloat16* __restrict__ shadow, long long n, float lr_t, const float* __restrict__ lr_t_dev,
+                                                   float b1, float b2, float eps, float gscale) {
+  if (lr_t_dev) lr_t = *lr_t_dev;          // step-dependent scalar kept on the device so that a captured CUDA graph can be replayed
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n4; i += (long long)gridDim.x * TPB) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -737,7 +738,16 @@ int ub_adam(float* param, const float* grad, float* m, float* v, void* bf16_shad
             float eps, float grad_scale, cudaStream_t stream) {
   UB_CHECK_ARG(param && grad && m && v && n > 0, "adam: bad args");
   const int grid = grid_for(n / 4 + 1, TPB, ub_num_sms() * 8);
-  adam_kernel<<<grid, TPB, 0, stream>>>(param, grad, m, v, (__nv_bfloat16*)bf16_shadow, n, lr_t, beta1, beta2, eps, grad_scale);
+  adam_kernel<<<grid, TPB, 0, stream>>>(param, grad, m, v, (__nv_bfloat16*)bf16_shadow, n, lr_t, nullptr, beta1, beta2, eps, grad_scale);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_adam_dev(float* param, const float* grad, float* m, float* v, void* bf16_shadow, long long n, const float* lr_t_dev, float beta1,
+                float beta2, float eps, float grad_scale, cudaStream_t stream) {
+  UB_CHECK_ARG(param && grad && m && v && lr_t_dev && n > 0, "adam_dev: bad args");
+  const int grid = grid_for(n / 4 + 1, TPB, ub_num_sms() * 8);
+  adam_kernel<<<grid, TPB, 0, stream>>>(param, grad, m, v, (__nv_bfloat16*)bf16_shadow, n, 0.f, lr_t_dev, beta1, beta2, eps, grad_scale);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
