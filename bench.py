@@ -308,9 +308,20 @@ def run_cuda(args):
     if dp:
         dp.barrier()
 
-    if rank != 0:
+    def finish():
+        # graphs that hold captured NCCL kernels must be gone before the communicator is torn down; a stuck teardown
+        # would turn a finished measurement into a hung job, so the process leaves without destroying the group
+        model._graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize(dev)
         if dp:
-            dp.shutdown()
+            dp.barrier()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
     fwd_fl, train_fl, fam_fl = step_flops()
     peaks = measured_peaks()
@@ -345,8 +356,7 @@ def run_cuda(args):
         "final_loss": final_loss,
     }
     os.write(json_fd, (json.dumps(line) + "\n").encode())
-    if dp:
-        dp.shutdown()
+    finish()
 
 
 def main():

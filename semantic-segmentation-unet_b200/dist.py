@@ -143,6 +143,11 @@ class DataParallel:
         if self.world_size > 1:
             dist.barrier()
 
-    def shutdown(self):
+    def shutdown(self, timeout_s=30.0):
+        """tear the process group down; bounded, because destroying a communicator whose kernels were captured in CUDA graphs
+        has been seen to block (release the graphs first: UNet._graphs.clear())"""
         if dist.is_initialized():
-            dist.destroy_process_group()
+            import threading
+            t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+            t.start()
+            t.join(timeout_s)

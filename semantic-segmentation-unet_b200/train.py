@@ -233,6 +233,11 @@ def train_model(output_folder, batch_size, reader_count, train_lmdb_filepath, te
         print('Shutting down test_reader')
         test_reader.shutdown()
         if strategy is not None:
+            try:
+                unet_model._graphs.clear()          # captured NCCL kernels must be released before the communicator
+                torch.cuda.synchronize()
+            except NameError:
+                pass
             strategy.shutdown()
 
 
