@@ -158,6 +158,10 @@ int ub_adam_dev(float* param, const float* grad, float* m, float* v, void* bf16_
  * src_layout 0: src [R][T][C] (conv [Cout][tap][Cin]); 1: src [T][R][C] (deconv [(2a+b)][Cout][Cin]) */
 int ub_transpose_pack(const float* src, void* dst, int R, int T, int C, int flip, int src_layout, int dst_dtype,
                       cudaStream_t stream);
+/* every pack of the model in one launch.  jobs_dev: device array of njobs records
+ *   { const float* src; void* dst; int R, T, C, flip, src_layout, tiles_c, tiles_r, tile_begin; }   (48 bytes, natural alignment)
+ * with tiles_c = ceil(C/32), tiles_r = ceil(R/32), tile_begin = exclusive prefix sum of tiles_c*tiles_r*T; total_tiles = the sum */
+int ub_transpose_pack_multi(const void* jobs_dev, int njobs, int total_tiles, int dst_dtype, cudaStream_t stream);
 int ub_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
 /* zscore_normalize (UNet/imagereader.py:33-66) per plane; src_dtype 0 = u8, 1 = u16, 2 = f32;
  * scratch: planes * UB_ZSCORE_BLOCKS * 2 doubles */

@@ -122,13 +122,31 @@ __global__ void __launch_bounds__(32 * RED_ROWLANES) bn_finalize_kernel(const fl
   const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double s = 0.0, q = 0.0;
-  if (c < C)
-#pragma unroll 4
-    for (int r = ry; r < rows; r += RED_ROWLANES)
-      for (int g = 0; g < groups; ++g) {
-        s += (double)partial[((size_t)r * 2 + 0) * ncols + g * C + c];
-        q += (double)partial[((size_t)r * 2 + 1) * ncols + g * C + c];
+  if (c < C) {
+    if (rows == UB_STATS_ROWS && groups == 1) {
+      // the common case: all loads of this thread are issued before the first add (the kernel is pure L2 latency otherwise)
+      constexpr int PER = (UB_STATS_ROWS + RED_ROWLANES - 1) / RED_ROWLANES;
+      float vs[PER], vq[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int r = ry + i * RED_ROWLANES;
+        vs[i] = r < UB_STATS_ROWS ? __ldg(partial + ((size_t)r * 2 + 0) * ncols + c) : 0.f;
+        vq[i] = r < UB_STATS_ROWS ? __ldg(partial + ((size_t)r * 2 + 1) * ncols + c) : 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        s += (double)vs[i];
+        q += (double)vq[i];
+      }
+    } else {
+#pragma unroll 4
+      for (int r = ry; r < rows; r += RED_ROWLANES)
+        for (int g = 0; g < groups; ++g) {
+          s += (double)partial[((size_t)r * 2 + 0) * ncols + g * C + c];
+          q += (double)partial[((size_t)r * 2 + 1) * ncols + g * C + c];
+        }
+    }
+  }
   s = block_rows_sum(s, sh);
   q = block_rows_sum(q, sh);
   if (ry != 0 || c >= C) return;
@@ -151,9 +169,22 @@ __global__ void __launch_bounds__(32 * RED_ROWLANES) reduce_rows_kernel(const fl
   const int lane = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   double s = 0.0;
-  if (c < ncols)
+  if (c < ncols) {
+    if (rows == UB_STATS_ROWS) {
+      constexpr int PER = (UB_STATS_ROWS + RED_ROWLANES - 1) / RED_ROWLANES;
+      float vs[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int r = ry + i * RED_ROWLANES;
+        vs[i] = r < UB_STATS_ROWS ? __ldg(partial + (size_t)r * row_stride + c) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < PER; ++i) s += (double)vs[i];
+    } else {
 #pragma unroll 4
-    for (int r = ry; r < rows; r += RED_ROWLANES) s += (double)partial[(size_t)r * row_stride + c];
+      for (int r = ry; r < rows; r += RED_ROWLANES) s += (double)partial[(size_t)r * row_stride + c];
+    }
+  }
   s = block_rows_sum(s, sh);
   if (ry == 0 && c < ncols) out[c] = (float)(s * (double)scale);
 }
@@ -514,6 +545,43 @@ __global__ void transpose_pack_kernel(const float* __restrict__ src, TO* __restr
   }
 }
 
+// All dgrad packs of the model in ONE launch: job j transposes src_j (fp32, layout as above) into dst_j; blockIdx.x walks the
+// concatenated 32x32 tile lists (tile_begin[j] .. tile_begin[j+1]).
+struct PackJob {
+  const float* src;
+  void* dst;
+  int R, T, C, flip, src_layout, tiles_c, tiles_r;
+  int tile_begin;
+};
+template <typename TO>
+__global__ void transpose_pack_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = njobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {                      // last job whose tile_begin <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].tile_begin <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackJob J = jobs[lo];
+  int t = b - J.tile_begin;
+  const int tc = t % J.tiles_c; t /= J.tiles_c;
+  const int tr = t % J.tiles_r;
+  const int tap = t / J.tiles_r;
+  const int r0 = tr * 32, c0 = tc * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    const size_t si = J.src_layout ? ((size_t)tap * J.R + r) * J.C + c : ((size_t)r * J.T + tap) * J.C + c;
+    tile[j][threadIdx.x] = (r < J.R && c < J.C) ? J.src[si] : 0.f;
+  }
+  __syncthreads();
+  const int tt = J.flip ? J.T - 1 - tap : tap;
+  TO* dst = reinterpret_cast<TO*>(J.dst);
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < J.R && c < J.C) dst[((size_t)c * J.T + tt) * J.R + r] = (TO)tile[threadIdx.x][j];
+  }
+}
+
 __global__ void __launch_bounds__(TPB) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) dst[i] = __float2bfloat16(src[i]);
 }
@@ -758,6 +826,16 @@ int ub_transpose_pack(const float* src, void* dst, int R, int T, int C, int flip
   if (dst_dtype == UB_BF16) transpose_pack_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(src, (__nv_bfloat16*)dst, R, T, C, flip, src_layout);
   else if (dst_dtype == UB_F32) transpose_pack_kernel<float><<<grid, block, 0, stream>>>(src, (float*)dst, R, T, C, flip, src_layout);
   else { ub_set_error("transpose_pack: bad dtype"); return UB_ERR_INVALID_ARG; }
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_transpose_pack_multi(const void* jobs_dev, int njobs, int total_tiles, int dst_dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(jobs_dev && njobs > 0 && total_tiles > 0, "transpose_pack_multi: bad args");
+  dim3 block(32, 8);
+  if (dst_dtype == UB_BF16) transpose_pack_multi_kernel<__nv_bfloat16><<<total_tiles, block, 0, stream>>>((const PackJob*)jobs_dev, njobs);
+  else if (dst_dtype == UB_F32) transpose_pack_multi_kernel<float><<<total_tiles, block, 0, stream>>>((const PackJob*)jobs_dev, njobs);
+  else { ub_set_error("transpose_pack_multi: bad dtype"); return UB_ERR_INVALID_ARG; }
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

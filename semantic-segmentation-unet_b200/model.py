@@ -202,12 +202,21 @@ class UNet:
         self._radius_cache = None
 
     def _repack_dgrad(self):
-        code = self.act_code
-        for n, L in self.layers.items():
-            if L.kind == "conv":
-                self._call("ub_transpose_pack", self._w(L), self.WT[n], L.cout, 9, L.cin, 1, 0, code)
-            elif L.kind == "deconv":
-                self._call("ub_transpose_pack", self._w(L), self.WT[n], L.cout, 4, L.cin, 0, 1, code)
+        """dgrad weight packs of every layer, one launch (21 tiny transposes otherwise)"""
+        if getattr(self, "_pack_jobs", None) is None:
+            import struct
+            rec, begin = [], 0
+            for n, L in self.layers.items():
+                if L.kind not in ("conv", "deconv"):
+                    continue
+                T, flip, layout = (9, 1, 0) if L.kind == "conv" else (4, 0, 1)
+                tc, tr = (L.cin + 31) // 32, (L.cout + 31) // 32
+                rec.append(struct.pack("<QQiiiiiiii", self._w(L).data_ptr(), self.WT[n].data_ptr(), L.cout, T, L.cin, flip, layout, tc, tr, begin))
+                begin += tc * tr * T
+            blob = np.frombuffer(b"".join(rec), dtype=np.uint8).copy()
+            self._pack_jobs = torch.from_numpy(blob).to(self.device)
+            self._pack_njobs, self._pack_tiles = len(rec), begin
+        self._call("ub_transpose_pack_multi", self._pack_jobs, self._pack_njobs, self._pack_tiles, self.act_code)
 
     def load_oracle_params(self, params):
         """params: dict in the TF layouts used by the oracle / a Keras checkpoint (conv [kh,kw,Cin,Cout], deconv
