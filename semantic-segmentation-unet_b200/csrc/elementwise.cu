@@ -3,11 +3,16 @@
 // All activations are NHWC; T = __nv_bfloat16 (product path) or float (fp32 check mode).  Every thread moves 8
 // consecutive channels (128-bit accesses for bf16); per-channel reductions are thread-private over a grid-stride
 // pixel loop, then one shared-memory tree per block, then one partial row per block (deterministic, no atomics).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int TPB = 256;
+#ifndef UB_BN_MINB
+#define UB_BN_MINB 3
+#endif
 
 template <typename T>
 struct V8;
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(TPB) dropout_scale_kernel(const T* __restrict_
 // ------------------------------------------------------------------ BN backward
 // pass 1: partial[row][0][c] = sum dy, partial[row][1][c] = sum dy * xhat
 template <typename T>
-__global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
+__global__ void __launch_bounds__(TPB, UB_BN_MINB) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, float* __restrict__ partial, long long M, int C) {
   const int G = C >> 3, PL = TPB / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
@@ -431,7 +436,7 @@ __global__ void __launch_bounds__(TPB, 3) bn_bwd_reduce_kernel(const T* __restri
 
 // pass 2: dz = gamma*rstd*(dy - dbeta/M - xhat*dgamma/M) * [a > 0 if relu];  partial[row][0][c] = sum dz (bias gradient)
 template <typename T>
-__global__ void __launch_bounds__(TPB, 3) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
+__global__ void __launch_bounds__(TPB, UB_BN_MINB) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ a, const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ dbeta, const float* __restrict__ dgamma,
                                                            T* __restrict__ dz, float* __restrict__ partial, long long M, int C, int relu) {
@@ -777,13 +782,24 @@ int ub_dropout_bwd(const void* in, const unsigned char* mask, void* out, long lo
   return UB_OK;
 }
 
+// resident blocks per SM for the two BatchNorm-backward passes (3 fills the SM when they run alone; 2 leaves room for a
+// co-resident weight-gradient CTA when the step overlaps them, UB_BN_BWD_CTAS=2)
+static int bn_bwd_ctas_per_sm() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("UB_BN_BWD_CTAS");
+    v = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 3;
+  }
+  return v;
+}
+
 int ub_bn_bwd_reduce(const void* dy, const void* a, const float* mean, const float* rstd, float* partial, long long M, int C, int dtype,
                      cudaStream_t stream) {
   UB_CHECK_ARG(dy && a && mean && rstd && partial && M > 0, "bn_bwd_reduce: bad args");
   UB_CHECK_SHAPE(channels_ok(C), "bn_bwd_reduce: C=%d must be a power of two in [64,2048]", C);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * C, stream));
   const int PL = TPB / (C >> 3);
-  const int grid = grid_for(M, PL * 4, ub_num_sms() * 3);      // one wave of 3 resident blocks per SM (<= UB_STATS_ROWS)
+  const int grid = grid_for(M, PL * 4, ub_num_sms() * bn_bwd_ctas_per_sm());      // one wave of resident blocks (<= UB_STATS_ROWS)
   UB_DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dy, (const T*)a, mean, rstd, partial, M, C)));
   UB_LAUNCH_CHECK();
   return UB_OK;
@@ -795,7 +811,7 @@ int ub_bn_bwd_apply(const void* dy, const void* a, const float* mean, const floa
   UB_CHECK_SHAPE(channels_ok(C), "bn_bwd_apply: C=%d must be a power of two in [64,2048]", C);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * C, stream));
   const int PL = TPB / (C >> 3);
-  const int grid = grid_for(M, PL * 4, ub_num_sms() * 3);
+  const int grid = grid_for(M, PL * 4, ub_num_sms() * bn_bwd_ctas_per_sm());
   UB_DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dy, (const T*)a, mean, rstd, gamma, dbeta, dgamma, (T*)dz,
                                                                         partial, M, C, relu)));
   UB_LAUNCH_CHECK();

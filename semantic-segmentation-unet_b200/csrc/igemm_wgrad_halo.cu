@@ -20,6 +20,8 @@
 // warp's store of one column is 128 contiguous bytes) either straight into dW (splits == 1) or into its slice of a
 // [splits][Cout*9*Cin] workspace that ub_wgrad_sum_splits adds up in a fixed order (deterministic, no atomics).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -52,6 +54,16 @@ struct Cfg<0> {   // mode P
   static constexpr int NPATCH = 2;
   static constexpr int NACC = 3;
   static constexpr int STAGES = 3;
+};
+template <>
+struct Cfg<2> {   // mode P with a two-deep pipeline: 148 KB of shared memory, leaves room for co-resident memory-bound CTAs
+  static constexpr int BLOCK_N = 128;
+  static constexpr int PH = TH;
+  static constexpr int PATCH_BYTES = PW * PH * 128;
+  static constexpr int PATCH_STRIDE = PATCH_BYTES;
+  static constexpr int NPATCH = 2;
+  static constexpr int NACC = 3;
+  static constexpr int STAGES = 2;
 };
 template <>
 struct Cfg<1> {   // mode Q
@@ -103,7 +115,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
   const int n_tile = item % p.n_tiles;
   item /= p.n_tiles;
   int dh = 0, cb0;
-  if (MODE == 0) {
+  if (MODE != 1) {
     dh = item % 3;
     cb0 = (item / 3) * 2;
   } else {
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
       // warp, not the tensor pipe, was the limit with one elect per MMA)
       const uint64_t bdesc = make_smem_desc(sa + L::OFF_DZ, DZ_BLK_BYTES, TW * 128);
       constexpr uint64_t B_STEP = (2 * TW * 128) >> 4, A_STEP = (2 * PW * 128) >> 4;
-      if (MODE == 0) {
+      if (MODE != 1) {
         const uint64_t adesc0 = make_smem_desc(sa, C::PATCH_STRIDE, PW * 128);
 #pragma unroll
         for (int dw = 0; dw < 3; ++dw)
@@ -209,7 +221,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_halo_kernel(const __grid_constan
     for (int a = 0; a < C::NACC; ++a) {
       int tap, ci;
       bool store = true;
-      if (MODE == 0) {
+      if (MODE != 1) {
         tap = dh * 3 + a;
         ci = (cb0 + half) * 64 + (row & 63);
       } else {
@@ -365,7 +377,12 @@ int ub_wgrad_halo(const void* x0, int C0, const void* x1, int C1, const void* dz
     p.out = dw;
     p.split_stride = 0;
   }
-  rc = pl.mode == 0 ? launch_wh<0>(p, stream) : launch_wh<1>(p, stream);
+  static int p2 = -1;
+  if (p2 < 0) {
+    const char* e = getenv("UB_WGRAD_P_STAGES");      // 2: shallower pipeline, smaller shared-memory footprint (co-residency experiments)
+    p2 = (e && e[0] == '2') ? 1 : 0;
+  }
+  rc = pl.mode == 0 ? (p2 ? launch_wh<2>(p, stream) : launch_wh<0>(p, stream)) : launch_wh<1>(p, stream);
   if (rc) return rc;
   if (pl.splits > 1) {
     const long long n4 = n_w / 4;      // n_w is a multiple of 64 * 64 * 9

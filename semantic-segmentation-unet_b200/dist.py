@@ -86,15 +86,21 @@ class DataParallel:
         if name != last:
             return
         self._next += 1
-        self._reduce_slice(model.G[lo:hi])
+        self._reduce_slice(model.G[lo:hi], getattr(model, "_wstream", None))
 
-    def _reduce_slice(self, t):
+    def _reduce_slice(self, t, side_stream=None):
         self.allreduce_calls += 1
         if t.is_cuda:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(t.device))
+            side_ready = None
+            if side_stream is not None:          # weight gradients are produced on the model's side stream
+                side_ready = torch.cuda.Event()
+                side_ready.record(side_stream)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ready)
+                if side_ready is not None:
+                    self._comm_stream.wait_event(side_ready)
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
         else:
             self._pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
@@ -104,7 +110,7 @@ class DataParallel:
         while self._next < len(self._buckets):          # safety: anything not yet launched
             lo, hi, _ = self._buckets[self._next]
             self._next += 1
-            self._reduce_slice(model.G[lo:hi])
+            self._reduce_slice(model.G[lo:hi], getattr(model, "_wstream", None))
         if model.G.is_cuda:
             torch.cuda.current_stream(model.G.device).wait_stream(self._comm_stream)
         for w in self._pending:

@@ -13,6 +13,7 @@ Layout decisions:
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -71,6 +72,8 @@ class UNet:
         self._buf = {}
         self._inference_stale = True
         self._radius_cache = None
+        self._wstream = None
+        self.overlap_wgrad = os.environ.get("UB_OVERLAP_WGRAD", "0") == "1"   # bf16 path: weight gradients on a side stream (see _side)
         self.use_graph = True              # replay the training step from a CUDA graph (one capture per input shape)
         self._graphs = {}
         self._lr_ring = None
@@ -95,6 +98,29 @@ class UNet:
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    # Weight-gradient kernels run on a side stream: wgrad(L) only needs dz_L and is not on the critical path
+    # (dz_L -> dgrad(L) -> BN backward of the layer below -> ...).  It is enqueued AFTER dgrad(L) and waits for it (two
+    # persistent tensor-core kernels cannot share an SM, whichever starts first would delay the other), so that its
+    # tensor-core work runs beside the HBM-bound BatchNorm-backward passes of the layer below.
+    def _side(self):
+        if self._wstream is None:
+            self._wstream = torch.cuda.Stream(device=self.device)
+        return self._wstream
+
+    def _fork_side(self):
+        """side stream waits for everything enqueued so far on the current stream"""
+        ws = self._side()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        ws.wait_event(ev)
+        return ws
+
+    def _join_side(self):
+        if self._wstream is not None:
+            ev = torch.cuda.Event()
+            ev.record(self._wstream)
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     def _ensure(self, name, numel, dtype):
         t = self._buf.get(name)
@@ -637,7 +663,8 @@ class UNet:
         c0, c1 = L.c0, L.c1
         if self.precision == "bf16":
             ws = self._b("wgrad_ws")
-            self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
+            if not self.overlap_wgrad:
+                self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
             # worth it only where the K loop is long enough to hide the longer epilogue (measured: 64-output-channel layers,
             # whose dgrad has a single 64-channel K block, lose more in the dgrad than the separate reduction pass costs)
             if dx0 is not None and red is not None and self.fuse_bn_reduce and L.cout >= 128:
@@ -647,6 +674,9 @@ class UNet:
                 self._red_ready = red.name
             elif dx0 is not None:
                 self._call("ub_conv3x3_dgrad", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w)
+            if self.overlap_wgrad:
+                with torch.cuda.stream(self._fork_side()):
+                    self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
         else:
             self._call("ub_check_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, N, h, w)
             if dx0 is not None:
@@ -659,6 +689,8 @@ class UNet:
         P = N * H * W
         done = on_layer_done or (lambda name: None)
         infer = getattr(self, "_bwd_inference", False)
+        if self.overlap_wgrad and self.precision == "bf16":
+            self._fork_side()          # the side stream takes part in this step (and in its graph capture) from here on
         # ---- head: BN backward + relu mask + 1x1 dgrad/wgrad
         L = Ls["head"]
         self._cur = "head"
@@ -693,8 +725,12 @@ class UNet:
             xin = self._b("y:" + prev.name)
             if self.precision == "bf16":
                 ws = self._b("wgrad_ws")
-                self._call("ub_deconv2x2_wgrad", xin, Lu.cin, dz, Lu.cout, dw, ws, ws.numel(), N, hi, wi)
+                if not self.overlap_wgrad:
+                    self._call("ub_deconv2x2_wgrad", xin, Lu.cin, dz, Lu.cout, dw, ws, ws.numel(), N, hi, wi)
                 self._call("ub_deconv2x2_dgrad", dz, Lu.cout, self.WT[Lu.name], self._b("g:" + prev.name), Lu.cin, N, hi, wi)
+                if self.overlap_wgrad:
+                    with torch.cuda.stream(self._fork_side()):
+                        self._call("ub_deconv2x2_wgrad", xin, Lu.cin, dz, Lu.cout, dw, ws, ws.numel(), N, hi, wi)
             else:
                 self._call("ub_check_deconv2x2_wgrad", xin, dz, dw, N, hi, wi, Lu.cin, Lu.cout)
                 self._call("ub_check_deconv2x2_dgrad", dz, self._wptr(Lu), self._b("g:" + prev.name), N, hi, wi, Lu.cin, Lu.cout)
@@ -727,6 +763,7 @@ class UNet:
                     self._call("ub_conv_first_dgrad", dz, self.P[La.off_w:La.off_w + La.n_w], input_grad, N, H, W, self.number_channels,
                                self.act_code)
             done(La.name)
+        self._join_side()
 
     # ------------------------------------------------------------------------------------------------ optimizer
     def _lr_t(self):

@@ -441,7 +441,7 @@ CASES = {
     "golden_c3_k8_fp32": lambda: case_golden("graph_c3_k8", "fp32"),
     "golden_c1_k2_bf16": lambda: case_golden("graph_c1_k2", "bf16"),
     "golden_c3_k8_bf16": lambda: case_golden("graph_c3_k8", "bf16"),
-    "curve_bf16": lambda: case_curve("bf16"),
+    "curve_bf16": lambda: case_curve("bf16", steps=200),          # north_star: loss curve over the first 200 steps
     "inference_fp32": lambda: case_inference("fp32"),
     "inference_bf16": lambda: case_inference("bf16"),
 }

@@ -77,7 +77,7 @@ def raw(fp):
         d = {"kernel": short(r[ki]), "grid": r[gi]}
         for key, i in idx.items():
             metric, scale = COLS[key]
-            if r[i] in ("", "n/a"):
+            if r[i] in ("", "n/a", "no data"):
                 continue
             if scale == "time":
                 d[key] = round(float(r[i].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3, "s": 1e6}.get(units[i], 1), 1)
