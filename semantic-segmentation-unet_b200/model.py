@@ -73,7 +73,7 @@ class UNet:
         self._inference_stale = True
         self._radius_cache = None
         self._wstream = None
-        self.overlap_wgrad = os.environ.get("UB_OVERLAP_WGRAD", "0") == "1"   # bf16 path: weight gradients on a side stream (see _side)
+        self.overlap_wgrad = os.environ.get("UB_OVERLAP_WGRAD", "1") == "1"   # bf16 path: weight gradients on a side stream (see _side)
         self.use_graph = True              # replay the training step from a CUDA graph (one capture per input shape)
         self._graphs = {}
         self._lr_ring = None
