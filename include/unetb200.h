@@ -41,6 +41,9 @@ extern "C" {
 const char* ub_last_error(void);
 int ub_version(void);
 int ub_device_sm_count(void);
+/* HOST utility (no device work): CRC-32C (Castagnoli) of n bytes at `data`, continuing from `crc` (0 to start), as used by
+ * the TensorBundle checkpoint files `tf.train.Checkpoint.write` produces (UNet/train.py:96, :181-184). Returns the CRC. */
+long long ub_host_crc32c(const void* data, long long n, long long crc);
 
 /* ---- tensor-core implicit GEMMs (bf16 storage, fp32 accumulate in TMEM) -------------------------------------- */
 

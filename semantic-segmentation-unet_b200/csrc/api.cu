@@ -84,7 +84,41 @@ int ub_tmap_mat2d(CUtensorMap* out, const void* base, long long rows, long long 
   return UB_OK;
 }
 
+// CRC-32C, slicing-by-8 tables built on first use (host only; checkpoint files are a few hundred MB)
+static uint32_t g_crc_tab[8][256];
+static bool g_crc_ready = false;
+static void crc32c_init() {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+    g_crc_tab[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc_tab[t][i] = (g_crc_tab[t - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[t - 1][i] & 0xff];
+  g_crc_ready = true;
+}
+
 extern "C" {
+long long ub_host_crc32c(const void* data, long long n, long long crc_in) {
+  if (!g_crc_ready) crc32c_init();
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~static_cast<uint32_t>(crc_in);
+  while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 7)) {
+    c = g_crc_tab[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+    --n;
+  }
+  while (n >= 8) {
+    uint64_t w;
+    memcpy(&w, p, 8);
+    w ^= c;
+    c = g_crc_tab[7][w & 0xff] ^ g_crc_tab[6][(w >> 8) & 0xff] ^ g_crc_tab[5][(w >> 16) & 0xff] ^ g_crc_tab[4][(w >> 24) & 0xff] ^
+        g_crc_tab[3][(w >> 32) & 0xff] ^ g_crc_tab[2][(w >> 40) & 0xff] ^ g_crc_tab[1][(w >> 48) & 0xff] ^ g_crc_tab[0][w >> 56];
+    p += 8;
+    n -= 8;
+  }
+  while (n-- > 0) c = g_crc_tab[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  return static_cast<long long>(~c & 0xffffffffu);
+}
 const char* ub_last_error(void) { return g_err; }
 int ub_version(void) { return UB_VERSION; }
 int ub_device_sm_count(void) { return ub_num_sms(); }

@@ -313,6 +313,23 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
     return launch_c3<64, 1, 2, 18, 1, 1>(p, a_base, a_ch, n_img, stream);
   }
   if (p.ncols % 128 == 0) return launch_c3<128, 2, 2, 4, 2>(p, a_base, a_ch, n_img, stream);       // 256 pixels x 128 columns
+  static int v64 = -1;
+  if (v64 < 0) {
+    const char* e = getenv("UB_CONV3_64");        // A/B switch for tools/bench_layers.py: pipeline shape of the 64 -> 64 layers
+    v64 = e ? atoi(e) : 0;
+  }
+  if (p.cblk_total == 1 && v64 == 1) return launch_c3<64, 2, 3, 9, 1>(p, a_base, a_ch, n_img, stream);   // 3 patches in flight, one staging buffer
+  if (p.cblk_total == 1 && v64 == 2) return launch_c3<64, 1, 4, 9, 2>(p, a_base, a_ch, n_img, stream);   // 128-pixel tiles, 4 patches in flight
+  if (p.cblk_total == 1 && v64 == 3) return launch_c3<64, 1, 5, 9, 2>(p, a_base, a_ch, n_img, stream);   // 128-pixel tiles, 5 patches in flight
+  if (p.cblk_total == 1 && v64 == 4) return launch_c3<64, 2, 3, 4, 2>(p, a_base, a_ch, n_img, stream);   // streamed weights, 3 patches in flight
+  if (p.cblk_total == 1 && v64 == 5) return launch_c3<64, 2, 4, 3, 1>(p, a_base, a_ch, n_img, stream);   // streamed weights, 4 patches in flight
+  static int v64b = -1;
+  if (v64b < 0) {
+    const char* e = getenv("UB_CONV3_64B");       // same for the 128 -> 64 layer (dec1a)
+    v64b = e ? atoi(e) : 0;
+  }
+  if (p.cblk_total == 2 && v64b == 1) return launch_c3<64, 2, 3, 6, 2>(p, a_base, a_ch, n_img, stream);  // 256-pixel super-tiles, streamed weights
+  if (p.cblk_total == 2 && v64b == 2) return launch_c3<64, 2, 2, 9, 2>(p, a_base, a_ch, n_img, stream);
   if (p.cblk_total == 1) return launch_c3<64, 2, 2, 9, 2>(p, a_base, a_ch, n_img, stream);         // 64 -> 64: weights resident, 256-pixel super-tiles
   return launch_c3<64, 1, 2, 18, 2>(p, a_base, a_ch, n_img, stream);                               // 128 -> 64 (dec1a): weights resident
 }

@@ -244,13 +244,13 @@ class UNet:
             self._pack_njobs, self._pack_tiles = len(rec), begin
         self._call("ub_transpose_pack_multi", self._pack_jobs, self._pack_njobs, self._pack_tiles, self.act_code)
 
-    def load_oracle_params(self, params):
-        """params: dict in the TF layouts used by the oracle / a Keras checkpoint (conv [kh,kw,Cin,Cout], deconv
-        [kh,kw,Cout,Cin], head [1,1,Cin,K]); also moving_mean / moving_var."""
-        host = self.P.cpu()
-        mm, mv = self.MM.cpu(), self.MV.cpu()
+    def _import_flat(self, params, host):
+        """dict in the TF layouts (conv [kh,kw,Cin,Cout], deconv [kh,kw,Cout,Cin], head [1,1,Cin,K]) -> flat host buffer"""
         for n, L in self.layers.items():
             w = torch.as_tensor(np.asarray(params[n + "/kernel"], dtype=np.float32))
+            want = (2, 2, L.cout, L.cin) if L.kind == "deconv" else ((1, 1) if L.kind == "head" else (3, 3)) + (L.cin, L.cout)
+            if tuple(w.shape) != want:
+                raise IOError(f"{n}/kernel has shape {tuple(w.shape)}, expected {want}")
             if L.kind == "deconv":
                 packed = w.reshape(4 * L.cout, L.cin)
             else:
@@ -259,6 +259,14 @@ class UNet:
             host[L.off_b:L.off_b + L.cout] = torch.as_tensor(np.asarray(params[n + "/bias"], dtype=np.float32))
             host[L.off_beta:L.off_beta + L.cout] = torch.as_tensor(np.asarray(params[n + "/beta"], dtype=np.float32))
             host[L.off_gamma:L.off_gamma + L.cout] = torch.as_tensor(np.asarray(params[n + "/gamma"], dtype=np.float32))
+        return host
+
+    def load_oracle_params(self, params):
+        """params: dict in the TF layouts used by the oracle / a Keras checkpoint (conv [kh,kw,Cin,Cout], deconv
+        [kh,kw,Cout,Cin], head [1,1,Cin,K]); also moving_mean / moving_var."""
+        host = self._import_flat(params, self.P.cpu())
+        mm, mv = self.MM.cpu(), self.MV.cpu()
+        for n, L in self.layers.items():
             if n + "/moving_mean" in params:
                 mm[L.off_stat:L.off_stat + L.cout] = torch.as_tensor(np.asarray(params[n + "/moving_mean"], dtype=np.float32))
                 mv[L.off_stat:L.off_stat + L.cout] = torch.as_tensor(np.asarray(params[n + "/moving_var"], dtype=np.float32))
@@ -993,11 +1001,39 @@ class UNet:
                 "step": self.step_count, "number_classes": self.number_classes, "number_channels": self.number_channels,
                 "learning_rate": self.learning_rate}
 
-    def save_checkpoint(self, checkpoint_filepath):
-        """counterpart of tf.train.Checkpoint(optimizer, model).write(path) (UNet/train.py:96, :181-184); native format"""
-        torch.save(self.state_dict(), checkpoint_filepath)
+    def _blocks(self):
+        return list(self.layers), [L.kind for L in self.layers.values()]
+
+    def save_checkpoint(self, checkpoint_filepath, format="tf"):
+        """Counterpart of tf.train.Checkpoint(optimizer, model).write(prefix) (UNet/train.py:96, :181-184).
+        format="tf": the same two files the reference leaves behind, <prefix>.index + <prefix>.data-00000-of-00001 (a
+        TensorBundle with the TF2 object-graph keys, unetb200/tfcheckpoint.py); format="native": one torch.save file."""
+        if format == "native":
+            torch.save(self.state_dict(), checkpoint_filepath)
+            return
+        if format != "tf":
+            raise ValueError("format must be 'tf' or 'native'")
+        from . import tfcheckpoint
+        names, kinds = self._blocks()
+        tfcheckpoint.save_unet(checkpoint_filepath, names, kinds, self.export_params(), self.export_flat(self.M), self.export_flat(self.V),
+                               step=self.step_count, learning_rate=self.learning_rate, beta_1=ADAM_B1, beta_2=ADAM_B2)
 
     def load_checkpoint(self, checkpoint_filepath: str):     # UNet/model.py:81-83 (expect_partial: optimizer slots optional)
+        import os
+        if os.path.exists(checkpoint_filepath + ".index"):
+            from . import tfcheckpoint
+            names, kinds = self._blocks()
+            ck = tfcheckpoint.load_unet(checkpoint_filepath, names, kinds)
+            k = ck["params"]["head/kernel"].shape[-1]
+            c = ck["params"]["enc1a/kernel"].shape[2]
+            if k != self.number_classes or c != self.number_channels:
+                raise IOError("checkpoint was written for a different number_classes / number_channels")
+            if ck["adam_m"] is not None:
+                self.M.copy_(self._import_flat(ck["adam_m"], torch.zeros(self.n_flat)))
+                self.V.copy_(self._import_flat(ck["adam_v"], torch.zeros(self.n_flat)))
+                self.step_count = int(ck["step"] or 0)
+            self.load_oracle_params(ck["params"])
+            return
         sd = torch.load(checkpoint_filepath, map_location="cpu")
         if sd["number_classes"] != self.number_classes or sd["number_channels"] != self.number_channels:
             raise IOError("checkpoint was written for a different number_classes / number_channels")

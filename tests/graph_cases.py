@@ -378,7 +378,8 @@ def case_train_driver():
         r["train_acc_last10"] = float(np.mean([float(l[3]) for l in lines[-10:]]))
         r["test_loss"] = [round(float(v), 4) for v in test_loss]
         r["files"] = sorted(os.listdir(out))
-        r["ckpt"] = os.path.exists(os.path.join(out, "checkpoint", "ckpt"))
+        # the two files tf.train.Checkpoint.write leaves behind (UNet/train.py:181-184)
+        r["ckpt"] = sorted(os.listdir(os.path.join(out, "checkpoint"))) == ["ckpt.data-00000-of-00001", "ckpt.index"]
         r["csv_rows"] = len(open(os.path.join(out, "test_loss.csv")).read().split())
         tb = [f for f in r["files"] if f.startswith("tensorboard-")]
         r["tb"] = bool(tb) and sorted(os.listdir(os.path.join(out, tb[0]))) == ["test", "train"]
@@ -427,7 +428,44 @@ def case_estimate_radius(C=1, K=2, seed=41):
     return r
 
 
+def case_checkpoint_roundtrip():
+    """save_checkpoint / load_checkpoint (UNet/train.py:96, :181-184; UNet/model.py:81-83) in the TensorBundle format and the
+    native one: weights, moving statistics, Adam moments and the step counter survive bit-for-bit, and training continues
+    identically from the restored state."""
+    import tempfile
+    from unetb200.model import UNet
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(2, 1, 32, 48)).astype(np.float32)
+    lab = rng.integers(0, 2, size=(2, 32, 48)).astype(np.uint8)
+    m = UNet(2, 2, 1, 1e-3, seed=3)
+    for _ in range(3):
+        m.train_step(x, lab, dropout_masks={})
+    r = {}
+    with tempfile.TemporaryDirectory() as d:
+        for fmt in ("tf", "native"):
+            path = os.path.join(d, fmt, "ckpt")
+            os.makedirs(os.path.dirname(path))
+            m.save_checkpoint(path, format=fmt)
+            r[fmt + "_files"] = sorted(os.listdir(os.path.dirname(path)))
+            m2 = UNet(2, 2, 1, 1e-3, seed=99)
+            m2.load_checkpoint(path)
+            same = all(bool(torch.equal(getattr(m, a), getattr(m2, a))) for a in ("P", "M", "V", "MM", "MV", "S")) and m2.step_count == m.step_count
+            la = float(m.train_step(x, lab, dropout_masks={}, apply_update=False).item())
+            lb = float(m2.train_step(x, lab, dropout_masks={}, apply_update=False).item())
+            m.step_count -= 1          # apply_update=False still counted the step
+            r[fmt] = bool(same and la == lb and bool(torch.equal(m.G, m2.G)))
+        wrong = UNet(3, 2, 1, 1e-3, seed=0)
+        try:
+            wrong.load_checkpoint(os.path.join(d, "tf", "ckpt"))
+            r["mismatch_raises"] = False
+        except IOError:
+            r["mismatch_raises"] = True
+    r["ok"] = bool(r["tf"] and r["native"] and r["mismatch_raises"] and r["tf_files"] == ["ckpt.data-00000-of-00001", "ckpt.index"])
+    return r
+
+
 CASES = {
+    "checkpoint_roundtrip": case_checkpoint_roundtrip,
     "estimate_radius_c1": lambda: case_estimate_radius(1, 2, 41),
     "estimate_radius_c3": lambda: case_estimate_radius(3, 4, 42),
     "train_driver": case_train_driver,

@@ -85,6 +85,9 @@ if __name__ == "__main__":
     pats = sys.argv[1:]
     variants = [("fwd", False, True), ("fwd", False, False), ("fwd", True, True), ("dgrad", False, False), ("dgrad", True, False),
                 ("wgrad", False, False), ("wgrad", True, False)]
+    modes = os.environ.get("BL_MODES")
+    if modes:
+        variants = [v for v in variants if v[0] in modes.split(",")]
     for name, (H, C0, C1, Cout) in LAYERS.items():
         if pats and not any(p in name for p in pats):
             continue
