@@ -176,16 +176,14 @@ def imread(fp):
 
 
 def imsave(fp, mask, image_format):
-    """UNet/inference.py:221-227 (deflate-compressed TIFF for 'tif', plain save otherwise)"""
-    from PIL import Image
-    im = Image.fromarray(mask)
+    """UNet/inference.py:221-227: 'tif' -> BigTIFF, zlib level 6, 1024 x 1024 tiles (what skimage/tifffile is asked for
+    there, written by unetb200/tiffio.py); anything else -> the format's plain writer"""
     if 'tif' in image_format:
-        try:
-            im.save(fp, compression='tiff_adobe_deflate', big_tiff=True)
-        except (TypeError, ValueError, OSError):
-            im.save(fp, compression='tiff_adobe_deflate')
-    else:
-        im.save(fp)
+        from . import tiffio
+        tiffio.write_tiled_bigtiff(fp, mask, tile=(1024, 1024), level=6)
+        return
+    from PIL import Image
+    Image.fromarray(mask).save(fp)
 
 
 def segment_file(img_filepath, unet_model):
