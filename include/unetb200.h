@@ -170,6 +170,26 @@ int ub_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
  * scratch: planes * UB_ZSCORE_BLOCKS * 2 doubles */
 int ub_zscore(const void* src, int src_dtype, float* dst, double* scratch, int planes, long long plane, cudaStream_t stream);
 
+/* ---- training-time augmentation on raw-pixel batches (UNet/augment.py:19-174, called from UNet/imagereader.py:283-294) ---
+ * Planes are NCHW as the reader ships them. dtype codes here: 0 = u8, 1 = u16, 2 = f32.
+ * ub_aug_warp: dst[n,c,y,x] = bilinear sample of src[n,c] at (m0 x + m1 y + m2, m3 x + m4 y + m5), mats = double[N][6], the
+ *   INVERSE map skimage.transform.warp(order=1, mode='reflect') is given (augment.py:160-167); mirror boundary without edge
+ *   repeat; fp64 coordinates.  dst_dtype 2 = f32; 0 = uint8 class index rounded half-to-even (the mask, augment.py:155).
+ * ub_aug_minmax: partial = float[N][64][2] per-image (min, max) partials over all channels.
+ * ub_aug_noise: x += range_n * (factors[n][0] * z + factors[n][1]), z ~ N(0,1) Philox(seed, offset), range_n = max - min
+ *   from the partials (noise: augment.py:118-127; intensity shift: :141-153).
+ * ub_aug_blur_axis: one axis (0 = H, 1 = W) of scipy.ndimage.gaussian_filter(mode='reflect') (augment.py:130-139): per-image
+ *   symmetric taps weights = double[N][33] (w[0] = centre), radius = int[N] (0 = copy).
+ * ub_aug_chanmix: the same filter along the channel axis as an N x C x C matrix (double[N][C][C]), in place. */
+int ub_aug_warp(const void* src, int src_dtype, void* dst, int dst_dtype, const double* mats, int N, int C, int H, int W,
+                cudaStream_t stream);
+int ub_aug_minmax(const float* x, float* partial, int N, long long per_image, cudaStream_t stream);
+int ub_aug_noise(float* x, const float* minmax_partial, const float* factors, int N, long long per_image, unsigned long long seed,
+                 unsigned long long offset, cudaStream_t stream);
+int ub_aug_blur_axis(const float* src, float* dst, const double* weights, const int* radius, int axis, int N, int C, int H, int W,
+                     cudaStream_t stream);
+int ub_aug_chanmix(float* x, const double* mix, int N, int C, long long plane, cudaStream_t stream);
+
 /* ---- fp32 check mode (CUDA cores, fp32 storage) ----------------------------------------------------------------- */
 int ub_check_conv3x3(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias, float* out0, int Co0,
                      float* out1, int Co1, int N, int H, int W, int relu, cudaStream_t stream);

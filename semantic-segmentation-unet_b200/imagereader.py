@@ -15,8 +15,10 @@ What is different underneath ("device-side fast reader contract")
 pixels (uint8 / uint16 / float32) plus uint8 class indices from pinned memory -- 2-3 bytes per pixel instead of the
 reference's 4 + 4K -- and the z-score (ub_zscore, one plane per image and channel) runs on the device; the train step
 consumes the class index directly.  `get_example()` still yields the reference's (float32 CHW, int32 one-hot HWK)
-pair for callers that want it.  Augmentation (UNet/augment.py) is outside the hot path and not built: a reader
-constructed with use_augmentation=True says so once and serves un-augmented tiles.
+pair for callers that want it.  Augmentation (UNet/augment.py, applied per example at imagereader.py:283-294 with the
+class constants :78-85) runs on the DEVICE on the raw batch (unetb200/augment.py + csrc/augment.cu): a reader built with
+use_augmentation=True draws the per-example parameters in the reference's order (`draw_augmentation`) and
+`device_batch()` applies them between the upload and the z-score.
 """
 from __future__ import annotations
 
@@ -159,6 +161,15 @@ def imread(fp):
 
 # ---------------------------------------------------------------------------------------------- reader
 class ImageReader:
+    # augmentation parameters of the reference reader (UNet/imagereader.py:78-85)
+    _reflection_flag = True
+    _rotation_flag = True
+    _jitter_augmentation_severity = 0.1
+    _noise_augmentation_severity = 0.02
+    _scale_augmentation_severity = 0.1
+    _blur_max_sigma = 2
+    _intensity_augmentation_severity = None
+
     def __init__(self, img_db, use_augmentation=True, balance_classes=False, shuffle=True, num_workers=1, number_classes=2,
                  seed=None, rank=0, world_size=1):
         self.image_db = img_db
@@ -198,8 +209,8 @@ class ImageReader:
             print('Dataset Example Count by Class:')
             for i in range(len(self.keys)):
                 print('  class: {} count: {}'.format(i, len(self.keys[i])))
-        if self.use_augmentation:
-            print('ImageReader: augmentation (UNet/augment.py) is not part of the B200 hot path and is not built; serving un-augmented tiles')
+        self._np_rng = np.random.RandomState(seed if seed is None else (int(seed) + 7919 * rank) % (1 << 32))
+        self._augmenter = None
         self.key_idx = rank          # un-shuffled readers stride through the keys (imagereader.py:237-241)
         self._pinned = None
 
@@ -287,6 +298,27 @@ class ImageReader:
             xv[b] = img.transpose((2, 0, 1)) if tdt is not None else img.transpose((2, 0, 1)).astype(np.float32)
             lv[b] = mask
         return xi, li
+
+    def draw_augmentation(self, batch_size):
+        """per-example augmentation parameters of one batch (UNet/imagereader.py:287-294 -> augment.py:61-153)"""
+        from . import augment
+        H, W, _ = self.image_size
+        return augment.draw_params(self._np_rng, batch_size, H, W, self._rotation_flag, self._reflection_flag, self._jitter_augmentation_severity,
+                                   self._noise_augmentation_severity, self._scale_augmentation_severity, self._blur_max_sigma,
+                                   self._intensity_augmentation_severity)
+
+    def device_batch(self, batch_size, unet_model):
+        """one training / test batch on the model's device: upload raw pixels + class indices, augment (if enabled), z-score.
+        -> (float32 [B,C,H,W] normalised images, uint8 [B,H,W] labels), the pair UNet.train_step consumes"""
+        xi, li = self.next_raw_batch(batch_size)
+        dev = unet_model.device
+        raw, lab = xi.to(dev, non_blocking=True), li.to(dev, non_blocking=True)
+        if self.use_augmentation:
+            from . import augment
+            if self._augmenter is None:
+                self._augmenter = augment.DeviceAugmenter(dev, seed=int(self._np_rng.randint(0, 2 ** 31 - 1)))
+            raw, lab = self._augmenter(raw, lab, self.draw_augmentation(batch_size))
+        return unet_model.normalize_batch(raw), lab
 
     def src_dtype_code(self):
         """ub_zscore source code of the stored pixels: 0 = u8, 1 = u16, 2 = f32"""

@@ -136,9 +136,7 @@ def train_model(output_folder, batch_size, reader_count, train_lmdb_filepath, te
         test_summary = _Summary(os.path.join(output_folder, 'tensorboard-' + current_time, 'test')) if is_chief else None
 
         def device_batch(reader):
-            xi, li = reader.next_raw_batch(batch_size)
-            x = unet_model.normalize_batch(xi.to(dev, non_blocking=True))
-            return x, li.to(dev, non_blocking=True)
+            return reader.device_batch(batch_size, unet_model)      # upload, device augmentation (train reader), z-score
 
         epoch = 0
         print('Running Network')

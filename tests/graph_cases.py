@@ -464,7 +464,46 @@ def case_checkpoint_roundtrip():
     return r
 
 
+def case_reader_augmented():
+    """ImageReader(use_augmentation=True).device_batch: LMDB records -> raw upload -> device augmentation with the reference's
+    reader constants (UNet/imagereader.py:78-85, :283-294) -> per-tile z-score; and one train step on the result"""
+    import tempfile
+    from scipy.ndimage import gaussian_filter
+    import unetb200.imagereader as R
+    from unetb200.model import UNet
+    rng = np.random.default_rng(13)
+    recs = []
+    for i in range(6):
+        f = gaussian_filter(rng.normal(size=(64, 96)), 3)
+        img = np.clip(3000 + 4000 * f + rng.normal(0, 30, size=f.shape), 0, 65535).astype(np.uint16)
+        recs.append((f"im{i:03d}.tif", img[..., None], (f > 0.02).astype(np.uint8)))
+    r = {}
+    with tempfile.TemporaryDirectory() as d:
+        R.write_database(os.path.join(d, "t.lmdb"), recs)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            plain = R.ImageReader(os.path.join(d, "t.lmdb"), use_augmentation=False, shuffle=False, number_classes=2)
+            aug = R.ImageReader(os.path.join(d, "t.lmdb"), use_augmentation=True, shuffle=False, number_classes=2, seed=5)
+        m = UNet(2, 4, 1, 1e-3, seed=1)
+        x0, l0 = plain.device_batch(4, m)
+        x0, l0 = x0.clone(), l0.clone()
+        x1, l1 = aug.device_batch(4, m)
+        r["shape_ok"] = bool(tuple(x1.shape) == (4, 1, 64, 96) and x1.dtype == torch.float32 and tuple(l1.shape) == (4, 64, 96) and l1.dtype == torch.uint8)
+        r["mean"] = float(x1.mean(dim=(1, 2, 3)).abs().max())
+        r["std"] = [round(float(v), 4) for v in x1.std(dim=(1, 2, 3), unbiased=False)]
+        r["labels_in_range"] = bool(int(l1.max()) <= 1)
+        r["differs"] = float((x1 - x0).abs().mean())
+        r["fg_plain"], r["fg_aug"] = float(l0.float().mean()), float(l1.float().mean())
+        loss = float(m.train_step(x1, l1).item())
+        r["loss"] = loss
+    r["ok"] = bool(r["shape_ok"] and r["mean"] < 1e-3 and all(abs(v - 1.0) < 1e-2 for v in r["std"]) and r["labels_in_range"]
+                   and r["differs"] > 0.1 and abs(r["fg_aug"] - r["fg_plain"]) < 0.25 and np.isfinite(loss))
+    return r
+
+
 CASES = {
+    "reader_augmented": case_reader_augmented,
     "checkpoint_roundtrip": case_checkpoint_roundtrip,
     "estimate_radius_c1": lambda: case_estimate_radius(1, 2, 41),
     "estimate_radius_c3": lambda: case_estimate_radius(3, 4, 42),

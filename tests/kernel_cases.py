@@ -489,6 +489,79 @@ def case_check_convs(seed=13):
     return r
 
 
+def case_augment(C=1, dtype="u16", N=3, H=48, W=80, seed=0, rotation=True):
+    """unetb200.augment.DeviceAugmenter (csrc/augment.cu) against the oracle's restatement of UNet/augment.py with the same
+    drawn parameters; noise off (its field is Philox-generated on the device), so image and mask are comparable exactly."""
+    import unetb200.augment as UA
+    from oracle import augment_oracle as AO
+
+    class Rng:
+        def __init__(self, s):
+            self.r = np.random.RandomState(s)
+
+        def rand(self):
+            return self.r.rand()
+
+    rng = np.random.default_rng(seed)
+    if dtype == "u16":
+        raw = rng.integers(0, 65535, size=(N, C, H, W)).astype(np.uint16)
+        t = torch.tensor(raw.view(np.int16), device="cuda")
+    elif dtype == "u8":
+        raw = rng.integers(0, 255, size=(N, C, H, W)).astype(np.uint8)
+        t = torch.tensor(raw, device="cuda")
+    else:
+        raw = rng.normal(100.0, 20.0, size=(N, C, H, W)).astype(np.float32)
+        t = torch.tensor(raw, device="cuda")
+    from scipy.ndimage import gaussian_filter
+    lab = np.stack([(gaussian_filter(rng.normal(size=(H, W)), 3) > 0).astype(np.uint8) * (1 + (i % 2)) for i in range(N)])
+    p = UA.draw_params(Rng(seed), N, H, W, rotation_flag=rotation, reflection_flag=True, jitter_augmentation_severity=0.1,
+                       noise_augmentation_severity=0, scale_augmentation_severity=0.1, blur_augmentation_max_sigma=2,
+                       intensity_augmentation_severity=0.05)
+    p["blur_sigma"][0] = 1.3                      # at least one blurred and one un-blurred example
+    if N > 1:
+        p["blur_sigma"][1] = 0.0
+    aug = UA.DeviceAugmenter("cuda", seed=1)
+    out, lab_out = aug(t, torch.tensor(lab, device="cuda"), p)
+    out, lab_out = out.cpu().numpy(), lab_out.cpu().numpy()
+    e_img, agree = 0.0, 1.0
+    for i in range(N):
+        pi = {k: (v[i] if k != "orientation" else (None if np.isnan(v[i]) else v[i])) for k, v in p.items()}
+        ref_img, ref_mask = AO.augment_image(raw[i].transpose(1, 2, 0).astype(np.float32), lab[i], pi)
+        rng_i = float(ref_img.max() - ref_img.min())
+        e_img = max(e_img, float(np.abs(out[i].transpose(1, 2, 0) - ref_img).max() / rng_i))
+        agree = min(agree, float((lab_out[i] == ref_mask).mean()))
+    r = dict(e_img=e_img, mask_agree=agree, blur=[float(v) for v in p["blur_sigma"]], orientation=[float(v) for v in p["orientation"]])
+    r["ok"] = bool(e_img < 2e-6 and agree >= 0.999)      # image: fp32 intermediate vs the oracle's fp64; mask: exact-tie roundings only
+    return r
+
+
+def case_augment_noise(N=4, C=1, H=128, W=128):
+    """ub_aug_minmax + ub_aug_noise: sigma = noise_factor * (max - min) per image (UNet/augment.py:118-127), N(0,1) field statistics,
+    intensity shift = shift_factor * range (:141-153), different fields per call"""
+    C_ = _C()
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-5.0, 11.0, size=(N, C, H, W)).astype(np.float32)
+    x[:, :, 0, 0], x[:, :, 0, 1] = -5.0, 11.0
+    fac = np.array([[0.02, 0.0], [-0.01, 0.0], [0.0, 0.03], [0.0, 0.0]], dtype=np.float32)[:N]
+    xd = dev(x, torch.float32)
+    mm = torch.zeros(N * 64 * 2, device="cuda")
+    C_.call("ub_aug_minmax", xd, mm, N, C * H * W, stream())
+    m = mm.cpu().numpy().reshape(N, 64, 2)
+    ok_mm = bool(np.allclose(m[:, :, 0].min(1), -5.0) and np.allclose(m[:, :, 1].max(1), 11.0))
+    C_.call("ub_aug_noise", xd, mm, dev(fac, torch.float32), N, C * H * W, 1234, 0, stream())
+    d = xd.cpu().numpy().astype(np.float64) - x
+    s0, s1 = d[0].std(), d[1].std()
+    y = dev(x, torch.float32)
+    C_.call("ub_aug_noise", y, mm, dev(fac, torch.float32), N, C * H * W, 1234, 1 << 32, stream())
+    d2 = y.cpu().numpy().astype(np.float64) - x
+    z = d[0] / (0.02 * 16.0)
+    r = dict(minmax=ok_mm, std0=float(s0), std1=float(s1), mean0=float(d[0].mean()), shift2=float(d[2].mean()), untouched=float(np.abs(d[3]).max()),
+             kurt=float((z ** 4).mean()), corr_calls=float(np.corrcoef(d[0].ravel(), d2[0].ravel())[0, 1]))
+    r["ok"] = bool(ok_mm and abs(s0 - 0.32) < 0.01 and abs(s1 - 0.16) < 0.005 and abs(r["mean0"]) < 0.01 and abs(r["shift2"] - 0.48) < 1e-5
+                   and float(d[2].std()) < 1e-6 and r["untouched"] == 0.0 and abs(r["kurt"] - 3.0) < 0.15 and abs(r["corr_calls"]) < 0.05)
+    return r
+
+
 CASES = {
     # tcgen05 implicit GEMMs
     "conv_fwd_64_64": lambda: case_conv3x3_fwd(64, 0, 64),
@@ -535,4 +608,8 @@ CASES = {
     "zscore": case_zscore,
     "dropout_mask": case_dropout_mask,
     "check_convs": case_check_convs,
+    "augment_c1_u16": lambda: case_augment(1, "u16"),
+    "augment_c3_u8": lambda: case_augment(3, "u8", N=2, H=64, W=48, seed=1),
+    "augment_c2_f32_norot": lambda: case_augment(2, "f32", N=2, H=32, W=32, seed=2, rotation=False),
+    "augment_noise": case_augment_noise,
 }
