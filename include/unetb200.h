@@ -102,6 +102,12 @@ int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const
 int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
                       const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K,
                       int dtype, cudaStream_t stream);
+/* same, and accumulates the BatchNorm-backward sums of the 64-channel tensor dx differentiates (saved activation red_a, batch
+ * red_mean / red_rstd): red_partial[UB_STATS_ROWS][2][64], summed by ub_reduce_rows -- replaces ub_bn_bwd_reduce for that layer */
+int ub_head_bwd_apply_bnred(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
+                            const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K,
+                            int dtype, const void* red_a, const float* red_mean, const float* red_rstd, float* red_partial,
+                            cudaStream_t stream);
 /* Inference epilogue: argmax of the head written into each tile's zone of the uint8 mask -- UNet/inference.py:105-129.
  * x: [ntiles][h][w][64]; geo: device int[ntiles][6] = {cy0, cy1, cx0, cx1, dst_y, dst_x} (crop box inside the tile, destination
  * of its top-left corner in the mask); scale/shift: BatchNorm moving statistics of the head folded (gamma*rstd, beta-mean*scale);
@@ -146,6 +152,12 @@ int ub_bn_inference_rstd(const float* moving_var, float* rstd, int n, float eps,
 /* dy = maxpool_bwd(dpool, idx) + dskip (skip fan-out, model.py:91/:132 ...), optional dropout backward */
 int ub_maxpool2x2_bwd_add(const void* dpool, const unsigned char* idx, const void* dskip, const unsigned char* drop_mask, void* dy,
                           int N, int H, int W, int C, int dtype, cudaStream_t stream);
+/* same, and accumulates the BatchNorm-backward sums of the tensor dy differentiates (saved activation a, batch mean / rstd):
+ * red_partial[UB_STATS_ROWS][2][C] = per-block (sum dy, rstd * sum dy (a - mean)), to be summed by ub_reduce_rows -- replaces
+ * the ub_bn_bwd_reduce pass over dy and a */
+int ub_maxpool2x2_bwd_add_bnred(const void* dpool, const unsigned char* idx, const void* dskip, const unsigned char* drop_mask, void* dy,
+                                int N, int H, int W, int C, const void* a, const float* mean, const float* rstd, float* red_partial,
+                                int dtype, cudaStream_t stream);
 int ub_dropout_bwd(const void* in, const unsigned char* mask, void* out, long long n, int dtype, cudaStream_t stream);
 /* Philox4x32-10 Bernoulli(0.5) keep mask, one byte per element */
 int ub_dropout_mask(unsigned char* mask, long long n, unsigned long long seed, unsigned long long offset, cudaStream_t stream);

@@ -334,13 +334,21 @@ __global__ void __launch_bounds__(TPB, 3) bn_apply_pool_kernel(const T* __restri
   }
 }
 
-// dy[n,h,w,c] = (slot matches ? dpool : 0) + dskip   (skip fan-out sum), optional dropout backward
-template <typename T>
+// dy[n,h,w,c] = (slot matches ? dpool : 0) + dskip   (skip fan-out sum), optional dropout backward.
+// RED: dy is dL/dy of a BatchNorm'd tensor whose saved activation is `a`: the BatchNorm-backward sums of that layer
+// (red[row][0][c] = sum dy, red[row][1][c] = rstd_c * sum dy * (a - mean_c), of the STORED dy) are accumulated here, which
+// replaces the separate bn_bwd_reduce pass over dy and a.
+template <typename T, bool RED>
 __global__ void __launch_bounds__(TPB) pool_bwd_add_kernel(const T* __restrict__ dpool, const uint8_t* __restrict__ idx,
                                                            const T* __restrict__ dskip, const uint8_t* __restrict__ drop_mask,
-                                                           T* __restrict__ dy, int N, int H, int W, int C) {
+                                                           T* __restrict__ dy, int N, int H, int W, int C, const T* __restrict__ a,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           float* __restrict__ red) {
   const int G = C >> 3, Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)N * Ho * Wo * G;
+  float acc[2][8] = {};
+  float mu[8] = {};
+  if (RED) load8f(mean + (threadIdx.x % G) * 8, mu);      // gridDim.x * TPB is a multiple of G: a thread keeps its channel group
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < total; i += (long long)gridDim.x * TPB) {
     const int g = (int)(i % G);
     long long t = i / G;
@@ -356,12 +364,13 @@ __global__ void __launch_bounds__(TPB) pool_bwd_add_kernel(const T* __restrict__
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       const long long off = (((long long)n * H + 2 * ho + (s >> 1)) * W + 2 * wo + (s & 1)) * C + c0;
-      float f[8];
+      float f[8], av[8];
       if (dskip) V8<T>::load(dskip + off, f);
       else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = 0.f;
       }
+      if (RED) V8<T>::load(a + off, av);
       uint2 dm = make_uint2(0x01010101u, 0x01010101u);
       if (drop_mask) dm = __ldg(reinterpret_cast<const uint2*>(drop_mask + off));
       const uint8_t* dmb = reinterpret_cast<const uint8_t*>(&dm);
@@ -370,9 +379,21 @@ __global__ void __launch_bounds__(TPB) pool_bwd_add_kernel(const T* __restrict__
         float v = f[k] + (sl[k] == s ? dp[k] : 0.f);
         if (drop_mask) v = dmb[k] ? 2.f * v : 0.f;
         f[k] = v;
+        if (RED) {
+          const float vs = storage_round<T>(v);
+          acc[0][k] += vs;
+          acc[1][k] = fmaf(vs, av[k] - mu[k], acc[1][k]);
+        }
       }
       V8<T>::store(dy + off, f);
     }
+  }
+  if (RED) {
+    float rs[8];
+    load8f(rstd + (threadIdx.x % G) * 8, rs);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[1][k] *= rs[k];
+    block_channel_reduce<2>(acc, C, red);
   }
 }
 
@@ -769,7 +790,23 @@ int ub_maxpool2x2_bwd_add(const void* dpool, const unsigned char* idx, const voi
   UB_CHECK_SHAPE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool2x2_bwd_add: C %% 8, even H/W");
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
   const int grid = grid_for(total, TPB, ub_num_sms() * 16);
-  UB_DISPATCH_T(dtype, (pool_bwd_add_kernel<T><<<grid, TPB, 0, stream>>>((const T*)dpool, idx, (const T*)dskip, drop_mask, (T*)dy, N, H, W, C)));
+  UB_DISPATCH_T(dtype, (pool_bwd_add_kernel<T, false><<<grid, TPB, 0, stream>>>((const T*)dpool, idx, (const T*)dskip, drop_mask, (T*)dy, N, H, W,
+                                                                               C, nullptr, nullptr, nullptr, nullptr)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_maxpool2x2_bwd_add_bnred(const void* dpool, const unsigned char* idx, const void* dskip, const unsigned char* drop_mask, void* dy,
+                                int N, int H, int W, int C, const void* a, const float* mean, const float* rstd, float* red_partial,
+                                int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(dpool && idx && dy && a && mean && rstd && red_partial, "maxpool2x2_bwd_add_bnred: bad args");
+  UB_CHECK_SHAPE(channels_ok(C) && H % 2 == 0 && W % 2 == 0, "maxpool2x2_bwd_add_bnred: C=%d must be a power of two in [64,2048], even H/W", C);
+  UB_CUDA(cudaMemsetAsync(red_partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * C, stream));
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  const int cap = ub_num_sms() * 3 < UB_STATS_ROWS ? ub_num_sms() * 3 : UB_STATS_ROWS;      // one wave of resident blocks, one partial row each
+  const int grid = grid_for(total, TPB, cap);
+  UB_DISPATCH_T(dtype, (pool_bwd_add_kernel<T, true><<<grid, TPB, 0, stream>>>((const T*)dpool, idx, (const T*)dskip, drop_mask, (T*)dy, N, H, W,
+                                                                              C, (const T*)a, mean, rstd, red_partial)));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

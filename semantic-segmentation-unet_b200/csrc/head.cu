@@ -525,13 +525,24 @@ __global__ void __launch_bounds__(TPB) head_bwd_reduce_kernel(const float* __res
 
 // pass 2: dz_k = gamma_k rstd_k (dy_k - dbeta_k/P - xhat_k dgamma_k/P) [a_k > 0]
 //         dx[p][c] = sum_k w[k][c] dz_k   ;   partial[row] = { dW[k][c] (K*64), db[k] (K) }
-template <typename T, int K>
+template <typename T, int K, bool RED>
 __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ a, const T* __restrict__ x,
                                                              const float* __restrict__ w, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                              const float* __restrict__ dbeta, const float* __restrict__ dgamma,
-                                                             T* __restrict__ dx, float* __restrict__ partial, long long P) {
+                                                             T* __restrict__ dx, float* __restrict__ partial, long long P,
+                                                             const T* __restrict__ red_a, const float* __restrict__ red_mean,
+                                                             const float* __restrict__ red_rstd, float* __restrict__ red_out) {
+  // RED: dx is dL/dy of the BatchNorm'd 64-channel tensor below the head (dec1b); its backward sums
+  // red_out[row][0][c] = sum dx, red_out[row][1][c] = rstd_c * sum dx * (red_a - mean_c) (of the STORED dx) are accumulated here
   __shared__ float red[TPB / 32][K * 64 + K];
+  __shared__ float rred[RED ? TPB / 32 : 1][128];
+  float racc[2][8] = {};
+  float rmu[8] = {};
+  if (RED) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rmu[i] = red_mean[(threadIdx.x & 7) * 8 + i];
+  }
   const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float wr[K][8], accw[K][8] = {}, accb[K] = {};
@@ -583,8 +594,29 @@ __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __rest
           }
         }
         if (dx) st8<T>(dx + px[u] * 64 + sub * 8, o);
+        if (RED) {
+          float av[8];
+          ld8<T>(red_a + px[u] * 64 + sub * 8, av);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float vs = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16(o[i])) : o[i];
+            racc[0][i] += vs;
+            racc[1][i] = fmaf(vs, av[i] - rmu[i], racc[1][i]);
+          }
+        }
       }
     }
+  }
+  if (RED) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = racc[c][i];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 8) rred[warp][c * 64 + sub * 8 + i] = v;
+      }
   }
   // reduce over the 4 pixels of each warp (lanes with equal sub), then over warps through smem
 #pragma unroll
@@ -607,6 +639,15 @@ __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __rest
 #pragma unroll
     for (int wv = 0; wv < TPB / 32; ++wv) t += red[wv][i];
     partial[(size_t)blockIdx.x * ncomp + i] = t;
+  }
+  if (RED) {
+    for (int i = threadIdx.x; i < 128; i += TPB) {
+      float t = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < TPB / 32; ++wv) t += rred[wv][i];
+      if (i >= 64) t *= red_rstd[i - 64];
+      red_out[(size_t)blockIdx.x * 128 + i] = t;
+    }
   }
 }
 
@@ -839,17 +880,42 @@ int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const
 }
 
 // partial: UB_STATS_ROWS * (K*64 + K) floats; row layout {dW[K][64], db[K]}
-int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
-                      const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K, int dtype,
-                      cudaStream_t stream) {
+static int head_bwd_apply_launch(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
+                                 const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K,
+                                 int dtype, const void* red_a, const float* red_mean, const float* red_rstd, float* red_out,
+                                 cudaStream_t stream) {
   UB_CHECK_ARG(dy && a && x && w && mean && rstd && gamma && dbeta && dgamma && partial && P > 0, "head_bwd_apply: bad args");
   UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_bwd_apply: K");
   const int grid = grid_for(P, 64 * 4, UB_STATS_ROWS);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * (K * 64 + K), stream));
-  UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_bwd_apply_kernel<T, KK><<<grid, TPB, 0, stream>>>(dy, a, (const T*)x, w, mean, rstd, gamma, dbeta,
-                                                                                              dgamma, (T*)dx, partial, P))));
+  if (red_out) {
+    UB_CHECK_ARG(red_a && red_mean && red_rstd && dx, "head_bwd_apply_bnred: bad args");
+    UB_CUDA(cudaMemsetAsync(red_out, 0, sizeof(float) * UB_STATS_ROWS * 128, stream));
+    UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_bwd_apply_kernel<T, KK, true><<<grid, TPB, 0, stream>>>(
+                                              dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx, partial, P, (const T*)red_a, red_mean,
+                                              red_rstd, red_out))));
+  } else {
+    UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_bwd_apply_kernel<T, KK, false><<<grid, TPB, 0, stream>>>(
+                                              dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx, partial, P, nullptr, nullptr, nullptr,
+                                              nullptr))));
+  }
   UB_LAUNCH_CHECK();
   return UB_OK;
+}
+
+int ub_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
+                      const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K, int dtype,
+                      cudaStream_t stream) {
+  return head_bwd_apply_launch(dy, a, x, w, mean, rstd, gamma, dbeta, dgamma, dx, partial, P, K, dtype, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int ub_head_bwd_apply_bnred(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd,
+                            const float* gamma, const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K,
+                            int dtype, const void* red_a, const float* red_mean, const float* red_rstd, float* red_partial,
+                            cudaStream_t stream) {
+  UB_CHECK_ARG(red_partial, "head_bwd_apply_bnred: red_partial is null");
+  return head_bwd_apply_launch(dy, a, x, w, mean, rstd, gamma, dbeta, dgamma, dx, partial, P, K, dtype, red_a, red_mean, red_rstd, red_partial,
+                               stream);
 }
 
 int ub_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int ntiles, int h, int wd,

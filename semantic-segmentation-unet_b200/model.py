@@ -78,6 +78,7 @@ class UNet:
         self._graphs = {}
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
+        self.fuse_bn_reduce_ew = os.environ.get("UB_FUSE_EW", "0") == "1"   # ... and in the pool-backward / head-backward passes
         self._build_layout()
         self.class_weights = None
         if class_weights is not None:
@@ -712,8 +713,17 @@ class UNet:
             self._call("ub_head_bwd_reduce", dl, a, mean, rstd, self.partial, P, K)
             self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2 * K, K, dbeta, 1.0)
             self._call("ub_reduce_rows", self.partial[K:], _C.UB_STATS_ROWS, 2 * K, K, dgamma, 1.0)
-        self._call("ub_head_bwd_apply", dl, a, self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
-                   self.P[L.off_gamma:L.off_gamma + K], dbeta, dgamma, self._b("g:dec1b"), self.partial, P, K, self.act_code)
+        if self.fuse_bn_reduce_ew and self.precision == "bf16" and not infer and K <= 4:
+            # the head's dgrad writes dL/dy of dec1b: that layer's BatchNorm-backward sums come out of the same pass
+            Ld = Ls["dec1b"]
+            rm, rr = self._bn_vectors(Ld, True)
+            self._call("ub_head_bwd_apply_bnred", dl, a, self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
+                       self.P[L.off_gamma:L.off_gamma + K], dbeta, dgamma, self._b("g:dec1b"), self.partial, P, K, self.act_code,
+                       self._b("a:dec1b"), rm, rr, self.partial_red)
+            self._red_ready = "dec1b"
+        else:
+            self._call("ub_head_bwd_apply", dl, a, self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
+                       self.P[L.off_gamma:L.off_gamma + K], dbeta, dgamma, self._b("g:dec1b"), self.partial, P, K, self.act_code)
         ncomp = K * 64 + K
         self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, ncomp, K * 64, self.G[L.off_w:L.off_w + K * 64], 1.0)
         self._call("ub_reduce_rows", self.partial[K * 64:], _C.UB_STATS_ROWS, ncomp, K, self.G[L.off_b:L.off_b + K], 1.0)
@@ -757,8 +767,17 @@ class UNet:
         for lvl in (4, 3, 2, 1):
             h, w = self._dims(H, W, lvl)
             La, Lb = Ls[f"enc{lvl}a"], Ls[f"enc{lvl}b"]
-            self._call("ub_maxpool2x2_bwd_add", self._b(f"gpool{lvl}"), self._b(f"idx{lvl}"), self._b(f"gskip{lvl}"),
-                       dm.get("drop4") if lvl == 4 else None, self._b("g:" + Lb.name), N, h, w, Lb.cout, self.act_code)
+            if self.fuse_bn_reduce_ew and self.precision == "bf16" and not infer:
+                # the pass that assembles dL/dy of enc<l>b also accumulates that layer's BatchNorm-backward sums
+                rm, rr = self._bn_vectors(Lb, True)
+                self._cur = Lb.name
+                self._call("ub_maxpool2x2_bwd_add_bnred", self._b(f"gpool{lvl}"), self._b(f"idx{lvl}"), self._b(f"gskip{lvl}"),
+                           dm.get("drop4") if lvl == 4 else None, self._b("g:" + Lb.name), N, h, w, Lb.cout, self._b("a:" + Lb.name), rm, rr,
+                           self.partial_red, self.act_code)
+                self._red_ready = Lb.name
+            else:
+                self._call("ub_maxpool2x2_bwd_add", self._b(f"gpool{lvl}"), self._b(f"idx{lvl}"), self._b(f"gskip{lvl}"),
+                           dm.get("drop4") if lvl == 4 else None, self._b("g:" + Lb.name), N, h, w, Lb.cout, self.act_code)
             self._conv_bwd(Lb, self._b("y:" + La.name), None, N, h, w, self._b("g:" + La.name), None, red=La)
             done(Lb.name)
             if lvl > 1:

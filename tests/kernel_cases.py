@@ -302,6 +302,39 @@ def case_pool_bwd(C_=64, N=2, H=16, W=24, seed=7):
     return dict(err=e, ok=bool(e < 1e-6))
 
 
+def case_pool_bwd_bnred(C_=128, N=2, H=16, W=24, seed=17, dtype="bf16", drop=True):
+    """ub_maxpool2x2_bwd_add_bnred: same dy as the plain kernel plus the BatchNorm-backward sums of the layer dy belongs to
+    (what ub_bn_bwd_reduce computes from the stored dy and the saved activation a)"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    tdt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    code = C.UB_BF16 if dtype == "bf16" else C.UB_F32
+    rnd = bf16_round if dtype == "bf16" else (lambda v: np.asarray(v, dtype=np.float32).astype(np.float64))
+    dp = rnd(rng.normal(size=(N, H // 2, W // 2, C_)))
+    idx = rng.integers(0, 4, size=(N, H // 2, W // 2, C_)).astype(np.uint8)
+    dskip = rnd(rng.normal(size=(N, H, W, C_)))
+    mask = rng.integers(0, 2, size=(N, H, W, C_)).astype(np.uint8) if drop else None
+    a = rnd(np.maximum(rng.normal(0.3, 1.0, size=(N, H, W, C_)), 0))
+    mean = rng.normal(0.4, 0.1, size=C_).astype(np.float32)
+    rstd = rng.uniform(0.5, 2.0, size=C_).astype(np.float32)
+    ref = ON.pool_bwd(dp, idx.astype(np.int64)) + dskip
+    if drop:
+        ref = ref * mask * 2.0
+    dy = torch.empty((N, H, W, C_), dtype=tdt, device="cuda")
+    red = torch.full((C.UB_STATS_ROWS * 2 * C_,), 7.0, dtype=torch.float32, device="cuda")
+    C.call("ub_maxpool2x2_bwd_add_bnred", dev(dp, tdt), dev(idx, torch.uint8), dev(dskip, tdt), dev(mask, torch.uint8) if drop else None, dy,
+           N, H, W, C_, dev(a, tdt), dev(mean, torch.float32), dev(rstd, torch.float32), red, code, stream())
+    torch.cuda.synchronize()
+    got = dy.float().cpu().numpy().astype(np.float64)
+    s0, s1 = stats_from_partial(red, C_)
+    xh = (a - mean.astype(np.float64)) * rstd.astype(np.float64)
+    e = rel_err(got, ref)
+    e0 = rel_err(s0, got.sum((0, 1, 2)))                 # sums are of the STORED gradient
+    e1 = rel_err(s1, (got * xh).sum((0, 1, 2)))
+    tol = 1e-2 if dtype == "bf16" else 1e-6
+    return dict(err=e, err_sum=e0, err_sumx=e1, ok=bool(e < tol and e0 < 1e-5 and e1 < 1e-5))
+
+
 def case_conv_first(Cin=1, N=2, H=16, W=24, seed=8):
     C = _C()
     rng = np.random.default_rng(seed)
@@ -377,14 +410,30 @@ def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
     gw = torch.empty(K * 64 + K, device="cuda")
     C.call("ub_head_bwd_apply", dl, a_d, xd, wd, mean, rstd, gd, red[:K], red[K:], dx, partial, P, K, C.UB_F32, stream())
     C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, K * 64 + K, K * 64 + K, gw, 1.0, stream())
+    # fused variant: same dx / partials, plus the BatchNorm-backward sums of the 64-channel tensor below the head
+    ra = np.maximum(rng.normal(0.2, 1.0, size=(P, 64)), 0).astype(np.float32)
+    rmean = rng.normal(0.4, 0.1, size=64).astype(np.float32)
+    rrstd = rng.uniform(0.5, 2.0, size=64).astype(np.float32)
+    dx2 = torch.empty((P, 64), dtype=torch.float32, device="cuda")
+    partial2 = torch.empty_like(partial)
+    redp = torch.full((C.UB_STATS_ROWS * 128,), 3.0, device="cuda")
+    gw2 = torch.empty(K * 64 + K, device="cuda")
+    C.call("ub_head_bwd_apply_bnred", dl, a_d, xd, wd, mean, rstd, gd, red[:K], red[K:], dx2, partial2, P, K, C.UB_F32,
+           dev(ra, torch.float32), dev(rmean, torch.float32), dev(rrstd, torch.float32), redp, stream())
+    C.call("ub_reduce_rows", partial2, C.UB_STATS_ROWS, K * 64 + K, K * 64 + K, gw2, 1.0, stream())
     torch.cuda.synchronize()
+    s0, s1 = stats_from_partial(redp, 64)
+    dxn = dx.cpu().numpy().astype(np.float64)
+    fused = dict(e_fused_dx=float((dx2 - dx).abs().max()), e_fused_gw=float((gw2 - gw).abs().max()),
+                 e_red0=rel_err(s0, dxn.sum(0)), e_red1=rel_err(s1, (dxn * ((ra - rmean).astype(np.float64) * rrstd)).sum(0)))
     la = la.cpu().numpy()
     r = dict(e_a=rel_err(a_d.cpu().numpy(), a), e_sm=rel_err(sm.cpu().numpy(), p), e_loss=abs(la[0] - loss_ref) / abs(loss_ref),
              e_acc=abs(la[1] - acc_ref), e_dl=rel_err(dl.cpu().numpy(), dy_ref), e_dbeta=rel_err(red[:K].cpu().numpy(), dbeta),
              e_dgamma=rel_err(red[K:].cpu().numpy(), dgamma), e_dx=rel_err(dx.cpu().numpy(), dx_ref),
              e_dW=rel_err(gw[:K * 64].cpu().numpy().reshape(K, 64), dW_ref), e_db=rel_err(gw[K * 64:].cpu().numpy(), db_ref))
+    r.update(fused)
     r = {k: float(v) for k, v in r.items()}
-    r["ok"] = bool(all(v < 2e-4 for k, v in r.items() if k.startswith("e_")))
+    r["ok"] = bool(all(v < 2e-4 for k, v in r.items() if k.startswith("e_")) and r["e_fused_dx"] == 0.0 and r["e_fused_gw"] == 0.0)
     return r
 
 
@@ -599,6 +648,9 @@ CASES = {
     "bn_bwd_bf16_512": lambda: case_bn_bwd(512, N=1, H=8, W=8, dtype="bf16"),
     "bn_bwd_norelu": lambda: case_bn_bwd(128, dtype="f32", relu=0),
     "pool_bwd": case_pool_bwd,
+    "pool_bwd_bnred_bf16": case_pool_bwd_bnred,
+    "pool_bwd_bnred_f32_nodrop": lambda: case_pool_bwd_bnred(64, N=1, H=8, W=8, dtype="f32", drop=False),
+    "pool_bwd_bnred_512": lambda: case_pool_bwd_bnred(512, N=3, H=32, W=32, dtype="bf16", drop=False),
     "conv_first_c1": lambda: case_conv_first(1),
     "conv_first_c3": lambda: case_conv_first(3),
     "conv_first_c2_oddw": lambda: case_conv_first(2, W=22),
