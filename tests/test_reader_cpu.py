@@ -118,3 +118,22 @@ def test_early_stopping_selection():
     from unetb200.train import select_best_epoch
     assert select_best_epoch([0.5, 0.40004, 0.4, 0.41]) == 1          # first epoch within 1e-4 of the minimum
     assert select_best_epoch([0.3]) == 0
+
+
+def test_reader_draws_augmentation_with_the_reference_constants(tmp_path):
+    """UNet/imagereader.py:78-85: rotation + reflection on, jitter 0.1, noise 0.02, scale 0.1, blur sigma <= 2, intensity off"""
+    db = str(tmp_path / "aug.lmdb")
+    R.write_database(db, _pairs(4))
+    a = R.ImageReader(db, use_augmentation=True, shuffle=True, number_classes=3, seed=3)
+    b = R.ImageReader(db, use_augmentation=True, shuffle=True, number_classes=3, seed=3)
+    p, q = a.draw_augmentation(64), b.draw_augmentation(64)
+    assert all(np.array_equal(p[k], q[k], equal_nan=True) for k in p)             # seeded: reproducible
+    assert ((0 <= p["orientation"]) & (p["orientation"] < 360)).all()
+    assert 5 < p["reflect_x"].sum() < 59 and 5 < p["reflect_y"].sum() < 59
+    assert np.abs(p["jitter_x"]).max() <= int(0.1 * 48) and np.abs(p["jitter_y"]).max() <= int(0.1 * 32)
+    assert (p["scale_x"] >= 0.9).all() and (p["scale_x"] <= 1.1).all() and (p["scale_y"] >= 0.9).all() and (p["scale_y"] <= 1.1).all()
+    assert np.abs(p["noise_factor"]).max() <= 0.02 and (p["noise_factor"] < 0).any() and (p["noise_factor"] > 0).any()
+    assert (p["blur_sigma"] >= 0).all() and p["blur_sigma"].max() <= 2 and (p["blur_sigma"] == 0).sum() > 10     # negative draws = no blur
+    assert (p["shift_factor"] == 0).all()
+    r1 = R.ImageReader(db, use_augmentation=True, shuffle=True, number_classes=3, seed=3, rank=1, world_size=2)
+    assert not np.array_equal(r1.draw_augmentation(8)["orientation"], a.draw_augmentation(8)["orientation"])      # ranks draw differently
