@@ -45,13 +45,16 @@ __global__ void __launch_bounds__(TPB) aug_warp_kernel(const TI* __restrict__ sr
   const double m0 = mats[n * 6 + 0], m1 = mats[n * 6 + 1], m2 = mats[n * 6 + 2], m3 = mats[n * 6 + 3], m4 = mats[n * 6 + 4],
                m5 = mats[n * 6 + 5];
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < plane; i += (long long)gridDim.x * TPB) {
-    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    const int y = (int)((unsigned)i / (unsigned)W), x = (int)((unsigned)i - (unsigned)y * (unsigned)W);      // plane < 2^31 (host check)
     const double c = m0 * x + m1 * y + m2;
     const double r = m3 * x + m4 * y + m5;
     const double fr = floor(r), fc = floor(c);
     const long long minr = (long long)fr, minc = (long long)fc, maxr = (long long)ceil(r), maxc = (long long)ceil(c);
     const double dr = r - fr, dc = c - fc;
-    const long long r0 = reflect_nodup(H, minr), r1 = reflect_nodup(H, maxr), c0 = reflect_nodup(W, minc), c1 = reflect_nodup(W, maxc);
+    // in-range coordinates (almost every sample) skip the 64-bit mirror arithmetic
+    const bool inside = minr >= 0 && maxr < H && minc >= 0 && maxc < W;
+    const int r0 = inside ? (int)minr : (int)reflect_nodup(H, minr), r1 = inside ? (int)maxr : (int)reflect_nodup(H, maxr);
+    const int c0 = inside ? (int)minc : (int)reflect_nodup(W, minc), c1 = inside ? (int)maxc : (int)reflect_nodup(W, maxc);
     const double top = (1.0 - dc) * px(s, r0 * W + c0) + dc * px(s, r0 * W + c1);
     const double bot = (1.0 - dc) * px(s, r1 * W + c0) + dc * px(s, r1 * W + c1);
     const double v = (1.0 - dr) * top + dr * bot;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(TPB) aug_blur_axis_kernel(const float* __restr
       d[i] = s[i];
       continue;
     }
-    const int y = (int)(i / W), x = (int)(i - (long long)y * W);
+    const int y = (int)((unsigned)i / (unsigned)W), x = (int)((unsigned)i - (unsigned)y * (unsigned)W);
     double acc = 0.0;
     if (axis == 0) {
       for (int k = -rad; k <= rad; ++k) acc += w[k < 0 ? -k : k] * (double)s[(long long)reflect_dup(H, y + k) * W + x];
@@ -212,6 +215,7 @@ int ub_aug_warp(const void* src, int src_dtype, void* dst, int dst_dtype, const 
   UB_CHECK_ARG(src && dst && mats && N > 0 && C > 0 && H > 0 && W > 0, "aug_warp: bad args");
   UB_CHECK_ARG(src != dst, "aug_warp: in-place warps are not possible");
   UB_CHECK_SHAPE((long long)N * C <= 65535, "aug_warp: N*C=%lld planes exceed the grid limit", (long long)N * C);
+  UB_CHECK_SHAPE((long long)H * W < (1ll << 31), "aug_warp: planes of %d x %d pixels exceed 2^31", H, W);
   const dim3 grid(blocks_for((long long)H * W, ub_num_sms() * 8), N * C);
   if (dst_dtype == 2) {
     if (src_dtype == 0) aug_warp_kernel<uint8_t, float, false><<<grid, TPB, 0, stream>>>((const uint8_t*)src, (float*)dst, mats, C, H, W);
@@ -251,7 +255,7 @@ int ub_aug_blur_axis(const float* src, float* dst, const double* weights, const 
                      cudaStream_t stream) {
   UB_CHECK_ARG(src && dst && weights && radius && src != dst && (axis == 0 || axis == 1) && N > 0 && C > 0 && H > 0 && W > 0,
                "aug_blur_axis: bad args");
-  UB_CHECK_SHAPE((long long)N * C <= 65535, "aug_blur_axis: N*C");
+  UB_CHECK_SHAPE((long long)N * C <= 65535 && (long long)H * W < (1ll << 31), "aug_blur_axis: N*C planes / plane size");
   aug_blur_axis_kernel<<<dim3(blocks_for((long long)H * W, ub_num_sms() * 8), N * C), TPB, 0, stream>>>(src, dst, weights, radius, axis, C, H, W);
   UB_LAUNCH_CHECK();
   return UB_OK;

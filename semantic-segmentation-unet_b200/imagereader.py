@@ -275,17 +275,25 @@ class ImageReader:
             yield self.get_example()
 
     # B200 path -----------------------------------------------------------------------------------------------
-    def next_raw_batch(self, batch_size):
-        """-> (images [B,C,H,W] in the stored dtype, labels uint8 [B,H,W]) in pinned host memory (reused buffers)"""
+    def next_raw_batch(self, batch_size, slot=0):
+        """-> (images [B,C,H,W] in the stored dtype, labels uint8 [B,H,W]) in pinned host memory.  The buffers of a `slot` are
+        reused; if an upload from them is still in flight (`mark_uploaded`) the host waits for it before overwriting them."""
         import torch
         H, W, C = self.image_size
         dt = self.img_dtype
         tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.int16, np.dtype(np.float32): torch.float32}.get(dt)
-        if self._pinned is None or self._pinned[0].shape[0] != batch_size:
+        if self._pinned is None:
+            self._pinned, self._uploaded = {}, {}
+        buf = self._pinned.get(slot)
+        if buf is None or buf[0].shape[0] != batch_size:
             pin = torch.cuda.is_available()
-            self._pinned = (torch.empty((batch_size, C, H, W), dtype=tdt or torch.float32, pin_memory=pin),
-                            torch.empty((batch_size, H, W), dtype=torch.uint8, pin_memory=pin))
-        xi, li = self._pinned
+            buf = (torch.empty((batch_size, C, H, W), dtype=tdt or torch.float32, pin_memory=pin),
+                   torch.empty((batch_size, H, W), dtype=torch.uint8, pin_memory=pin))
+            self._pinned[slot] = buf
+        ev = self._uploaded.pop(slot, None)
+        if ev is not None:
+            ev.synchronize()
+        xi, li = buf
         xv = xi.numpy()
         if tdt is torch.int16:
             xv = xv.view(np.uint16)
@@ -299,6 +307,10 @@ class ImageReader:
             lv[b] = mask
         return xi, li
 
+    def mark_uploaded(self, slot, event):
+        """`event` (recorded after the async H2D copies of this slot's pinned buffers) guards their reuse"""
+        self._uploaded[slot] = event
+
     def draw_augmentation(self, batch_size):
         """per-example augmentation parameters of one batch (UNet/imagereader.py:287-294 -> augment.py:61-153)"""
         from . import augment
@@ -307,18 +319,25 @@ class ImageReader:
                                    self._noise_augmentation_severity, self._scale_augmentation_severity, self._blur_max_sigma,
                                    self._intensity_augmentation_severity)
 
-    def device_batch(self, batch_size, unet_model):
-        """one training / test batch on the model's device: upload raw pixels + class indices, augment (if enabled), z-score.
-        -> (float32 [B,C,H,W] normalised images, uint8 [B,H,W] labels), the pair UNet.train_step consumes"""
-        xi, li = self.next_raw_batch(batch_size)
+    def device_batch(self, batch_size, unet_model, slot=0):
+        """one training / test batch on the model's device, on the CURRENT stream: upload raw pixels + class indices, augment
+        (if enabled), z-score.  -> (float32 [B,C,H,W] normalised images, uint8 [B,H,W] labels), the pair UNet.train_step
+        consumes.  `slot` names the pinned staging buffers and the device output buffer (callers that keep two batches alive,
+        unetb200.train's one-ahead prefetch, alternate slots)."""
+        import torch
+        xi, li = self.next_raw_batch(batch_size, slot)
         dev = unet_model.device
         raw, lab = xi.to(dev, non_blocking=True), li.to(dev, non_blocking=True)
+        if dev.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            self.mark_uploaded(slot, ev)
         if self.use_augmentation:
             from . import augment
             if self._augmenter is None:
                 self._augmenter = augment.DeviceAugmenter(dev, seed=int(self._np_rng.randint(0, 2 ** 31 - 1)))
             raw, lab = self._augmenter(raw, lab, self.draw_augmentation(batch_size))
-        return unet_model.normalize_batch(raw), lab
+        return unet_model.normalize_batch(raw, slot="{}:{}".format(id(self), slot)), lab
 
     def src_dtype_code(self):
         """ub_zscore source code of the stored pixels: 0 = u8, 1 = u16, 2 = f32"""

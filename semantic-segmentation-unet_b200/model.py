@@ -839,16 +839,16 @@ class UNet:
             raise IOError(f"labels must be [N,H,W] class indices, got {tuple(t.shape)}")
         return t.to(torch.uint8).contiguous()
 
-    def normalize_batch(self, raw, src_code=None):
+    def normalize_batch(self, raw, src_code=None, slot=""):
         """per-tile, per-channel z-score on the device (UNet/imagereader.py:300, :33-66): raw [N,C,H,W] uint8 / uint16
-        (as int16 bits) / float32 device tensor -> float32 NCHW in a persistent buffer"""
+        (as int16 bits) / float32 device tensor -> float32 NCHW in a persistent buffer (one per `slot`)"""
         N, C, H, W = raw.shape
         if src_code is None:
             src_code = {torch.uint8: 0, torch.int16: 1, torch.float32: 2}.get(raw.dtype, 1 if str(raw.dtype) == "torch.uint16" else None)
             if src_code is None:
                 raise IOError(f"unsupported pixel dtype {raw.dtype}")
-        out = self._ensure("x_norm", N * C * H * W, torch.float32)[:N * C * H * W].view(N, C, H, W)
-        scratch = self._ensure("zscore_scratch", N * C * _C.UB_ZSCORE_BLOCKS * 2, torch.float64)
+        out = self._ensure("x_norm" + str(slot), N * C * H * W, torch.float32)[:N * C * H * W].view(N, C, H, W)
+        scratch = self._ensure("zscore_scratch" + str(slot), N * C * _C.UB_ZSCORE_BLOCKS * 2, torch.float64)
         self._cur = "input"
         self._call("ub_zscore", raw.contiguous(), src_code, out, scratch, N * C, H * W)
         return out

@@ -136,7 +136,46 @@ def train_model(output_folder, batch_size, reader_count, train_lmdb_filepath, te
         test_summary = _Summary(os.path.join(output_folder, 'tensorboard-' + current_time, 'test')) if is_chief else None
 
         def device_batch(reader):
-            return reader.device_batch(batch_size, unet_model)      # upload, device augmentation (train reader), z-score
+            return reader.device_batch(batch_size, unet_model)      # upload, z-score (test reader: on the step's stream)
+
+        class _Prefetch:
+            """The next training batch is uploaded, augmented and z-scored on a side stream while the current step runs (the
+            reference's dataset.prefetch, UNet/train.py:85).  Two slots: a slot is rewritten only after the step that consumed
+            it has finished on the device."""
+
+            def __init__(self, reader):
+                self.reader = reader
+                self.stream = torch.cuda.Stream(device=dev)
+                self.slot = 0
+                self.step_done = [None, None]
+                self.next = None
+
+            def _issue(self):
+                k = self.slot
+                self.slot ^= 1
+                if self.step_done[k] is not None:
+                    self.stream.wait_event(self.step_done[k])
+                with torch.cuda.stream(self.stream):
+                    x, lab = self.reader.device_batch(batch_size, unet_model, slot=k)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                lab.record_stream(torch.cuda.current_stream(dev))         # consumed by the step on the main stream
+                return x, lab, ev, k
+
+            def get(self):
+                if self.next is None:
+                    self.next = self._issue()
+                x, lab, ev, k = self.next
+                torch.cuda.current_stream(dev).wait_event(ev)
+                self.next = self._issue()
+                return x, lab, k
+
+            def consumed(self, k):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                self.step_done[k] = ev
+
+        prefetch = _Prefetch(train_reader)
 
         epoch = 0
         print('Running Network')
@@ -164,8 +203,9 @@ def train_model(output_folder, batch_size, reader_count, train_lmdb_filepath, te
 
             step = 0
             while step <= cur_train_epoch_size:          # steps 0..n inclusive (UNet/train.py:136-138)
-                x, lab = device_batch(train_reader)
+                x, lab, slot = prefetch.get()
                 unet_model.dist_train_step(strategy, (x, lab, train_loss_metric, train_acc_metric))
+                prefetch.consumed(slot)
                 if pending is not None:
                     flush(pending)
                 vals = torch.empty(2, dtype=torch.float32, pin_memory=True)
