@@ -117,11 +117,26 @@ __global__ void __launch_bounds__(TPB) aug_noise_kernel(float* __restrict__ x, c
                                                         unsigned long long offset) {
   const int n = blockIdx.y;
   __shared__ float s_range;
+  __shared__ float s_lo[MM_BLOCKS / 32], s_hi[MM_BLOCKS / 32];
+  if (threadIdx.x < MM_BLOCKS) {          // one partial per thread, shuffle min/max (order-independent)
+    float lo = partial[((long long)n * MM_BLOCKS + threadIdx.x) * 2 + 0];
+    float hi = partial[((long long)n * MM_BLOCKS + threadIdx.x) * 2 + 1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      s_lo[threadIdx.x >> 5] = lo;
+      s_hi[threadIdx.x >> 5] = hi;
+    }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    float lo = INFINITY, hi = -INFINITY;
-    for (int b = 0; b < MM_BLOCKS; ++b) {
-      lo = fminf(lo, partial[((long long)n * MM_BLOCKS + b) * 2 + 0]);
-      hi = fmaxf(hi, partial[((long long)n * MM_BLOCKS + b) * 2 + 1]);
+    float lo = s_lo[0], hi = s_hi[0];
+    for (int w = 1; w < MM_BLOCKS / 32; ++w) {
+      lo = fminf(lo, s_lo[w]);
+      hi = fmaxf(hi, s_hi[w]);
     }
     s_range = hi - lo;
   }

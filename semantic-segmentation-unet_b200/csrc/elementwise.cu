@@ -676,11 +676,31 @@ template <typename TI>
 __global__ void __launch_bounds__(TPB) zscore_apply_kernel(const TI* __restrict__ x, float* __restrict__ y, const double* __restrict__ sums,
                                                            int nblk, long long plane) {
   __shared__ float s_mu, s_inv;
-  if (threadIdx.x == 0) {
+  __shared__ double sh[2][TPB / 32];
+  {
+    // every block reduces the plane's partials the same way (fixed shuffle tree, then warp totals in order): one load per
+    // thread instead of a serial loop on thread 0, which dominated this kernel for tile-sized planes
     double ts = 0.0, tq = 0.0;
-    for (int b = 0; b < nblk; ++b) {
+    for (int b = threadIdx.x; b < nblk; b += TPB) {
       ts += sums[((size_t)blockIdx.y * nblk + b) * 2 + 0];
       tq += sums[((size_t)blockIdx.y * nblk + b) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      tq += __shfl_xor_sync(0xffffffffu, tq, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      sh[0][threadIdx.x >> 5] = ts;
+      sh[1][threadIdx.x >> 5] = tq;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < TPB / 32; ++w) {
+      ts += sh[0][w];
+      tq += sh[1][w];
     }
     const double mu = ts / (double)plane;
     double var = tq / (double)plane - mu * mu;
