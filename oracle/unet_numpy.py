@@ -198,3 +198,60 @@ class ManualUNet:
                 d = d * self.drop["drop4"]
             d = self._conv_bwd(f"enc{lvl}a", self._conv_bwd(f"enc{lvl}b", d), need_dx=(lvl != 1))
         return self.g
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BatchNorm folded into the CONSUMER convolution ("the plan for it"): y = s * a + t per input channel, the conv
+# reads `a` with weights W' = W * s[ci]; because 'same' padding is applied to y (zeros), the constant t contributes only
+# through the taps that fall INSIDE the image: a bias that takes 9 values per output channel (3 row cases x 3 column cases).
+def fold_weights(w_hwio, s, t):
+    """-> (W' [k,k,Ci,Co] = W * s[ci], Tt [k,k,Co] = sum_ci W[dy,dx,ci,co] * t[ci])"""
+    return w_hwio * s[None, None, :, None], np.einsum("yxio,i->yxo", w_hwio, t)
+
+
+def border_case_bias(Tt, b):
+    """bias[row_case][col_case][co]: case 0 = first row/column (tap -1 is outside), 1 = interior, 2 = last row/column (tap +1
+    is outside).  For a 1-pixel-high/wide image both neighbours are outside: handled by `conv_fwd_folded` via explicit masks."""
+    k = Tt.shape[0]
+    out = np.zeros((3, 3, Tt.shape[2]), dtype=Tt.dtype)
+    for rc in range(3):
+        for cc in range(3):
+            rows = [d for d in range(k) if not (rc == 0 and d == 0) and not (rc == 2 and d == k - 1)]
+            cols = [d for d in range(k) if not (cc == 0 and d == 0) and not (cc == 2 and d == k - 1)]
+            out[rc, cc] = b + sum(Tt[dy, dx] for dy in rows for dx in cols)
+    return out
+
+
+def conv_fwd_folded(a, w_hwio, b, s, t):
+    """== conv_fwd(s * a + t, W, b) for H, W >= 2, computed from `a` alone (what the folded kernel will do)"""
+    N, H, W, _ = a.shape
+    assert H >= 2 and W >= 2
+    Wf, Tt = fold_weights(w_hwio, s, t)
+    z = conv_fwd(a, Wf, np.zeros_like(b))
+    bias = border_case_bias(Tt, b)
+    rc = np.ones(H, dtype=np.int64)
+    rc[0], rc[-1] = 0, 2
+    cc = np.ones(W, dtype=np.int64)
+    cc[0], cc[-1] = 0, 2
+    return z + bias[rc[:, None], cc[None, :]][None]
+
+
+def border_sums(dz):
+    """Sdz[dy,dx,co] = sum of dz over the output pixels whose tap (dy-1, dx-1) neighbour lies inside the image: the total minus
+    the first / last row and column strips (plus the doubly-subtracted corner)."""
+    N, H, W, Co = dz.shape
+    tot = dz.sum((0, 1, 2))
+    row = {0: dz[:, 0].sum((0, 1)), 1: np.zeros(Co, dz.dtype), 2: dz[:, H - 1].sum((0, 1))}      # excluded strip per tap row
+    col = {0: dz[:, :, 0].sum((0, 1)), 1: np.zeros(Co, dz.dtype), 2: dz[:, :, W - 1].sum((0, 1))}
+    cor = {(0, 0): dz[:, 0, 0].sum(0), (0, 2): dz[:, 0, W - 1].sum(0), (2, 0): dz[:, H - 1, 0].sum(0), (2, 2): dz[:, H - 1, W - 1].sum(0)}
+    out = np.zeros((3, 3, Co), dtype=dz.dtype)
+    for dy in range(3):
+        for dx in range(3):
+            out[dy, dx] = tot - row[dy] - col[dx] + cor.get((dy, dx), 0.0)
+    return out
+
+
+def conv_wgrad_folded(a, dz, s, t):
+    """== conv_wgrad(s * a + t, dz, 3)[0] from `a`: dW[dy,dx,ci,co] = s[ci] * dW_a[dy,dx,ci,co] + t[ci] * Sdz[dy,dx,co]"""
+    dw_a, _ = conv_wgrad(a, dz, 3)
+    return dw_a * s[None, None, :, None] + t[None, None, :, None] * border_sums(dz)[:, :, None, :]

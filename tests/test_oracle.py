@@ -226,3 +226,29 @@ def test_estimate_radius_is_96_for_this_topology():
     p = O.init_params(1, 2, seed=3, base=8, dtype=torch.float64)
     r, g = O.estimate_radius(p, 1, seed=0)
     assert r == 96 and g.shape == (192, 192)
+
+
+def test_batchnorm_fold_identities():
+    """The algebra the next round's folded-BatchNorm kernels rely on: convolving the pre-BN activation with
+    channel-scaled weights plus a 9-case border bias equals convolving the BatchNorm output, and the weight gradient follows
+    from the gradient on `a` plus a border-sum correction -- exactly, in fp64, including 2-pixel images and negative scales."""
+    from oracle import unet_numpy as ON
+    rng = np.random.default_rng(0)
+    for (N, H, W, Ci, Co) in [(2, 7, 9, 5, 4), (1, 2, 2, 3, 2), (3, 2, 6, 4, 3), (1, 16, 3, 2, 5)]:
+        a = np.maximum(rng.normal(0.3, 1.0, size=(N, H, W, Ci)), 0)
+        w = rng.normal(size=(3, 3, Ci, Co))
+        b = rng.normal(size=Co)
+        s = rng.normal(size=Ci)                      # gamma * rstd: either sign
+        t = rng.normal(size=Ci)                      # beta - mean * s
+        y = a * s + t
+        ref = ON.conv_fwd(y, w, b)
+        got = ON.conv_fwd_folded(a, w, b, s, t)
+        assert np.abs(got - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+        dz = rng.normal(size=(N, H, W, Co))
+        dw_ref, _ = ON.conv_wgrad(y, dz, 3)
+        dw = ON.conv_wgrad_folded(a, dz, s, t)
+        assert np.abs(dw - dw_ref).max() < 1e-11 * max(1.0, np.abs(dw_ref).max())
+    # the interior bias is the plain bias plus the full tap sum; a corner drops 5 of the 9 taps
+    Tt = rng.normal(size=(3, 3, 2))
+    bias = ON.border_case_bias(Tt, np.zeros(2))
+    assert np.allclose(bias[1, 1], Tt.sum((0, 1))) and np.allclose(bias[0, 0], Tt[1:, 1:].sum((0, 1))) and np.allclose(bias[2, 1], Tt[:2].sum((0, 1)))
