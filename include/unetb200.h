@@ -202,6 +202,25 @@ int ub_aug_blur_axis(const float* src, float* dst, const double* weights, const 
                      cudaStream_t stream);
 int ub_aug_chanmix(float* x, const double* mix, int N, int C, long long plane, cudaStream_t stream);
 
+/* ---- BatchNorm folded into the consumer convolution (training forward; NOT YET ENABLED in the step: compiled, parity cases written,
+ * first GPU run pending) ------------------------------------------------------------------------------------------------------
+ * The producer's BatchNorm (UNet/model.py:36) is y = s a + t per channel; the consumer conv reads the pre-BatchNorm activation a
+ * with W' = W s[ci] and a bias that depends on the pixel's border case, so y is never written.
+ * ub_fold_conv3_weights: w fp32 [Cout][9][C0+C1] -> w_out bf16 (same layout) scaled per input channel; a source with mean == NULL
+ *   is taken as already normalised (s = 1, t = 0); bias9 = float[9][Cout] (case = row case * 3 + column case; 0 first, 1 interior,
+ *   2 last); scale_out / shift_out = float[C0+C1] (s, t) for ub_wgrad_fold_fix.
+ * ub_conv3x3_fwd_cases: ub_conv3x3_fwd with that bias table (H, W >= 2).
+ * ub_border_sums: sdz = float[9][C], sum of dz over the output pixels whose tap neighbour is inside the image; total = float[C]
+ *   sum of dz over all pixels (the bias gradient); scratch = 8 * C floats.
+ * ub_wgrad_fold_fix: dw [Cout][9][Cin] (weight gradient computed with x = a) <- scale[ci] * dw + shift[ci] * sdz[tap][co]. */
+int ub_fold_conv3_weights(const float* w, int Cout, int C0, const float* mean0, const float* rstd0, const float* gamma0, const float* beta0,
+                          int C1, const float* mean1, const float* rstd1, const float* gamma1, const float* beta1, const float* bias,
+                          void* w_out, float* bias9, float* scale_out, float* shift_out, cudaStream_t stream);
+int ub_conv3x3_fwd_cases(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias9, void* out, float* stats, int N,
+                         int H, int W, int Cout, int relu, cudaStream_t stream);
+int ub_border_sums(const void* dz, const float* total, float* sdz, float* scratch, int N, int H, int W, int C, int dtype, cudaStream_t stream);
+int ub_wgrad_fold_fix(float* dw, const float* scale, const float* shift, const float* sdz, int Cout, int Cin, cudaStream_t stream);
+
 /* ---- fp32 check mode (CUDA cores, fp32 storage) ----------------------------------------------------------------- */
 int ub_check_conv3x3(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias, float* out0, int Co0,
                      float* out1, int Co1, int N, int H, int W, int relu, cudaStream_t stream);

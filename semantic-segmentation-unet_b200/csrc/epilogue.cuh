@@ -33,22 +33,26 @@ struct EpiParams {
 };
 
 // RED: 0 = off, 1 = one `a`-tile buffer (fetched at the start of its part), 2 = two buffers (fetched one part ahead)
-template <int BLOCK_N, int OUT_BUFS, int RED = 0>
+// CASEB: the bias is a [9][ncols] table indexed by the pixel's border case (3 row cases x 3 column cases) -- the forward
+// convolution of a BatchNorm-FOLDED input (`ub_conv3x3_fwd_cases`): 'same' padding is applied after BatchNorm, so the folded
+// shift contributes only through the taps that lie inside the image (oracle/unet_numpy.py border_case_bias)
+template <int BLOCK_N, int OUT_BUFS, int RED = 0, int CASEB = 0>
 struct EpiSmem {
   static constexpr int OUT_BYTES = (BLOCK_N / 64) * EPI_OUT_BLK;
   static constexpr int OFF_STAT = 0;                                  // float[row groups <= 8][2][BLOCK_N]: aliases staging buffer 0,
                                                                       // only touched in finish() after every TMA store has drained
   static constexpr int OFF_ABUF = OUT_BUFS * OUT_BYTES;               // RED: the `a` tile, same swizzled layout as the staging tile
-  static constexpr int OFF_VEC = OFF_ABUF + RED * OUT_BYTES;          // bias, scale, shift: float[3][BLOCK_N]
-  static constexpr int OFF_ABAR = OFF_VEC + 3 * BLOCK_N * 4;          // RED: mbarrier of the `a` tile load
+  static constexpr int OFF_VEC = OFF_ABUF + RED * OUT_BYTES;          // scale, shift, bias: float[2 + NBIAS][BLOCK_N]
+  static constexpr int NBIAS = CASEB ? 9 : 1;
+  static constexpr int OFF_ABAR = OFF_VEC + (2 + NBIAS) * BLOCK_N * 4;   // RED: mbarrier of the `a` tile load
   static constexpr int TOTAL = OFF_ABAR + 16;
   static_assert(8 * 2 * BLOCK_N * 4 <= OUT_BYTES, "statistics scratch must fit the staging buffer");
 };
 
 // TILE_W_: pixels per tile row (tile row r of accumulator row m: m / TILE_W_, column m % TILE_W_)
-template <int BLOCK_N, int OUT_BUFS, int TILE_W_, int RED = 0>
+template <int BLOCK_N, int OUT_BUFS, int TILE_W_, int RED = 0, int CASEB = 0>
 struct Epilogue {
-  using S = EpiSmem<BLOCK_N, OUT_BUFS, RED>;
+  using S = EpiSmem<BLOCK_N, OUT_BUFS, RED, CASEB>;
   static constexpr int COLS_PER_THREAD = BLOCK_N / 2;          // this warp's half of the columns
   static constexpr int NCHUNK = COLS_PER_THREAD / 32;
   static constexpr int PAIRS = BLOCK_N / 2;                    // column pairs
@@ -85,6 +89,7 @@ struct Epilogue {
   }
 
   __device__ __forceinline__ float* vec() const { return reinterpret_cast<float*>(base + S::OFF_VEC); }
+  static __device__ __forceinline__ int bias_off(int k) { return k ? (2 + k) * BLOCK_N : 0; }
 
   // column-dependent vectors of this CTA's n_tile (call once, or when n_tile changes); ends with a barrier
   __device__ __forceinline__ void load_vectors(int n_tile) {
@@ -94,6 +99,10 @@ struct Epilogue {
       v[c] = ep.bias ? ep.bias[col] : 0.f;
       v[BLOCK_N + c] = post ? ep.post_scale[col] : 1.f;
       v[2 * BLOCK_N + c] = post ? ep.post_shift[col] : 0.f;
+      if (CASEB) {          // ep.bias = [9][ncols]: case 0 sits in the plain bias slot, cases 1..8 behind scale / shift
+#pragma unroll
+        for (int k = 1; k < 9; ++k) v[bias_off(k) + c] = ep.bias[(size_t)k * ep.ncols + col];
+      }
     }
     if (RED) {
       red_nt = n_tile;
@@ -164,6 +173,13 @@ struct Epilogue {
     if (first) mbar_wait(&tfull[as], aphase);
     tc_fence_after();
     const float* v = vec();
+    const float* vb = v;
+    if (CASEB) {
+      // border case of this thread's pixel: row case * 3 + column case, 0 = first, 1 = interior, 2 = last (H, W >= 2)
+      const int hh = h0 + row / TILE_W_, ww = w0 + row % TILE_W_;
+      const int rc = hh <= 0 ? 0 : (hh >= ep.H - 1 ? 2 : 1), cc = ww <= 0 ? 0 : (ww >= ep.W - 1 ? 2 : 1);
+      vb = v + bias_off(rc * 3 + cc);
+    }
     const uint32_t row_smem = smem_u32(out_stage) + row * 128;
     const int rsw = row & 7;
 #pragma unroll
@@ -175,7 +191,7 @@ struct Epilogue {
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(r[j]) + v[chunk * 32 + j];
+        const float x = __uint_as_float(r[j]) + vb[chunk * 32 + j];
         f[j] = ep.relu ? fmaxf(x, 0.f) : x;
       }
       if (post) {

@@ -1,0 +1,182 @@
+// BatchNorm folded into the CONSUMER convolution (training forward), DESIGN.md "the plan for it":
+//   y = s * a + t per input channel (s = gamma * rstd, t = beta - mean * s of the PRODUCER's BatchNorm, UNet/model.py:36),
+//   conv(y) = conv_{W * s}(a) + sum over the taps that fall inside the image of (W . t)      ('same' padding pads y, not a)
+// so the consumer reads the pre-BatchNorm activation `a` and the y tensor is never written.  Small helper kernels:
+//   ub_fold_conv3_weights  W' = bf16(W * s[ci]), the 9-case border bias table, and s / t for the backward fix-up
+//   ub_border_sums         Sdz[tap][co] = sum of dz over the pixels whose tap neighbour is inside the image
+//   ub_wgrad_fold_fix      dW = s[ci] * dW_a + t[ci] * Sdz[tap][co]      (dW_a = weight gradient computed on `a`)
+// The algebra is proven in fp64 in oracle/unet_numpy.py (fold_weights, border_case_bias, border_sums, conv_wgrad_folded).
+// STATUS: compiled and covered by parity cases (tests/kernel_cases.py PENDING_CASES) but not yet run on a B200 and not wired
+// into the training step (UNet.fold_bn stays False) -- the GPU budget of the round ended first.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ void channel_affine(int ci, int C0, const float* mean0, const float* rstd0, const float* gamma0, const float* beta0,
+                                               const float* mean1, const float* rstd1, const float* gamma1, const float* beta1, float& s,
+                                               float& t) {
+  const bool first = ci < C0;
+  const float* mean = first ? mean0 : mean1;
+  if (!mean) {          // this source is a real (already normalised) tensor: identity
+    s = 1.f;
+    t = 0.f;
+    return;
+  }
+  const int c = first ? ci : ci - C0;
+  s = (first ? gamma0 : gamma1)[c] * (first ? rstd0 : rstd1)[c];
+  t = (first ? beta0 : beta1)[c] - mean[c] * s;
+}
+
+// one block per output channel: w [Cout][9][Cin] fp32 -> w_out bf16, Tt[tap] = sum_ci w * t (fp64), bias9[case][co]
+__global__ void __launch_bounds__(TPB) fold_conv3_kernel(const float* __restrict__ w, int Cout, int C0, const float* mean0, const float* rstd0,
+                                                         const float* gamma0, const float* beta0, int C1, const float* mean1,
+                                                         const float* rstd1, const float* gamma1, const float* beta1,
+                                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ w_out,
+                                                         float* __restrict__ bias9, float* __restrict__ scale_out,
+                                                         float* __restrict__ shift_out) {
+  const int co = blockIdx.x;
+  const int Cin = C0 + C1;
+  double tt[9] = {};
+  for (int ci = threadIdx.x; ci < Cin; ci += TPB) {
+    float s, t;
+    channel_affine(ci, C0, mean0, rstd0, gamma0, beta0, mean1, rstd1, gamma1, beta1, s, t);
+    if (co == 0) {
+      scale_out[ci] = s;
+      shift_out[ci] = t;
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const size_t i = ((size_t)co * 9 + tap) * Cin + ci;
+      const float wv = w[i];
+      w_out[i] = __float2bfloat16(wv * s);
+      tt[tap] += (double)wv * (double)t;
+    }
+  }
+  __shared__ double sh[9][TPB / 32];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    double v = tt[tap];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[tap][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    // border case k = row case * 3 + column case: 0 = first row / column (tap offset -1 is outside), 1 = interior, 2 = last
+    const int rc = threadIdx.x / 3, cc = threadIdx.x % 3;
+    double acc = bias ? (double)bias[co] : 0.0;
+    for (int dy = 0; dy < 3; ++dy) {
+      if ((rc == 0 && dy == 0) || (rc == 2 && dy == 2)) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        if ((cc == 0 && dx == 0) || (cc == 2 && dx == 2)) continue;
+        double tsum = 0.0;
+        for (int wv = 0; wv < TPB / 32; ++wv) tsum += sh[dy * 3 + dx][wv];
+        acc += tsum;
+      }
+    }
+    bias9[(size_t)threadIdx.x * Cout + co] = (float)acc;
+  }
+}
+
+// raw[s][c]: s = 0 top row, 1 bottom row, 2 left column, 3 right column, 4..7 corners (tl, tr, bl, br); NHWC dz
+template <typename T>
+__global__ void __launch_bounds__(TPB) border_strips_kernel(const T* __restrict__ dz, float* __restrict__ raw, int N, int H, int W, int C) {
+  const int s = blockIdx.y;
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int g = threadIdx.x >> 6;          // 4 pixel lanes
+  const long long count = s < 2 ? (long long)N * W : (s < 4 ? (long long)N * H : N);
+  double acc = 0.0;
+  if (c < C) {
+    for (long long p = g; p < count; p += 4) {
+      int n, h, w;
+      if (s < 2) {
+        n = (int)(p / W);
+        w = (int)(p % W);
+        h = s == 0 ? 0 : H - 1;
+      } else if (s < 4) {
+        n = (int)(p / H);
+        h = (int)(p % H);
+        w = s == 2 ? 0 : W - 1;
+      } else {
+        n = (int)p;
+        h = (s == 4 || s == 5) ? 0 : H - 1;
+        w = (s == 4 || s == 6) ? 0 : W - 1;
+      }
+      acc += (double)(float)dz[(((long long)n * H + h) * W + w) * C + c];
+    }
+  }
+  __shared__ double sh[4][64];
+  sh[g][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (g == 0 && c < C) raw[(size_t)s * C + c] = (float)(sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+}
+
+// sdz[tap][c] = total - (row strip excluded by the tap) - (column strip excluded by the tap) + (their common corner)
+__global__ void border_finish_kernel(const float* __restrict__ raw, const float* __restrict__ total, float* __restrict__ sdz, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float tot = total[c];
+  for (int dy = 0; dy < 3; ++dy)
+    for (int dx = 0; dx < 3; ++dx) {
+      float v = tot;
+      if (dy == 0) v -= raw[0 * C + c];
+      if (dy == 2) v -= raw[1 * C + c];
+      if (dx == 0) v -= raw[2 * C + c];
+      if (dx == 2) v -= raw[3 * C + c];
+      if (dy != 1 && dx != 1) v += raw[(4 + (dy == 2 ? 2 : 0) + (dx == 2 ? 1 : 0)) * C + c];
+      sdz[(size_t)(dy * 3 + dx) * C + c] = v;
+    }
+}
+
+__global__ void __launch_bounds__(TPB) wgrad_fold_fix_kernel(float* __restrict__ dw, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, const float* __restrict__ sdz, int Cout, int Cin) {
+  const long long n = (long long)Cout * 9 * Cin;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n; i += (long long)gridDim.x * TPB) {
+    const int ci = (int)(i % Cin);
+    const long long r = i / Cin;
+    const int tap = (int)(r % 9), co = (int)(r / 9);
+    dw[i] = fmaf(scale[ci], dw[i], shift[ci] * sdz[(size_t)tap * Cout + co]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ub_fold_conv3_weights(const float* w, int Cout, int C0, const float* mean0, const float* rstd0, const float* gamma0, const float* beta0,
+                          int C1, const float* mean1, const float* rstd1, const float* gamma1, const float* beta1, const float* bias,
+                          void* w_out, float* bias9, float* scale_out, float* shift_out, cudaStream_t stream) {
+  UB_CHECK_ARG(w && w_out && bias9 && scale_out && shift_out && Cout > 0 && C0 > 0 && C1 >= 0, "fold_conv3_weights: bad args");
+  UB_CHECK_ARG(!mean0 || (rstd0 && gamma0 && beta0), "fold_conv3_weights: source 0 needs mean, rstd, gamma and beta");
+  UB_CHECK_ARG(!mean1 || (rstd1 && gamma1 && beta1 && C1 > 0), "fold_conv3_weights: source 1 needs mean, rstd, gamma and beta");
+  fold_conv3_kernel<<<Cout, TPB, 0, stream>>>(w, Cout, C0, mean0, rstd0, gamma0, beta0, C1, mean1, rstd1, gamma1, beta1, bias,
+                                             (__nv_bfloat16*)w_out, bias9, scale_out, shift_out);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_border_sums(const void* dz, const float* total, float* sdz, float* scratch, int N, int H, int W, int C, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(dz && total && sdz && scratch && N > 0 && H >= 2 && W >= 2 && C > 0, "border_sums: bad args (H, W >= 2; scratch = 8 * C floats)");
+  const dim3 grid((C + 63) / 64, 8);
+  if (dtype == UB_BF16) border_strips_kernel<__nv_bfloat16><<<grid, TPB, 0, stream>>>((const __nv_bfloat16*)dz, scratch, N, H, W, C);
+  else if (dtype == UB_F32) border_strips_kernel<float><<<grid, TPB, 0, stream>>>((const float*)dz, scratch, N, H, W, C);
+  else UB_CHECK_ARG(false, "border_sums: bad dtype %d", dtype);
+  UB_LAUNCH_CHECK();
+  border_finish_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, total, sdz, C);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_wgrad_fold_fix(float* dw, const float* scale, const float* shift, const float* sdz, int Cout, int Cin, cudaStream_t stream) {
+  UB_CHECK_ARG(dw && scale && shift && sdz && Cout > 0 && Cin > 0, "wgrad_fold_fix: bad args");
+  const long long n = (long long)Cout * 9 * Cin;
+  long long blocks = (n + TPB - 1) / TPB;
+  if (blocks > (long long)ub_num_sms() * 16) blocks = (long long)ub_num_sms() * 16;
+  wgrad_fold_fix_kernel<<<(int)blocks, TPB, 0, stream>>>(dw, scale, shift, sdz, Cout, Cin);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+}  // extern "C"

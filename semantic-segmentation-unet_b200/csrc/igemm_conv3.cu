@@ -57,9 +57,9 @@ struct Conv3Params {
   const void* w_base;        // host-side only: weight matrix [ncols][9 * Cin] for the tensor map
 };
 
-template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED, int CASEB = 0>
 struct C3Smem {
-  using E = EpiSmem<BLOCK_N, OUT_BUFS, RED>;
+  using E = EpiSmem<BLOCK_N, OUT_BUFS, RED, CASEB>;
   using P = Patch<MT>;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int OFF_B = A_STAGES * P::STRIDE;
@@ -73,9 +73,9 @@ struct C3Smem {
   static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
 };
 
-template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED, int CASEB = 0>
 __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid_constant__ Conv3Params p) {
-  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED>;
+  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED, CASEB>;
   using PT = Patch<MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
     __syncwarp();
   } else {
     // ================= epilogue (8 warps, epilogue.cuh) =================
-    Epilogue<BLOCK_N, OUT_BUFS, TW, RED> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    Epilogue<BLOCK_N, OUT_BUFS, TW, RED, CASEB> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
     epi.red_map = &p.red_map;
     epi.load_vectors(n_tile);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -254,12 +254,12 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
   }
 }
 
-template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED = 0>
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED = 0, int CASEB = 0>
 int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream) {
-  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED>;
+  using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED, CASEB>;
   using PT = Patch<MT>;
   static_assert(L::TOTAL <= 232448, "smem budget");
-  auto kern = conv3_kernel<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED>;
+  auto kern = conv3_kernel<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED, CASEB>;
   static bool attr_done = false;
   if (!attr_done) {
     UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -291,12 +291,17 @@ int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_
   return UB_OK;
 }
 
-int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream) {
+int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream, bool bias_cases = false) {
   p.cblk_total = 0;
   for (int i = 0; i < p.nsrc; ++i) p.cblk_total += p.cblk[i];
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
+  if (bias_cases) {            // forward of a BatchNorm-folded input: 9-case border bias (H, W >= 2 checked by the caller)
+    if (p.ncols % 128 == 0) return launch_c3<128, 2, 2, 4, 2, 0, 1>(p, a_base, a_ch, n_img, stream);
+    if (p.cblk_total == 1) return launch_c3<64, 2, 2, 9, 2, 0, 1>(p, a_base, a_ch, n_img, stream);
+    return launch_c3<64, 1, 2, 18, 2, 0, 1>(p, a_base, a_ch, n_img, stream);
+  }
   static int v1 = -1;
   if (v1 < 0) {
     const char* e = getenv("UB_CONV3_V1");       // A/B switch for tools/bench_layers.py: the round-1 128-pixel tiles
@@ -342,7 +347,8 @@ int out_map(CUtensorMap* m, const void* base, int C, int W, int H, int N) {
 
 // Called by the extern "C" entry points in igemm_fwd.cu.
 int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* post_scale,
-                      const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream) {
+                      const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream,
+                      int bias_cases) {
   Conv3Params p;
   memset(&p, 0, sizeof(p));
   int rc;
@@ -362,7 +368,8 @@ int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void
   p.ep.relu = relu;
   p.ep.stats = stats;
   p.ncols = Cout;
-  return launch(p, a_base, a_ch, N, stream);
+  if (bias_cases) UB_CHECK_SHAPE(H >= 2 && W >= 2, "conv3 with a border-case bias needs H, W >= 2 (got %d x %d)", H, W);
+  return launch(p, a_base, a_ch, N, stream, bias_cases != 0);
 }
 
 int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,

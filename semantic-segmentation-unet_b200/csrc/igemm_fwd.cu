@@ -251,7 +251,8 @@ int strided_map(CUtensorMap* m, const void* base, int C, int w, int h, int N, in
 
 // halo-patch kernels (igemm_conv3.cu)
 int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* post_scale,
-                      const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream);
+                      const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream,
+                      int bias_cases = 0);
 int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
                         const void* red_a, const float* red_mean, const float* red_rstd, float* red_partial, cudaStream_t stream);
 static bool legacy_conv3() {
@@ -297,6 +298,18 @@ int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w
   p.ep.stats = stats;
   p.ncols = Cout;
   return launch(p, N, stream);
+}
+
+// Forward of a convolution whose INPUT is the pre-BatchNorm activation of its producer(s) (BatchNorm folded into the weights,
+// ub_fold_conv3_weights): bias9 = [9][Cout], one bias vector per border case (row case * 3 + column case; 0 = first row /
+// column, 1 = interior, 2 = last) because 'same' padding is applied AFTER BatchNorm (UNet/model.py:30-36).  H, W >= 2.
+int ub_conv3x3_fwd_cases(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias9, void* out, float* stats, int N,
+                         int H, int W, int Cout, int relu, cudaStream_t stream) {
+  UB_CHECK_ARG(x0 && w && out && bias9, "conv3x3_fwd_cases: null pointer");
+  UB_CHECK_SHAPE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0 && Cout % 64 == 0 && (C1 == 0 || x1),
+                 "conv3x3_fwd_cases: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  UB_CHECK_SHAPE(N > 0 && H >= 2 && W >= 2, "conv3x3_fwd_cases: bad N/H/W");
+  return ub_conv3_halo_fwd(x0, C0, x1, C1, w, bias9, nullptr, nullptr, out, stats, N, H, W, Cout, relu, stream, 1);
 }
 
 // Inference form: y = relu(conv + b) * scale + shift with the BatchNorm moving statistics folded into scale/shift

@@ -33,7 +33,7 @@ def _pad8(n):
 
 class _Layer:
     __slots__ = ("name", "kind", "cin", "cout", "level", "ksize", "off_w", "off_b", "off_beta", "off_gamma", "n_w",
-                 "off_stat", "seg_begin", "seg_end", "c0", "c1")
+                 "off_stat", "seg_begin", "seg_end", "c0", "c1", "fold")
 
 
 class UNet:
@@ -79,6 +79,10 @@ class UNet:
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
         self.fuse_bn_reduce_ew = os.environ.get("UB_FUSE_EW", "0") == "1"   # ... and in the pool-backward / head-backward passes
+        # bf16 training forward with the producers' BatchNorm folded into the consumer convolutions (_forward_train_folded).
+        # Written at the end of round 1: kernels compiled and parity cases in tests/kernel_cases.py PENDING_CASES, not yet run on a
+        # B200 -- stays off until they have been.
+        self.fold_bn = os.environ.get("UB_FOLD_BN", "0") == "1"
         self._build_layout()
         self.class_weights = None
         if class_weights is not None:
@@ -149,6 +153,7 @@ class UNet:
             L.ksize = {"first": 9, "conv": 9, "deconv": 4, "head": 1}[kind]
             L.n_w = cout * L.ksize * cin
             L.c0 = L.c1 = 0
+            L.fold = None
             self.layers[name] = L
         off = 0
         soff = 0
@@ -508,6 +513,10 @@ class UNet:
             self._inference_stale = False
         if not training and self.precision == "bf16":
             return self._forward_folded(x, N, H, W)
+        if training and self.fold_bn and self.precision == "bf16":
+            return self._forward_train_folded(x, N, H, W, drop_masks or {})
+        for L in self.layers.values():
+            L.fold = None
         Ls = self.layers
         dm = drop_masks or {}
         # ---- encoder
@@ -559,6 +568,68 @@ class UNet:
             cur = self._bn_apply(La, N, h, w, training)
             self._conv_fwd(Lb, cur, Lb.cin, None, 0, N, h, w, training)
             cur = self._bn_apply(Lb, N, h, w, training)
+        return cur
+
+    def _conv_fwd_fold(self, L, x0, c0, p0, x1, c1, p1, N, h, w):
+        """conv3x3 whose sources are pre-BatchNorm activations: p0 / p1 = the producer layer whose BatchNorm (batch statistics of
+        this step) is folded into this layer's weights, or None for a source that is already normalised"""
+        self._cur = L.name
+        a = self._b("a:" + L.name)
+        L.c0, L.c1, L.fold = c0, c1, (p0, p1)
+        wf = self._ensure("wfold:" + L.name, L.n_w, torch.bfloat16)
+        b9 = self._ensure("bias9:" + L.name, 9 * L.cout, torch.float32)
+        sc = self._ensure("fold_s:" + L.name, L.cin, torch.float32)
+        sh = self._ensure("fold_t:" + L.name, L.cin, torch.float32)
+
+        def vecs(p):
+            if p is None:
+                return None, None, None, None
+            mean, rstd = self._bn_vectors(p, True)
+            gamma, beta = self._affine(p)
+            return mean, rstd, gamma, beta
+
+        self._call("ub_fold_conv3_weights", self._w(L), L.cout, c0, *vecs(p0), c1, *vecs(p1), self.P[L.off_b:L.off_b + L.cout], wf, b9, sc, sh)
+        self._call("ub_conv3x3_fwd_cases", x0, c0, x1, c1, wf, b9, a, self.partial, N, h, w, L.cout, 1)
+        self._finalize(L, L.cout, 1, N * h * w)
+        return a
+
+    def _forward_train_folded(self, x, N, H, W, dm):
+        """Training forward (bf16) in which a layer's BatchNorm output is not written when all of its consumers are 3x3
+        convolutions: those read the pre-BatchNorm activation with folded weights and a 9-case border bias (csrc/fold.cu).
+        Folded producers: enc<l>a, bota, dec<l>a, up<l>.  Kept: layers followed by max-pool (the pool needs y), by dropout, by a
+        transposed convolution or by the head."""
+        Ls = self.layers
+        for L in Ls.values():
+            L.fold = None
+        L = Ls["enc1a"]
+        self._cur = "enc1a"
+        self._call("ub_conv_first_fwd", x, self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], self._b("a:enc1a"),
+                   self.partial, N, H, W, self.number_channels, self.act_code)
+        self._finalize(L, L.cout, 1, N * H * W)
+        for lvl in (1, 2, 3, 4):
+            h, w = self._dims(H, W, lvl)
+            La, Lb = Ls[f"enc{lvl}a"], Ls[f"enc{lvl}b"]
+            if lvl > 1:
+                self._conv_fwd(La, self._b(f"pool{lvl - 1}"), La.cin, None, 0, N, h, w, True)
+            self._conv_fwd_fold(Lb, self._b("a:" + La.name), Lb.cin, La, None, 0, None, N, h, w)
+            self._bn_apply(Lb, N, h, w, True, drop=dm.get("drop4") if lvl == 4 else None, pool_lvl=lvl)
+        h, w = self._dims(H, W, 5)
+        La, Lb = Ls["bota"], Ls["botb"]
+        self._conv_fwd(La, self._b("pool4"), La.cin, None, 0, N, h, w, True)
+        self._conv_fwd_fold(Lb, self._b("a:bota"), Lb.cin, La, None, 0, None, N, h, w)
+        cur = self._bn_apply(Lb, N, h, w, True, drop=dm.get("dropb"))
+        for lvl in (4, 3, 2, 1):
+            hi, wi = self._dims(H, W, lvl + 1)
+            h, w = self._dims(H, W, lvl)
+            Lu, La, Lb = Ls[f"up{lvl}"], Ls[f"dec{lvl}a"], Ls[f"dec{lvl}b"]
+            self._cur = Lu.name
+            self._call("ub_deconv2x2_fwd", cur, Lu.cin, self._wptr(Lu), self.P[Lu.off_b:Lu.off_b + Lu.cout], self._b("a:" + Lu.name), self.partial,
+                       N, hi, wi, Lu.cout)
+            self._finalize(Lu, 4 * Lu.cout, 4, N * h * w)
+            # concat [skip, up] (model.py:117): the skip is a real y tensor, the up-convolution's BatchNorm is folded
+            self._conv_fwd_fold(La, self._b(f"y:enc{lvl}b"), Lu.cout, None, self._b("a:" + Lu.name), Lu.cout, Lu, N, h, w)
+            self._conv_fwd_fold(Lb, self._b("a:" + La.name), Lb.cin, La, None, 0, None, N, h, w)
+            cur = self._bn_apply(Lb, N, h, w, True)
         return cur
 
     def _forward_folded(self, x, N, H, W):
@@ -670,10 +741,24 @@ class UNet:
         dz = self._bn_bwd(L, N, h, w, 1)
         dw = self.G[L.off_w:L.off_w + L.n_w]
         c0, c1 = L.c0, L.c1
+        if L.fold is not None:          # this layer's forward read pre-BatchNorm activations: so does its weight gradient
+            p0, p1 = L.fold
+            x0 = self._b("a:" + p0.name) if p0 is not None else x0
+            x1 = self._b("a:" + p1.name) if p1 is not None else x1
+
+        def wgrad():
+            self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
+            if L.fold is not None:
+                # dW = s[ci] * dW_a + t[ci] * (sum of dz over the pixels whose tap neighbour is inside); the total is the bias gradient
+                sdz = self._ensure("fold_sdz", 9 * 2048, torch.float32)
+                scr = self._ensure("fold_scr", 8 * 2048, torch.float32)
+                self._call("ub_border_sums", dz, self.G[L.off_b:L.off_b + L.cout], sdz, scr, N, h, w, L.cout, self.act_code)
+                self._call("ub_wgrad_fold_fix", dw, self._b("fold_s:" + L.name), self._b("fold_t:" + L.name), sdz, L.cout, L.cin)
+
         if self.precision == "bf16":
             ws = self._b("wgrad_ws")
             if not self.overlap_wgrad:
-                self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
+                wgrad()
             # worth it only where the K loop is long enough to hide the longer epilogue (measured: 64-output-channel layers,
             # whose dgrad has a single 64-channel K block, lose more in the dgrad than the separate reduction pass costs)
             if dx0 is not None and red is not None and self.fuse_bn_reduce and L.cout >= 128:
@@ -685,7 +770,7 @@ class UNet:
                 self._call("ub_conv3x3_dgrad", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w)
             if self.overlap_wgrad:
                 with torch.cuda.stream(self._fork_side()):
-                    self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
+                    wgrad()
         else:
             self._call("ub_check_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, N, h, w)
             if dx0 is not None:

@@ -16,6 +16,7 @@ def all_cases():
     import kernel_cases as K
     d = dict(K.CASES)
     d.update(G.CASES)
+    d.update(K.PENDING_CASES)          # written but not yet run on a B200: only selected by `--pending` or by name
     return d
 
 
@@ -32,6 +33,11 @@ if __name__ == "__main__":
         sys.exit(0)
     pat = sys.argv[1] if len(sys.argv) > 1 else ""
     cases = all_cases()
+    import kernel_cases as K
+    if pat == "--pending":
+        pat = ",".join(K.PENDING_CASES)
+    elif not pat:
+        cases = {k: v for k, v in cases.items() if k not in K.PENDING_CASES}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     report = {}
     for name in cases:

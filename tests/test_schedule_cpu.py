@@ -1,0 +1,118 @@
+"""Dry run of the training / test / inference launch schedules on the CPU: every `UNet._call` is intercepted, checked against
+the C ABI declared in include/unetb200.h (entry point exists, argument count, pointer vs scalar kinds) and recorded -- no
+kernel runs.  It guards the host-side wiring (a renamed entry point, a missing argument, a tensor passed where an int is
+expected) for the default schedule and for the optional ones (side-stream weight gradients, fused reductions, BatchNorm fold)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import unetb200._C as C
+from unetb200 import model as M
+
+
+class DryUNet(M.UNet):
+    def __init__(self, *a, **kw):
+        self.calls = []
+        real = torch.cuda.is_available
+        torch.cuda.is_available = lambda: True
+        try:
+            super().__init__(*a, device="cpu", **kw)
+        finally:
+            torch.cuda.is_available = real
+        self.use_graph = False
+
+    def _stream(self):
+        return 0
+
+    def _fork_side(self):
+        return None                      # torch.cuda.stream(None) is a no-op context
+
+    def _join_side(self):
+        pass
+
+    def _call(self, name, *args):
+        assert name in C.DECLS, f"{name} is not declared in include/unetb200.h"
+        params = C.DECLS[name][1]
+        assert len(args) + 1 == len(params), f"{name}: {len(args)} arguments + stream, the header declares {len(params)}"
+        for a, (ctype, pname) in zip(args, params):
+            if ctype is ctypes.c_void_p:
+                assert a is None or isinstance(a, int) or hasattr(a, "data_ptr"), f"{name}({pname}): pointer argument got {type(a).__name__}"
+            elif ctype in (ctypes.c_float, ctypes.c_double):
+                assert isinstance(a, (int, float)) and not isinstance(a, bool), f"{name}({pname}): float argument got {type(a).__name__}"
+            else:
+                assert isinstance(a, (int, np.integer)) and not isinstance(a, bool), f"{name}({pname}): integer argument got {type(a).__name__}"
+        assert params[-1][0] is ctypes.c_void_p
+        self.launches += 1
+        self.calls.append((name, self._cur))
+        return 0
+
+
+def _step(m, N=1, C_=1, H=32, W=48, K=2):
+    x = torch.zeros((N, C_, H, W), dtype=torch.float32)
+    lab = torch.zeros((N, H, W), dtype=torch.uint8)
+    m.calls.clear()
+    m.train_step(x, lab)
+    return [n for n, _ in m.calls]
+
+
+def _count(names):
+    out = {}
+    for n in names:
+        out[n] = out.get(n, 0) + 1
+    return out
+
+
+@pytest.mark.parametrize("overlap", [False, True])
+def test_default_training_schedule(overlap):
+    m = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    m.overlap_wgrad = overlap
+    c = _count(_step(m))
+    assert c["ub_conv3x3_fwd"] == 17 and c["ub_conv_first_fwd"] == 1 and c["ub_deconv2x2_fwd"] == 4 and c["ub_head_fwd"] == 1
+    assert c["ub_conv3x3_wgrad"] == 17 and c["ub_deconv2x2_wgrad"] == 4 and c["ub_conv_first_wgrad"] == 1
+    assert c.get("ub_conv3x3_dgrad", 0) + c.get("ub_conv3x3_dgrad_bnred", 0) == 17 and c["ub_deconv2x2_dgrad"] == 4
+    assert c["ub_bn_apply"] + c["ub_bn_apply_pool"] == 22 and c["ub_bn_bwd_apply"] == 22 and c["ub_bn_finalize"] == 23
+    assert c["ub_adam"] == 1 and c["ub_transpose_pack_multi"] == 1 and c["ub_maxpool2x2_bwd_add"] == 4
+    assert "ub_fold_conv3_weights" not in c and "ub_maxpool2x2_bwd_add_bnred" not in c
+    # the fp32 check mode and the class-weighted 3-channel, 8-class configuration walk the same graph
+    for kw, shape in ((dict(precision="fp32"), (1, 1, 32, 32, 2)), (dict(precision="bf16", class_weights=[1.0] * 8), (1, 3, 32, 32, 8))):
+        mm = DryUNet(shape[4], 1, shape[1], seed=0, **kw)
+        mm.overlap_wgrad = overlap
+        assert len(_step(mm, *shape)) > 150
+
+
+def test_optional_schedules():
+    m = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    m.fuse_bn_reduce_ew = True
+    c = _count(_step(m))
+    assert c["ub_maxpool2x2_bwd_add_bnred"] == 4 and c["ub_head_bwd_apply_bnred"] == 1 and "ub_maxpool2x2_bwd_add" not in c
+    m = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    m.fold_bn = True
+    names = _step(m)
+    c = _count(names)
+    # 13 producers lose their BatchNorm-apply pass; their 13 consumers fold the weights, use the case bias and fix the weight gradient
+    assert c["ub_fold_conv3_weights"] == 13 and c["ub_conv3x3_fwd_cases"] == 13 and c["ub_conv3x3_fwd"] == 4
+    assert c["ub_bn_apply"] + c["ub_bn_apply_pool"] == 22 - 13
+    assert c["ub_border_sums"] == 13 and c["ub_wgrad_fold_fix"] == 13 and c["ub_conv3x3_wgrad"] == 17
+    folded = {l for n, l in m.calls if n == "ub_conv3x3_fwd_cases"}
+    assert folded == {"enc1b", "enc2b", "enc3b", "enc4b", "botb", "dec4a", "dec4b", "dec3a", "dec3b", "dec2a", "dec2b", "dec1a", "dec1b"}
+    # back to the default schedule on the same object
+    m.fold_bn = False
+    assert "ub_fold_conv3_weights" not in _count(_step(m)) and all(L.fold is None for L in m.layers.values())
+
+
+def test_test_step_and_inference_schedules():
+    m = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    x = torch.zeros((1, 1, 32, 32))
+    m.calls.clear()
+    m.test_step(x, torch.zeros((1, 32, 32), dtype=torch.uint8))
+    c = _count(n for n, _ in m.calls)
+    assert c["ub_conv3x3_fwd_affine"] == 17 and c["ub_maxpool2x2_fwd"] == 4 and "ub_bn_apply" not in c and c["ub_head_loss"] == 1
+    m.calls.clear()
+    m.forward_softmax(x)
+    assert _count(n for n, _ in m.calls)["ub_head_loss"] == 1
+    with pytest.raises(IOError):
+        m.forward_softmax(torch.zeros((1, 1, 24, 32)))              # not a multiple of 16 (UNet/inference.py:42)
+    with pytest.raises(IOError):
+        m.train_step(torch.zeros((1, 2, 32, 32)), torch.zeros((1, 32, 32), dtype=torch.uint8))      # wrong channel count
