@@ -112,7 +112,10 @@ def _q(t, storage, fwd=True, bwd=True):
     return t if storage is None else _StorageRound.apply(t, fwd, bwd)
 
 
-def _bn(x, name, params, training, new_stats, x_used=None):
+_FOLDED = {"enc1a", "enc2a", "enc3a", "enc4a", "bota", "dec1a", "dec2a", "dec3a", "dec4a", "up1", "up2", "up3", "up4"}
+
+
+def _bn(x, name, params, training, new_stats, x_used=None, scale_out=None):
     """BatchNormalization(axis=1), App. A.3: biased batch var to normalise, unbiased into the moving avg.
     x_used (bf16-storage emulation): the stored (rounded) activation that is normalised, while the statistics come
     from the unrounded accumulator values `x` -- the data flow of the CUDA path."""
@@ -131,14 +134,23 @@ def _bn(x, name, params, training, new_stats, x_used=None):
         mean = params[name + "/moving_mean"]
         var = params[name + "/moving_var"]
     xu = x if x_used is None else x_used
+    if scale_out is not None:                      # storage="bf16_fold": the consumer folds gamma * rstd into its weights
+        scale_out[name] = (torch.rsqrt(var + BN_EPS) * params[name + "/gamma"]).detach()
     return (xu - mean.view(1, -1, 1, 1)) * torch.rsqrt(var.view(1, -1, 1, 1) + BN_EPS) * g + b
 
 
-def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None, storage=None):
+def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None, storage=None, w_scale=None, scales=None):
+    """storage="bf16_fold" (the folded-BatchNorm forward prepared in csrc/fold.cu): a producer in _FOLDED does not store its
+    BatchNorm output (no rounding of y), and its consumer rounds the weights AFTER scaling them by gamma * rstd per input channel
+    (`w_scale`): conv(a, bf16(W s)) == conv(y, bf16(W s) / s) up to the shift term, which the CUDA path adds in fp32."""
     w = params[name + "/kernel"].permute(3, 2, 0, 1)          # HWIO -> OIHW  (App. A.1)
     k = w.shape[-1]
     tensor_core = storage is not None and k == 3 and w.shape[1] >= 64      # bf16 weight shadow; first layer/head stay fp32
-    if tensor_core:
+    if tensor_core and w_scale is not None:
+        sv = w_scale.view(1, -1, 1, 1)
+        sv = torch.where(sv == 0, torch.ones_like(sv), sv)
+        w = _q(w * sv, storage, True, False) / sv
+    elif tensor_core:
         w = _q(w, storage, True, False)
     z = F.conv2d(x, w, params[name + "/bias"], padding=k // 2)
     if relu_masks is not None and name in relu_masks:
@@ -153,6 +165,11 @@ def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None, sto
     head = (k == 1)
     if storage is None or head:                               # the head keeps fp32 activations on the CUDA path
         y = _bn(a, name, params, training, new_stats)
+    elif storage == "bf16_fold" and name in _FOLDED:          # y is never stored: only its gradient is (dgrad writes bf16)
+        if tensor_core:
+            y = _q(_bn(_q(a, storage), name, params, training, new_stats, scale_out=scales), storage, False, True)
+        else:
+            y = _q(_bn(a, name, params, training, new_stats, x_used=_q(a, storage), scale_out=scales), storage, False, True)
     elif tensor_core:                                         # tcgen05 epilogue: statistics of the STORED (rounded) activations
         y = _q(_bn(_q(a, storage), name, params, training, new_stats), storage)
     else:                                                     # first layer: statistics from the fp32 values, stored rounded
@@ -162,7 +179,7 @@ def _conv_block(x, name, params, training, new_stats, taps, relu_masks=None, sto
     return y
 
 
-def _deconv_block(x, name, params, training, new_stats, taps, storage=None):
+def _deconv_block(x, name, params, training, new_stats, taps, storage=None, scales=None):
     w = params[name + "/kernel"].permute(3, 2, 0, 1)          # [kh,kw,Cout,Cin] -> [Cin,Cout,kh,kw] (App. A.2)
     if storage is not None:
         w = _q(w, storage, True, False)
@@ -171,6 +188,8 @@ def _deconv_block(x, name, params, training, new_stats, taps, storage=None):
         taps[name + "/act"] = z
     if storage is None:
         y = _bn(z, name, params, training, new_stats)
+    elif storage == "bf16_fold":
+        y = _q(_bn(_q(z, storage), name, params, training, new_stats, scale_out=scales), storage, False, True)
     else:
         y = _q(_bn(_q(z, storage), name, params, training, new_stats), storage)
     if taps is not None:
@@ -210,28 +229,37 @@ def forward(params, x, training, dropout_masks=None, new_stats=None, taps=None, 
     pool_idx = pool_idx or {}
     st = storage
 
-    def cb(t, name):
-        return _conv_block(t, name, params, training, new_stats, taps, relu_masks, st)
+    scales = {} if st == "bf16_fold" else None
+
+    def cb(t, name, src=None):
+        """src (bf16_fold only): the producer(s) whose BatchNorm this conv folds -- a name, or (n_skip_channels, up name)"""
+        ws = None
+        if scales is not None and src is not None:
+            if isinstance(src, tuple):
+                ws = torch.cat([torch.ones(src[0], dtype=t.dtype), scales[src[1]]])
+            else:
+                ws = scales[src]
+        return _conv_block(t, name, params, training, new_stats, taps, relu_masks, st, ws, scales)
 
     def fan(t):      # a tensor with two consumers: each branch's gradient is stored (rounded) before the sum
         return _q(t, st, False, True)
 
-    c1 = cb(cb(x, "enc1a"), "enc1b")
+    c1 = cb(cb(x, "enc1a"), "enc1b", "enc1a")
     p1 = _pool(fan(c1), pool_idx.get("pool1"))
-    c2 = cb(cb(p1, "enc2a"), "enc2b")
+    c2 = cb(cb(p1, "enc2a"), "enc2b", "enc2a")
     p2 = _pool(fan(c2), pool_idx.get("pool2"))
-    c3 = cb(cb(p2, "enc3a"), "enc3b")
+    c3 = cb(cb(p2, "enc3a"), "enc3b", "enc3a")
     p3 = _pool(fan(c3), pool_idx.get("pool3"))
-    c4 = cb(cb(p3, "enc4a"), "enc4b")
+    c4 = cb(cb(p3, "enc4a"), "enc4b", "enc4a")
     c4 = _dropout(c4, dm.get("drop4"), training)                 # skip-4 carries the dropped tensor (Q2)
     p4 = _pool(fan(c4), pool_idx.get("pool4"))
-    bt = cb(cb(p4, "bota"), "botb")
+    bt = cb(cb(p4, "bota"), "botb", "bota")
     bt = _dropout(bt, dm.get("dropb"), training)
     d = bt
     for lvl, skip in ((4, c4), (3, c3), (2, c2), (1, c1)):
-        u = _deconv_block(d, f"up{lvl}", params, training, new_stats, taps, st)
+        u = _deconv_block(d, f"up{lvl}", params, training, new_stats, taps, st, scales)
         cat = torch.cat([fan(skip), u], dim=1)                    # [skip, up]  UNet/model.py:117
-        d = cb(cb(cat, f"dec{lvl}a"), f"dec{lvl}b")
+        d = cb(cb(cat, f"dec{lvl}a", (skip.shape[1], f"up{lvl}")), f"dec{lvl}b", f"dec{lvl}a")
     logits = cb(d, "head")                                        # 1x1 + ReLU + BN (Q1)
     logits = logits.permute(0, 2, 3, 1)
     return torch.softmax(logits, dim=-1), logits
