@@ -220,6 +220,14 @@ int ub_conv3x3_fwd_cases(const void* x0, int C0, const void* x1, int C1, const v
                          int H, int W, int Cout, int relu, cudaStream_t stream);
 int ub_border_sums(const void* dz, const float* total, float* sdz, float* scratch, int N, int H, int W, int C, int dtype, cudaStream_t stream);
 int ub_wgrad_fold_fix(float* dw, const float* scale, const float* shift, const float* sdz, int Cout, int Cin, cudaStream_t stream);
+/* the 1x1 head on a folded input (no padding, one bias): w fp32 [K][64] -> w_out = w s[c], bias_out[k] = b[k] + sum_c w[k][c] t[c];
+ * its weight gradient computed with x = a is fixed by dW[k][c] = s[c] dW[k][c] + t[c] db[k] */
+int ub_fold_head_weights(const float* w, const float* bias, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         float* w_out, float* bias_out, float* scale_out, float* shift_out, int K, cudaStream_t stream);
+int ub_head_wgrad_fold_fix(float* dw, const float* db, const float* scale, const float* shift, int K, cudaStream_t stream);
+/* ub_bn_apply_pool without the y output: pooled = maxpool2x2(dropout(BN(a))) and the argmax slots only */
+int ub_bn_pool(const void* a, void* pooled, unsigned char* idx, const float* mean, const float* rstd, const float* gamma,
+               const float* beta, const unsigned char* drop_mask, int N, int H, int W, int C, int dtype, cudaStream_t stream);
 
 /* ---- fp32 check mode (CUDA cores, fp32 storage) ----------------------------------------------------------------- */
 int ub_check_conv3x3(const float* x0, int C0, const float* x1, int C1, const float* w, const float* bias, float* out0, int Co0,

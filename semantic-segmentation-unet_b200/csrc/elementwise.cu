@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(TPB) bn_apply_kernel(const T* __restrict__ a, 
 
 // One thread = one 2x2 window x 8 channels: writes the 4 normalised pixels, the pooled max and its slot (2*dy+dx,
 // first max wins, matching argmax tie-breaking of the oracle).
-template <typename T>
+// STORE_Y = false: only the pooled tensor and the argmax slots are written (the consumers of y fold this BatchNorm, csrc/fold.cu)
+template <typename T, bool STORE_Y = true>
 __global__ void __launch_bounds__(TPB, 3) bn_apply_pool_kernel(const T* __restrict__ a, T* __restrict__ y, T* __restrict__ pooled,
                                                             uint8_t* __restrict__ idx, const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(TPB, 3) bn_apply_pool_kernel(const T* __restri
         if (drop_mask) v = dmb[k] ? 2.f * v : 0.f;
         f[k] = v;
       }
-      V8<T>::store(y + off, f);
+      if (STORE_Y) V8<T>::store(y + off, f);
       // compare what the consumer will read (storage precision), so the saved slot agrees with a re-computed pool
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -800,6 +801,18 @@ int ub_bn_apply_pool(const void* a, void* y, void* pooled, unsigned char* idx, c
   const int grid = grid_for(total, TPB, ub_num_sms() * 12);
   UB_DISPATCH_T(dtype, (bn_apply_pool_kernel<T><<<grid, TPB, 0, stream>>>((const T*)a, (T*)y, (T*)pooled, idx, mean, rstd, gamma, beta,
                                                                          drop_mask, N, H, W, C)));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_pool(const void* a, void* pooled, unsigned char* idx, const float* mean, const float* rstd, const float* gamma,
+               const float* beta, const unsigned char* drop_mask, int N, int H, int W, int C, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(a && pooled && idx && mean && rstd && gamma && beta, "bn_pool: bad args");
+  UB_CHECK_SHAPE(channels_ok(C) && H % 2 == 0 && W % 2 == 0, "bn_pool: C=%d must be a power of two in [64,2048], H/W even", C);
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  const int grid = grid_for(total, TPB, ub_num_sms() * 12);
+  UB_DISPATCH_T(dtype, (bn_apply_pool_kernel<T, false><<<grid, TPB, 0, stream>>>((const T*)a, nullptr, (T*)pooled, idx, mean, rstd, gamma, beta,
+                                                                                drop_mask, N, H, W, C)));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

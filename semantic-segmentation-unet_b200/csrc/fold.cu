@@ -141,9 +141,57 @@ __global__ void __launch_bounds__(TPB) wgrad_fold_fix_kernel(float* __restrict__
   }
 }
 
+// 1x1 head (no padding: one bias): w' = w * s[c], b' = b + sum_c w * t[c]; one block, K <= UB_MAX_CLASSES
+__global__ void fold_head_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ mean,
+                                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float* __restrict__ w_out, float* __restrict__ bias_out, float* __restrict__ scale_out,
+                                 float* __restrict__ shift_out, int K) {
+  __shared__ double sh[64];
+  const int c = threadIdx.x;          // 64 threads = 64 input channels
+  const float s = gamma[c] * rstd[c];
+  const float t = beta[c] - mean[c] * s;
+  scale_out[c] = s;
+  shift_out[c] = t;
+  for (int k = 0; k < K; ++k) {
+    const float wv = w[k * 64 + c];
+    w_out[k * 64 + c] = wv * s;
+    __syncthreads();
+    sh[c] = (double)wv * (double)t;
+    __syncthreads();
+    if (c == 0) {
+      double acc = bias ? (double)bias[k] : 0.0;
+      for (int i = 0; i < 64; ++i) acc += sh[i];
+      bias_out[k] = (float)acc;
+    }
+  }
+}
+
+// dW[k][c] = s[c] * dW_a[k][c] + t[c] * db[k]
+__global__ void head_wgrad_fold_fix_kernel(float* __restrict__ dw, const float* __restrict__ db, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K * 64) dw[i] = fmaf(scale[i & 63], dw[i], shift[i & 63] * db[i >> 6]);
+}
+
 }  // namespace
 
 extern "C" {
+
+int ub_fold_head_weights(const float* w, const float* bias, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         float* w_out, float* bias_out, float* scale_out, float* shift_out, int K, cudaStream_t stream) {
+  UB_CHECK_ARG(w && mean && rstd && gamma && beta && w_out && bias_out && scale_out && shift_out && K >= 1 && K <= UB_MAX_CLASSES,
+               "fold_head_weights: bad args");
+  fold_head_kernel<<<1, 64, 0, stream>>>(w, bias, mean, rstd, gamma, beta, w_out, bias_out, scale_out, shift_out, K);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_head_wgrad_fold_fix(float* dw, const float* db, const float* scale, const float* shift, int K, cudaStream_t stream) {
+  UB_CHECK_ARG(dw && db && scale && shift && K >= 1 && K <= UB_MAX_CLASSES, "head_wgrad_fold_fix: bad args");
+  head_wgrad_fold_fix_kernel<<<(K * 64 + 127) / 128, 128, 0, stream>>>(dw, db, scale, shift, K);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
 
 int ub_fold_conv3_weights(const float* w, int Cout, int C0, const float* mean0, const float* rstd0, const float* gamma0, const float* beta0,
                           int C1, const float* mean1, const float* rstd1, const float* gamma1, const float* beta1, const float* bias,

@@ -596,8 +596,8 @@ class UNet:
     def _forward_train_folded(self, x, N, H, W, dm):
         """Training forward (bf16) in which a layer's BatchNorm output is not written when all of its consumers are 3x3
         convolutions: those read the pre-BatchNorm activation with folded weights and a 9-case border bias (csrc/fold.cu).
-        Folded producers: enc<l>a, bota, dec<l>a, up<l>.  Kept: layers followed by max-pool (the pool needs y), by dropout, by a
-        transposed convolution or by the head."""
+        Folded producers: enc<l>a, bota, dec<l>a, up<l>, enc1b-enc3b (pool output written, y not) and dec1b (folded into the 1x1
+        head).  Kept: layers followed by dropout (enc4b, botb) or by a transposed convolution (dec2b-dec4b)."""
         Ls = self.layers
         for L in Ls.values():
             L.fold = None
@@ -612,7 +612,14 @@ class UNet:
             if lvl > 1:
                 self._conv_fwd(La, self._b(f"pool{lvl - 1}"), La.cin, None, 0, N, h, w, True)
             self._conv_fwd_fold(Lb, self._b("a:" + La.name), Lb.cin, La, None, 0, None, N, h, w)
-            self._bn_apply(Lb, N, h, w, True, drop=dm.get("drop4") if lvl == 4 else None, pool_lvl=lvl)
+            if lvl == 4:          # dropout sits between this BatchNorm and its consumers: y is materialised
+                self._bn_apply(Lb, N, h, w, True, drop=dm.get("drop4"), pool_lvl=lvl)
+            else:                 # pool and skip only: the pooled tensor is written, the skip consumer folds this BatchNorm
+                self._cur = Lb.name
+                mean, rstd = self._bn_vectors(Lb, True)
+                gamma, beta = self._affine(Lb)
+                self._call("ub_bn_pool", self._b("a:" + Lb.name), self._b(f"pool{lvl}"), self._b(f"idx{lvl}"), mean, rstd, gamma, beta, None,
+                           N, h, w, Lb.cout, self.act_code)
         h, w = self._dims(H, W, 5)
         La, Lb = Ls["bota"], Ls["botb"]
         self._conv_fwd(La, self._b("pool4"), La.cin, None, 0, N, h, w, True)
@@ -626,10 +633,15 @@ class UNet:
             self._call("ub_deconv2x2_fwd", cur, Lu.cin, self._wptr(Lu), self.P[Lu.off_b:Lu.off_b + Lu.cout], self._b("a:" + Lu.name), self.partial,
                        N, hi, wi, Lu.cout)
             self._finalize(Lu, 4 * Lu.cout, 4, N * h * w)
-            # concat [skip, up] (model.py:117): the skip is a real y tensor, the up-convolution's BatchNorm is folded
-            self._conv_fwd_fold(La, self._b(f"y:enc{lvl}b"), Lu.cout, None, self._b("a:" + Lu.name), Lu.cout, Lu, N, h, w)
+            # concat [skip, up] (model.py:117): both BatchNorms are folded, except the level-4 skip (dropout: a real y tensor)
+            Ls_skip = Ls[f"enc{lvl}b"]
+            if lvl == 4:
+                self._conv_fwd_fold(La, self._b("y:enc4b"), Lu.cout, None, self._b("a:" + Lu.name), Lu.cout, Lu, N, h, w)
+            else:
+                self._conv_fwd_fold(La, self._b("a:" + Ls_skip.name), Lu.cout, Ls_skip, self._b("a:" + Lu.name), Lu.cout, Lu, N, h, w)
             self._conv_fwd_fold(Lb, self._b("a:" + La.name), Lb.cin, La, None, 0, None, N, h, w)
-            cur = self._bn_apply(Lb, N, h, w, True)
+            if lvl > 1:           # feeds a transposed convolution: y is materialised; dec1b feeds the head, which folds it
+                cur = self._bn_apply(Lb, N, h, w, True)
         return cur
 
     def _forward_folded(self, x, N, H, W):
@@ -685,6 +697,20 @@ class UNet:
         K = self.number_classes
         P = N * H * W
         a = self._b("a:head")
+        if training and self.fold_bn and self.precision == "bf16":
+            # dec1b's BatchNorm folded into the 1x1 head (no padding: one bias vector), csrc/fold.cu
+            Ld = self.layers["dec1b"]
+            L.fold = (Ld, None)
+            wf = self._ensure("wfold:head", K * 64, torch.float32)
+            bf = self._ensure("bfold:head", _pad8(K), torch.float32)
+            sc = self._ensure("fold_s:head", 64, torch.float32)
+            sh = self._ensure("fold_t:head", 64, torch.float32)
+            mean, rstd = self._bn_vectors(Ld, True)
+            gamma, beta = self._affine(Ld)
+            self._call("ub_fold_head_weights", self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K], mean, rstd, gamma, beta, wf, bf, sc, sh, K)
+            self._call("ub_head_fwd", self._b("a:dec1b"), wf, bf, a, self.partial, P, K, self.act_code)
+            self._finalize(L, K, 1, P)
+            return a
         self._call("ub_head_fwd", self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K], a,
                    self.partial if training else None, P, K, self.act_code)
         if training:
@@ -790,6 +816,7 @@ class UNet:
         self._cur = "head"
         mean, rstd = self._bn_vectors(L, not infer)
         dl, a = self._b("dlogits"), self._b("a:head")
+        head_x = self._b("a:dec1b") if L.fold is not None else self._b("y:dec1b")       # folded head: its weight gradient reads `a` too
         dbeta, dgamma = self.G[L.off_beta:L.off_beta + K], self.G[L.off_gamma:L.off_gamma + K]
         if infer:
             dbeta.zero_()
@@ -802,16 +829,19 @@ class UNet:
             # the head's dgrad writes dL/dy of dec1b: that layer's BatchNorm-backward sums come out of the same pass
             Ld = Ls["dec1b"]
             rm, rr = self._bn_vectors(Ld, True)
-            self._call("ub_head_bwd_apply_bnred", dl, a, self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
+            self._call("ub_head_bwd_apply_bnred", dl, a, head_x, self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
                        self.P[L.off_gamma:L.off_gamma + K], dbeta, dgamma, self._b("g:dec1b"), self.partial, P, K, self.act_code,
                        self._b("a:dec1b"), rm, rr, self.partial_red)
             self._red_ready = "dec1b"
         else:
-            self._call("ub_head_bwd_apply", dl, a, self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
+            self._call("ub_head_bwd_apply", dl, a, head_x, self.P[L.off_w:L.off_w + L.n_w], mean, rstd,
                        self.P[L.off_gamma:L.off_gamma + K], dbeta, dgamma, self._b("g:dec1b"), self.partial, P, K, self.act_code)
         ncomp = K * 64 + K
         self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, ncomp, K * 64, self.G[L.off_w:L.off_w + K * 64], 1.0)
         self._call("ub_reduce_rows", self.partial[K * 64:], _C.UB_STATS_ROWS, ncomp, K, self.G[L.off_b:L.off_b + K], 1.0)
+        if L.fold is not None:          # dW[k][c] = s[c] dW_a[k][c] + t[c] db[k]
+            self._call("ub_head_wgrad_fold_fix", self.G[L.off_w:L.off_w + K * 64], self.G[L.off_b:L.off_b + K], self._b("fold_s:head"),
+                       self._b("fold_t:head"), K)
         done("head")
         # ---- decoder
         for lvl in (1, 2, 3, 4):

@@ -17,6 +17,7 @@ def all_cases():
     d = dict(K.CASES)
     d.update(G.CASES)
     d.update(K.PENDING_CASES)          # written but not yet run on a B200: only selected by `--pending` or by name
+    d.update(G.PENDING_CASES)
     return d
 
 
@@ -33,11 +34,14 @@ if __name__ == "__main__":
         sys.exit(0)
     pat = sys.argv[1] if len(sys.argv) > 1 else ""
     cases = all_cases()
+    import graph_cases as G
     import kernel_cases as K
+    pending = dict(K.PENDING_CASES)
+    pending.update(G.PENDING_CASES)
     if pat == "--pending":
-        pat = ",".join(K.PENDING_CASES)
+        pat = ",".join(pending)
     elif not pat:
-        cases = {k: v for k, v in cases.items() if k not in K.PENDING_CASES}
+        cases = {k: v for k, v in cases.items() if k not in pending}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     report = {}
     for name in cases:

@@ -716,7 +716,54 @@ def case_wgrad_folded(C0=64, C1=0, Cout=64, N=2, H=24, W=40, seed=32, identity0=
     return r
 
 
+def case_head_fold(K=2, P=777, seed=33):
+    """ub_fold_head_weights + ub_head_fwd on `a` == head on the BatchNorm output; ub_head_wgrad_fold_fix restores the weight gradient"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    a = np.maximum(rng.normal(0.3, 1.0, size=(P, 64)), 0).astype(np.float32)
+    w = (rng.normal(size=(K, 64)) / 8).astype(np.float32)
+    b = rng.normal(size=K).astype(np.float32) * 0.1
+    mean, rstd = rng.normal(0.4, 0.1, size=64).astype(np.float32), rng.uniform(0.5, 2.0, size=64).astype(np.float32)
+    gamma, beta = rng.normal(1.0, 0.3, size=64).astype(np.float32), rng.normal(0.0, 0.2, size=64).astype(np.float32)
+    s = gamma.astype(np.float64) * rstd
+    t = beta.astype(np.float64) - mean.astype(np.float64) * s
+    wf, bf = torch.empty((K, 64), device="cuda"), torch.empty(8, device="cuda")
+    sc, sh = torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+    C.call("ub_fold_head_weights", dev(w, torch.float32), dev(b, torch.float32), dev(mean, torch.float32), dev(rstd, torch.float32),
+           dev(gamma, torch.float32), dev(beta, torch.float32), wf, bf, sc, sh, K, stream())
+    out = torch.empty((P, K), device="cuda")
+    C.call("ub_head_fwd", dev(a, torch.float32), wf, bf, out, None, P, K, C.UB_F32, stream())
+    y = a.astype(np.float64) * s + t
+    ref = np.maximum(y @ w.astype(np.float64).T + b, 0)
+    dz = rng.normal(size=(P, K))
+    dw_a = torch.tensor((dz.T @ a.astype(np.float64)).astype(np.float32), device="cuda").contiguous()
+    db = torch.tensor(dz.sum(0).astype(np.float32), device="cuda")
+    C.call("ub_head_wgrad_fold_fix", dw_a, db, sc, sh, K, stream())
+    torch.cuda.synchronize()
+    r = dict(e_fwd=rel_err(out.cpu().numpy(), ref), e_dw=rel_err(dw_a.cpu().numpy(), dz.T @ y))
+    r["ok"] = bool(r["e_fwd"] < 1e-5 and r["e_dw"] < 1e-5)
+    return r
+
+
+def case_bn_pool_noy(C_=128, N=2, H=16, W=24, seed=34):
+    """ub_bn_pool == the pooled tensor and argmax slots of ub_bn_apply_pool (which also writes y)"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    a = dev(bf16_round(np.maximum(rng.normal(0.3, 1.0, size=(N, H, W, C_)), 0)), torch.bfloat16)
+    v = [dev(x.astype(np.float32), torch.float32) for x in (rng.normal(0.4, 0.1, C_), rng.uniform(0.5, 2.0, C_), rng.normal(1.0, 0.5, C_), rng.normal(0, 0.2, C_))]
+    y = torch.empty((N, H, W, C_), dtype=torch.bfloat16, device="cuda")
+    p1, p2 = (torch.empty((N, H // 2, W // 2, C_), dtype=torch.bfloat16, device="cuda") for _ in range(2))
+    i1, i2 = (torch.empty((N, H // 2, W // 2, C_), dtype=torch.uint8, device="cuda") for _ in range(2))
+    C.call("ub_bn_apply_pool", a, y, p1, i1, *v, None, N, H, W, C_, C.UB_BF16, stream())
+    C.call("ub_bn_pool", a, p2, i2, *v, None, N, H, W, C_, C.UB_BF16, stream())
+    torch.cuda.synchronize()
+    return dict(ok=bool(torch.equal(p1, p2) and torch.equal(i1, i2)))
+
+
 PENDING_CASES = {
+    "head_fold_k2": case_head_fold,
+    "head_fold_k8": lambda: case_head_fold(8, P=513),
+    "bn_pool_noy": case_bn_pool_noy,
     "fold_weights_64": case_fold_weights,
     "fold_weights_cat_128+128_256": lambda: case_fold_weights(128, 128, 256, identity0=True),
     "conv_fwd_folded_64_64": case_conv_fwd_folded,

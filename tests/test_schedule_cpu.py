@@ -91,10 +91,12 @@ def test_optional_schedules():
     m.fold_bn = True
     names = _step(m)
     c = _count(names)
-    # 13 producers lose their BatchNorm-apply pass; their 13 consumers fold the weights, use the case bias and fix the weight gradient
+    # 17 producers lose their BatchNorm-apply pass (13 conv/deconv layers, enc1b-3b behind a y-less pool, dec1b behind the folded
+    # head); the 13 consumer convs fold the weights, use the case bias and fix the weight gradient
     assert c["ub_fold_conv3_weights"] == 13 and c["ub_conv3x3_fwd_cases"] == 13 and c["ub_conv3x3_fwd"] == 4
-    assert c["ub_bn_apply"] + c["ub_bn_apply_pool"] == 22 - 13
+    assert c["ub_bn_apply"] == 4 and c["ub_bn_apply_pool"] == 1 and c["ub_bn_pool"] == 3          # botb, dec2b-4b | enc4b | enc1b-3b
     assert c["ub_border_sums"] == 13 and c["ub_wgrad_fold_fix"] == 13 and c["ub_conv3x3_wgrad"] == 17
+    assert c["ub_fold_head_weights"] == 1 and c["ub_head_wgrad_fold_fix"] == 1 and c["ub_head_fwd"] == 1
     folded = {l for n, l in m.calls if n == "ub_conv3x3_fwd_cases"}
     assert folded == {"enc1b", "enc2b", "enc3b", "enc4b", "botb", "dec4a", "dec4b", "dec3a", "dec3b", "dec2a", "dec2b", "dec1a", "dec1b"}
     # back to the default schedule on the same object
