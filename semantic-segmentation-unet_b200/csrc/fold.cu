@@ -6,8 +6,10 @@
 //   ub_border_sums         Sdz[tap][co] = sum of dz over the pixels whose tap neighbour is inside the image
 //   ub_wgrad_fold_fix      dW = s[ci] * dW_a + t[ci] * Sdz[tap][co]      (dW_a = weight gradient computed on `a`)
 // The algebra is proven in fp64 in oracle/unet_numpy.py (fold_weights, border_case_bias, border_sums, conv_wgrad_folded).
-// STATUS: compiled and covered by parity cases (tests/kernel_cases.py PENDING_CASES) but not yet run on a B200 and not wired
-// into the training step (UNet.fold_bn stays False) -- the GPU budget of the round ended first.
+//   ub_fold_head_weights / ub_head_wgrad_fold_fix   the same for the 1x1 head (no padding: a single bias vector)
+// STATUS: compiled, wired into the training step behind UNet.fold_bn (default False) and covered by parity cases
+// (tests/kernel_cases.py and tests/graph_cases.py PENDING_CASES), but not yet run on a B200 -- the GPU budget of the round
+// ended first.
 #include "common.cuh"
 
 namespace {
