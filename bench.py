@@ -105,7 +105,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in o.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def start(self):
         self._t.start()
