@@ -273,7 +273,8 @@ def write(path, items, psize=4096, map_size=None):
         buf = bytearray(psize)
         struct.pack_into("<QHHHH", buf, 0, pgno, 0, P_META, 0, 0)
         struct.pack_into("<IIQQ", buf, PAGEHDRSZ, MDB_MAGIC, MDB_DATA_VERSION, 0, map_size)
-        struct.pack_into(DB_FMT, buf, PAGEHDRSZ + 24, psize, 0, 0, 0, 0, 0, 0, P_INVALID)                       # FREE_DBI (md_pad = page size)
+        # FREE_DBI: md_pad carries the page size, md_flags = mm_flags = MDB_INTEGERKEY (0x08), as mdb_env_init_meta stamps it
+        struct.pack_into(DB_FMT, buf, PAGEHDRSZ + 24, psize, 0x08, 0, 0, 0, 0, 0, P_INVALID)
         struct.pack_into(DB_FMT, buf, PAGEHDRSZ + 24 + DB_SIZE, 0, 0, depth, n_branch, n_leaf, n_over, len(items), root)   # MAIN_DBI
         struct.pack_into("<QQ", buf, PAGEHDRSZ + 24 + 2 * DB_SIZE, last_pg if last_pg >= 1 else 1, txnid)
         return bytes(buf)
