@@ -118,3 +118,46 @@ def test_test_step_and_inference_schedules():
         m.forward_softmax(torch.zeros((1, 1, 24, 32)))              # not a multiple of 16 (UNet/inference.py:42)
     with pytest.raises(IOError):
         m.train_step(torch.zeros((1, 2, 32, 32)), torch.zeros((1, 32, 32), dtype=torch.uint8))      # wrong channel count
+
+
+def test_tiled_inference_schedule():
+    """unetb200.inference.segment_device on the dry model: tiles grouped by shape, batched, every zone handed to ub_head_argmax
+    exactly once with the geometry of tile_plan (UNet/inference.py:56-129); two ranks split the tiles without overlap"""
+    import unetb200.inference as I
+
+    class Geo(DryUNet):
+        def _call(self, name, *args):
+            if name == "ub_head_argmax":
+                geo, n = args[9], args[6]
+                self.zones.extend(geo[:n].tolist())
+            return super()._call(name, *args)
+
+    H, W = 2048 + 160, 1024 + 496
+    plan = I.tile_plan(H, W, 1024, 96)
+    seen = []
+    for rank in (0, 1):
+        m = Geo(2, 1, 1, precision="bf16", seed=0)
+        m.zones = []
+
+        class D:
+            world_size = 2
+        D.rank = rank
+        real = torch.distributed.all_reduce
+        torch.distributed.all_reduce = lambda *a, **k: None          # the mask SUM-reduce across ranks (no process group here)
+        try:
+            mask = I.segment_device(torch.zeros((1, H, W)), m, 1024, radius=96, tile_batch=4, dist=D)
+        finally:
+            torch.distributed.all_reduce = real
+        assert tuple(mask.shape) == (H, W) and mask.dtype == torch.uint8
+        c = _count(n for n, _ in m.calls)
+        shapes = {}
+        for t in plan[rank::2]:
+            shapes.setdefault((t["y1"] - t["y0"], t["x1"] - t["x0"]), []).append(t)
+        assert c["ub_head_argmax"] == sum(-(-len(v) // 4) for v in shapes.values())
+        seen += m.zones
+    want = sorted([t["cy0"], t["cy1"], t["cx0"], t["cx1"], t["dy"], t["dx"]] for t in plan)
+    assert sorted(seen) == want
+    cover = np.zeros((H, W), dtype=np.int32)
+    for cy0, cy1, cx0, cx1, dy, dx in seen:
+        cover[dy:dy + cy1 - cy0, dx:dx + cx1 - cx0] += 1
+    assert (cover == 1).all()
