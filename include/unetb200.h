@@ -181,6 +181,14 @@ int ub_cast_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
 /* zscore_normalize (UNet/imagereader.py:33-66) per plane; src_dtype 0 = u8, 1 = u16, 2 = f32;
  * scratch: planes * UB_ZSCORE_BLOCKS * 2 doubles */
 int ub_zscore(const void* src, int src_dtype, float* dst, double* scratch, int planes, long long plane, cudaStream_t stream);
+/* the same normalisation in two halves, for an image whose rows are split across ranks (unetb200.inference.segment_banded; first
+ * GPU run pending): ub_zscore_sums -> sums = double[planes][2] (sum, sum of squares) over `plane` elements of each plane
+ * (planes `plane_stride` elements apart; scratch as for ub_zscore), to be SUM-all-reduced; ub_zscore_apply_sums normalises
+ * contiguous planes with the statistics sums / count */
+int ub_zscore_sums(const void* src, int src_dtype, double* sums, double* scratch, int planes, long long plane, long long plane_stride,
+                   cudaStream_t stream);
+int ub_zscore_apply_sums(const void* src, int src_dtype, float* dst, const double* sums, double count, int planes, long long plane,
+                         cudaStream_t stream);
 
 /* ---- training-time augmentation on raw-pixel batches (UNet/augment.py:19-174, called from UNet/imagereader.py:283-294) ---
  * Planes are NCHW as the reader ships them. dtype codes here: 0 = u8, 1 = u16, 2 = f32.

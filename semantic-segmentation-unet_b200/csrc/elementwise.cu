@@ -718,6 +718,84 @@ __global__ void __launch_bounds__(TPB) zscore_apply_kernel(const TI* __restrict_
     yp[i] = ((float)xp[i] - mu) / inv;
 }
 
+// ---- z-score in two halves (image split across ranks: each rank sums the rows it owns, the sums are all-reduced, then
+// every rank normalises its band with the GLOBAL statistics; unetb200.inference.segment_banded) -----------------------------
+template <typename TI>
+__global__ void __launch_bounds__(TPB) zscore_part_stats_kernel(const TI* __restrict__ x, double* __restrict__ partial, long long plane,
+                                                                long long plane_stride) {
+  const TI* xp = x + (long long)blockIdx.y * plane_stride;
+  double s = 0.0, q = 0.0;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < plane; i += (long long)gridDim.x * TPB) {
+    const double v = (double)(float)xp[i];
+    s += v;
+    q += v * v;
+  }
+  __shared__ double sh[2][TPB / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = s;
+    sh[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < TPB / 32; ++w) {
+      ts += sh[0][w];
+      tq += sh[1][w];
+    }
+    partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 0] = ts;
+    partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 + 1] = tq;
+  }
+}
+
+// sums[plane][2] = fixed-order sum of the plane's block partials (one block per plane)
+__global__ void __launch_bounds__(TPB) zscore_fold_partials_kernel(const double* __restrict__ partial, double* __restrict__ sums, int nblk) {
+  __shared__ double sh[2][TPB / 32];
+  double ts = 0.0, tq = 0.0;
+  for (int b = threadIdx.x; b < nblk; b += TPB) {
+    ts += partial[((size_t)blockIdx.x * nblk + b) * 2 + 0];
+    tq += partial[((size_t)blockIdx.x * nblk + b) * 2 + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ts += __shfl_xor_sync(0xffffffffu, ts, o);
+    tq += __shfl_xor_sync(0xffffffffu, tq, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = ts;
+    sh[1][threadIdx.x >> 5] = tq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < TPB / 32; ++w) {
+      a += sh[0][w];
+      b += sh[1][w];
+    }
+    sums[blockIdx.x * 2 + 0] = a;
+    sums[blockIdx.x * 2 + 1] = b;
+  }
+}
+
+// y = (x - mean) / (std <= 1 ? 1 : std) with mean / std from sums[plane] = (sum, sum of squares) over `count` samples
+template <typename TI>
+__global__ void __launch_bounds__(TPB) zscore_apply_sums_kernel(const TI* __restrict__ x, float* __restrict__ y, const double* __restrict__ sums,
+                                                                double count, long long plane) {
+  const double mu_d = sums[blockIdx.y * 2 + 0] / count;
+  double var = sums[blockIdx.y * 2 + 1] / count - mu_d * mu_d;
+  if (var < 0.0) var = 0.0;
+  const float sd = (float)sqrt(var);
+  const float mu = (float)mu_d, inv = (sd <= 1.0f) ? 1.0f : sd;
+  const TI* xp = x + (long long)blockIdx.y * plane;
+  float* yp = y + (long long)blockIdx.y * plane;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < plane; i += (long long)gridDim.x * TPB)
+    yp[i] = ((float)xp[i] - mu) / inv;
+}
+
 inline int grid_for(long long work_items, int per_block, int cap) {
   long long g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -960,6 +1038,33 @@ int ub_zscore(const void* src, int src_dtype, float* dst, double* scratch, int p
     ub_set_error("zscore: bad src dtype %d", src_dtype);
     return UB_ERR_INVALID_ARG;
   }
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_zscore_sums(const void* src, int src_dtype, double* sums, double* scratch, int planes, long long plane, long long plane_stride,
+                   cudaStream_t stream) {
+  UB_CHECK_ARG(src && sums && scratch && planes > 0 && plane > 0 && plane_stride >= plane, "zscore_sums: bad args");
+  const int nblk = grid_for(plane, TPB * 8, UB_ZSCORE_BLOCKS);
+  const dim3 grid(nblk, planes);
+  if (src_dtype == 0) zscore_part_stats_kernel<uint8_t><<<grid, TPB, 0, stream>>>((const uint8_t*)src, scratch, plane, plane_stride);
+  else if (src_dtype == 1) zscore_part_stats_kernel<uint16_t><<<grid, TPB, 0, stream>>>((const uint16_t*)src, scratch, plane, plane_stride);
+  else if (src_dtype == 2) zscore_part_stats_kernel<float><<<grid, TPB, 0, stream>>>((const float*)src, scratch, plane, plane_stride);
+  else UB_CHECK_ARG(false, "zscore_sums: bad src dtype %d", src_dtype);
+  UB_LAUNCH_CHECK();
+  zscore_fold_partials_kernel<<<planes, TPB, 0, stream>>>(scratch, sums, nblk);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_zscore_apply_sums(const void* src, int src_dtype, float* dst, const double* sums, double count, int planes, long long plane,
+                         cudaStream_t stream) {
+  UB_CHECK_ARG(src && dst && sums && count > 0 && planes > 0 && plane > 0, "zscore_apply_sums: bad args");
+  const dim3 grid(grid_for(plane, TPB * 4, 4096), planes);
+  if (src_dtype == 0) zscore_apply_sums_kernel<uint8_t><<<grid, TPB, 0, stream>>>((const uint8_t*)src, dst, sums, count, plane);
+  else if (src_dtype == 1) zscore_apply_sums_kernel<uint16_t><<<grid, TPB, 0, stream>>>((const uint16_t*)src, dst, sums, count, plane);
+  else if (src_dtype == 2) zscore_apply_sums_kernel<float><<<grid, TPB, 0, stream>>>((const float*)src, dst, sums, count, plane);
+  else UB_CHECK_ARG(false, "zscore_apply_sums: bad src dtype %d", src_dtype);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -127,6 +127,100 @@ def segment_device(img_chw, unet_model, tile_size=TILE_SIZE, radius=None, tile_b
     return mask
 
 
+def band_plan(height, width, tile_size, radius, world):
+    """Row-band sharding of the tile plan: rank r owns a contiguous run of tile ROWS, i.e. the zone rows [zy0, zy1) across the
+    whole width, and needs the image rows [y0, y1) (its zones plus halo).  Zones of different ranks are disjoint and cover the
+    image, so each rank uploads / normalises / segments only its band and the mask is assembled by concatenating bands --
+    instead of every rank uploading the whole image and all-reducing the whole mask (segment_device)."""
+    plan = tile_plan(height, width, tile_size, radius)
+    rows = sorted({t["dy"] for t in plan})
+    out = []
+    for r in range(world):
+        lo, hi = (len(rows) * r) // world, (len(rows) * (r + 1)) // world
+        mine_rows = set(rows[lo:hi])
+        tiles = [t for t in plan if t["dy"] in mine_rows]
+        if not tiles:
+            out.append(dict(tiles=[], y0=0, y1=0, zy0=0, zy1=0))
+            continue
+        out.append(dict(tiles=tiles, y0=min(t["y0"] for t in tiles), y1=max(t["y1"] for t in tiles), zy0=min(t["dy"] for t in tiles),
+                        zy1=max(t["dy"] + t["cy1"] - t["cy0"] for t in tiles)))
+    return out
+
+
+def segment_banded(raw_host, unet_model, dist, tile_size=TILE_SIZE, radius=None, tile_batch=TILE_BATCH, out_host=None):
+    """Tiled inference of one image with the ROWS sharded over the ranks of `dist` (NOT YET RUN ON A B200; segment_device is the
+    verified path).  raw_host: pinned host tensor [C, H, W] of raw pixels (uint8 / uint16-as-int16 bits / float32), the same on
+    every rank.  Each rank uploads its band, the per-channel z-score statistics of the UNPADDED image (UNet/inference.py:206) are
+    summed over the owned rows and all-reduced (2 doubles per channel), the band is normalised, reflect-padded where it touches
+    the bottom / right edge (inference.py:46), segmented, and the band masks are sent to rank 0.
+    Returns the uint8 device mask [H, W] on rank 0 (None elsewhere); if `out_host` (pinned uint8 [H, W]) is given rank 0 copies it."""
+    import torch
+    import torch.distributed as td
+    from . import _C
+    C, H, W = raw_host.shape
+    dev = unet_model.device
+    rank, world = dist.rank, dist.world_size
+    pad_y, pad_x = _pad_amounts(H, W)
+    Hp, Wp = H + pad_y, W + pad_x
+    if radius is None:
+        radius = unet_model.estimate_radius()
+    bands = band_plan(Hp, Wp, tile_size, radius, world)
+    b = bands[rank]
+    code = {torch.uint8: 0, torch.int16: 1, torch.float32: 2}[raw_host.dtype]
+    st = unet_model._stream()
+    sums = torch.zeros((C, 2), dtype=torch.float64, device=dev)
+    band_mask = None
+    if b["tiles"]:
+        y0, y1 = b["y0"], min(b["y1"], H)                       # rows that exist in the unpadded image
+        raw = torch.empty((C, y1 - y0, W), dtype=raw_host.dtype, device=dev)
+        for c in range(C):                                       # each channel's band is one contiguous chunk of the host image
+            raw[c].copy_(raw_host[c, y0:y1], non_blocking=True)
+        oz0, oz1 = b["zy0"], min(b["zy1"], H)                    # owned rows of the unpadded image: they carry the statistics
+        scratch = torch.empty(C * _C.UB_ZSCORE_BLOCKS * 2, dtype=torch.float64, device=dev)
+        if oz1 > oz0:
+            _C.call("ub_zscore_sums", raw[:, oz0 - y0:], code, sums, scratch, C, (oz1 - oz0) * W, (y1 - y0) * W, st)
+    if world > 1:
+        td.all_reduce(sums, op=td.ReduceOp.SUM)
+    if b["tiles"]:
+        x = torch.empty((C, y1 - y0, W), dtype=torch.float32, device=dev)
+        _C.call("ub_zscore_apply_sums", raw, code, x, sums, float(H) * float(W), C, (y1 - y0) * W, st)
+        bot = b["y1"] - y1                                       # padded rows below the image that this band's tiles read
+        if bot or pad_x:
+            x = torch.nn.functional.pad(x[None], (0, pad_x, 0, bot), mode="reflect")[0].contiguous()
+        zr = b["zy1"] - b["zy0"]
+        band_mask = torch.zeros((zr, Wp), dtype=torch.uint8, device=dev)
+        groups = {}
+        for t in b["tiles"]:
+            groups.setdefault((t["y1"] - t["y0"], t["x1"] - t["x0"]), []).append(t)
+        order = [t for shape in groups for t in groups[shape]]
+        geo = torch.from_numpy(np.array([[t["cy0"], t["cy1"], t["cx0"], t["cx1"], t["dy"] - b["zy0"], t["dx"]] for t in order], dtype=np.int32)).to(dev)
+        k = 0
+        for (h, w), tiles in groups.items():
+            xb = torch.empty((min(tile_batch, len(tiles)), C, h, w), dtype=torch.float32, device=dev)
+            for s0 in range(0, len(tiles), tile_batch):
+                chunk = tiles[s0:s0 + tile_batch]
+                for i, t in enumerate(chunk):
+                    xb[i].copy_(x[:, t["y0"] - b["y0"]:t["y1"] - b["y0"], t["x0"]:t["x1"]])
+                unet_model.predict_tiles_into(xb[:len(chunk)], geo[k:k + len(chunk)], band_mask, Wp)
+                k += len(chunk)
+    # assemble on rank 0: bands are disjoint row ranges of the padded mask
+    if rank == 0:
+        mask = torch.empty((Hp, Wp), dtype=torch.uint8, device=dev)
+        if band_mask is not None:
+            mask[b["zy0"]:b["zy1"]].copy_(band_mask)
+        for r in range(1, world):
+            br = bands[r]
+            if br["tiles"]:
+                td.recv(mask[br["zy0"]:br["zy1"]], src=r)
+        mask = mask[:H, :W]
+        if out_host is not None:
+            out_host.copy_(mask, non_blocking=True)
+        return mask
+    if band_mask is not None:
+        td.send(band_mask, dst=0)
+    return None
+
+
 def zscore_device(img_chw_raw, unet_model):
     """whole-image per-channel z-score (UNet/imagereader.py:33-66, called at inference.py:206) on the GPU.
     img_chw_raw: device tensor [C,H,W] of dtype uint8 / uint16-as-int16-bits / float32."""

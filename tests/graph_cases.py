@@ -517,8 +517,30 @@ def _with_fold(fn):
     return run
 
 
+def case_banded_inference():
+    """segment_banded (row bands, split z-score) on one rank == zscore_device + segment_device, incl. reflect padding"""
+    import unetb200.inference as I
+    from unetb200.model import UNet
+    rng = np.random.default_rng(8)
+    H, W = 1024 + 200 + 6, 1024 + 90
+    img = np.clip(rng.normal(3045.0, 376.0, size=(1, H, W)), 0, 65535).astype(np.uint16)
+    m = UNet(2, 1, 1, 1e-4, seed=4)
+    raw = torch.tensor(img.view(np.int16)).pin_memory()
+    x = I.zscore_device(raw.to(m.device), m)
+    pad_y, pad_x = I._pad_amounts(H, W)
+    xp = torch.nn.functional.pad(x[None], (0, pad_x, 0, pad_y), mode="reflect")[0].contiguous()
+    ref = I.segment_device(xp, m, 1024, radius=96)[:H, :W]
+
+    class D:
+        rank, world_size = 0, 1
+    got = I.segment_banded(raw, m, D, 1024, radius=96)
+    agree = float((got == ref).float().mean())
+    return dict(agree=agree, fg=float((ref == 1).float().mean()), ok=bool(agree == 1.0))
+
+
 # written after the round's GPU budget had run out: not yet run on a B200, not collected by pytest (tests/gpu_probe.py --pending)
 PENDING_CASES = {
+    "banded_inference": case_banded_inference,
     "fold_live_bf16_c1k2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23)),
     "fold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8)),
     "fold_golden_c1_k2_bf16": _with_fold(lambda: case_golden("graph_c1_k2", "bf16")),

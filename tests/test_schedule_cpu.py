@@ -161,3 +161,60 @@ def test_tiled_inference_schedule():
     for cy0, cy1, cx0, cx1, dy, dx in seen:
         cover[dy:dy + cy1 - cy0, dx:dx + cx1 - cx0] += 1
     assert (cover == 1).all()
+
+
+def test_banded_inference_schedule():
+    """unetb200.inference.segment_banded (row bands per rank) on the dry model: per rank, the rows uploaded, the statistics call
+    over the owned rows only, and zones that tile the rank's band; bands of all ranks tile the padded image"""
+    import torch.distributed as td
+    import unetb200.inference as I
+
+    H, W, world = 2048 + 150, 1024 + 490, 3                      # not multiples of 16: bottom / right reflect padding
+    Hp, Wp = H + (16 - H % 16) % 16, W + (16 - W % 16) % 16
+    raw = torch.zeros((1, H, W), dtype=torch.int16)
+    cover = np.zeros((Hp, Wp), dtype=np.int32)
+    owned_rows = 0
+    real_call, real_ar, real_send, real_recv = C.call, td.all_reduce, td.send, td.recv
+    try:
+        td.all_reduce = lambda *a, **k: None
+        td.send = lambda *a, **k: None
+        td.recv = lambda *a, **k: None
+        for rank in range(world):
+            log = []
+
+            def fake_call(name, *args):
+                assert name in C.DECLS and len(args) == len(C.DECLS[name][1]), name          # called with the stream as last argument
+                log.append((name, args))
+                return 0
+
+            C.call = fake_call
+
+            class Geo(DryUNet):
+                def _call(self, name, *args):
+                    if name == "ub_head_argmax":
+                        self.zones.extend(args[9][:args[6]].tolist())
+                    return super()._call(name, *args)
+
+            m = Geo(2, 1, 1, precision="bf16", seed=0)
+            m.zones = []
+
+            class D:
+                world_size = world
+            D.rank = rank
+            out = I.segment_banded(raw, m, D, 1024, radius=96, tile_batch=4)
+            assert (out is not None) == (rank == 0)
+            if rank == 0:
+                assert tuple(out.shape) == (H, W)
+            b = I.band_plan(Hp, Wp, 1024, 96, world)[rank]
+            names = [n for n, _ in log]
+            assert names == ["ub_zscore_sums", "ub_zscore_apply_sums"]
+            _, a = log[0]
+            rows_owned = min(b["zy1"], H) - b["zy0"]
+            assert a[5] == rows_owned * W and a[6] == (min(b["y1"], H) - b["y0"]) * W and a[4] == 1
+            owned_rows += rows_owned
+            assert log[1][1][4] == float(H) * float(W)                                      # statistics of the whole unpadded image
+            for cy0, cy1, cx0, cx1, dy, dx in m.zones:
+                cover[b["zy0"] + dy:b["zy0"] + dy + cy1 - cy0, dx:dx + cx1 - cx0] += 1
+    finally:
+        C.call, td.all_reduce, td.send, td.recv = real_call, real_ar, real_send, real_recv
+    assert owned_rows == H and (cover == 1).all()

@@ -52,7 +52,13 @@ def main():
     pad_y, pad_x = I._pad_amounts(S, S)
     out_host = torch.empty((S, S), dtype=torch.uint8).pin_memory()
 
+    banded = dp is not None and os.environ.get("UB_INFER_BANDED", "0") == "1"      # row-band sharding (first GPU run pending)
+
     def one():
+        if banded:
+            I.segment_banded(host, m, dp, I.TILE_SIZE, radius=96, tile_batch=args.tile_batch, out_host=out_host if rank == 0 else None)
+            torch.cuda.synchronize(dev)
+            return
         raw = host.to(dev, non_blocking=True)
         x = I.zscore_device(raw, m)
         if pad_y or pad_x:
