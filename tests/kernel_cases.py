@@ -760,7 +760,36 @@ def case_bn_pool_noy(C_=128, N=2, H=16, W=24, seed=34):
     return dict(ok=bool(torch.equal(p1, p2) and torch.equal(i1, i2)))
 
 
+def case_published_known_answers():
+    """the CUDA kernels against the API-documentation examples of the ops they replace: Adam (lr 0.1, var 10.0, grad = var -> 9.9)
+    and CategoricalCrossentropy ([[0,1,0],[0,0,1]] vs [[0.05,0.95,0],[0.1,0.8,0.1]] -> 0.0513, 2.303); see tests/test_oracle_published.py"""
+    C = _C()
+    p = dev(np.array([10.0] * 8), torch.float32)
+    g = p.clone()
+    m, v = torch.zeros(8, device="cuda"), torch.zeros(8, device="cuda")
+    import math
+    lr_t = 0.1 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    C.call("ub_adam", p, g, m, v, None, 8, lr_t, 0.9, 0.999, 1e-7, 1.0, stream())
+    # head loss: BatchNorm made the identity (mean 0, rstd 1, gamma 1, beta 0) so the "logits" are log p
+    y_pred = np.clip(np.array([[0.05, 0.95, 0.0], [0.1, 0.8, 0.1]]), 1e-7, 1 - 1e-7)
+    a = dev(np.log(y_pred) + 20.0, torch.float32)            # + constant: a stays > 0 like a ReLU output; softmax is shift invariant
+    K, P = 3, 2
+    ones, zeros = torch.ones(K, device="cuda"), torch.zeros(K, device="cuda")
+    lab = dev(np.array([1, 2]), torch.uint8)
+    sm = torch.empty((P, K), device="cuda")
+    dl = torch.empty((P, K), device="cuda")
+    partial = torch.zeros(C.UB_STATS_ROWS * 2, device="cuda")
+    C.call("ub_head_loss", a, zeros, ones, ones, zeros, lab, None, 1.0, 1.0 / P, sm, dl, partial, P, K, stream())
+    la = torch.empty(2, device="cuda")
+    C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2, 2, la, 1.0, stream())
+    torch.cuda.synchronize()
+    r = dict(adam=float(p[0]), loss_sum=float(la[0]), acc=float(la[1]), sm_err=rel_err(sm.cpu().numpy(), y_pred))
+    r["ok"] = bool(abs(r["adam"] - 9.9) < 1e-5 and abs(r["loss_sum"] - 2.354) < 1e-3 and abs(r["acc"] - 0.5) < 1e-6 and r["sm_err"] < 1e-5)
+    return r
+
+
 PENDING_CASES = {
+    "published_known_answers": case_published_known_answers,
     "head_fold_k2": case_head_fold,
     "head_fold_k8": lambda: case_head_fold(8, P=513),
     "bn_pool_noy": case_bn_pool_noy,
