@@ -104,3 +104,77 @@ def test_bucketed_allreduce_world2_gloo():
         assert mm == 0.5                         # MEAN of moving statistics
         assert p0 == 5.0 and changed == 1        # rank 0's variables broadcast
         assert nrep == 2 and same
+
+
+def _banded_worker(rank, world, port, q):
+    """segment_banded over gloo with the kernels replaced by markers: the z-score sums carry the rank, the argmax kernel paints
+    the zones it is handed with rank + 1 -- so the statistics all-reduce, the band geometry and the assembly on rank 0 are checked"""
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import numpy as np
+    import unetb200._C as C
+    import unetb200.inference as I
+    from unetb200 import dist as D
+    from unetb200 import model as M
+    dp = D.DataParallel(backend="gloo")
+    try:
+        real = torch.cuda.is_available
+        torch.cuda.is_available = lambda: True
+
+        class Dry(M.UNet):
+            def _stream(self):
+                return 0
+
+            def _call(self, name, *args):
+                if name == "ub_head_argmax":
+                    geo, n, mask, ld = args[9], args[6], args[10], args[11]
+                    for cy0, cy1, cx0, cx1, dy, dx in geo[:n].tolist():
+                        mask[dy:dy + cy1 - cy0, dx:dx + cx1 - cx0] = rank + 1
+                return 0
+        try:
+            m = Dry(2, 1, 1, precision="bf16", seed=0, device="cpu")
+        finally:
+            torch.cuda.is_available = real
+        seen = {}
+
+        def fake_call(name, *args):
+            if name == "ub_zscore_sums":
+                args[2][:] = torch.tensor([[float(rank + 1), 10.0 * (rank + 1)]], dtype=torch.float64)
+            elif name == "ub_zscore_apply_sums":
+                seen["sums"] = args[3].clone()
+                args[2].zero_()
+            return 0
+        C.call = fake_call
+        H, W = 2048 + 150, 1024 + 490
+        raw = torch.zeros((1, H, W), dtype=torch.int16)
+        out = I.segment_banded(raw, m, dp, 1024, radius=96, tile_batch=4)
+        Hp, Wp = H + (16 - H % 16) % 16, W + (16 - W % 16) % 16
+        bands = I.band_plan(Hp, Wp, 1024, 96, world)
+        ok_mask = None
+        if rank == 0:
+            want = np.zeros((Hp, Wp), dtype=np.uint8)
+            for r, b in enumerate(bands):
+                want[b["zy0"]:b["zy1"]] = r + 1
+            ok_mask = bool(np.array_equal(out.numpy(), want[:H, :W]))
+        q.put((rank, out is not None, ok_mask, seen["sums"].tolist()))
+    finally:
+        dp.shutdown()
+
+
+@pytest.mark.timeout(300)
+def test_banded_inference_world3_gloo():
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_banded_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, has_out, ok_mask, sums in res:
+        assert has_out == (rank == 0)
+        if rank == 0:
+            assert ok_mask, "bands assembled on rank 0 do not tile the image by owner"
+        assert sums == [[6.0, 60.0]]             # 1 + 2 + 3 and 10 + 20 + 30: every rank normalises with the GLOBAL statistics
