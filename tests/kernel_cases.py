@@ -712,7 +712,7 @@ def case_wgrad_folded(C0=64, C1=0, Cout=64, N=2, H=24, W=40, seed=32, identity0=
     dw_ref, _ = ON.conv_wgrad(a * s + t, dz, 3)
     r = dict(e_sdz=rel_err(sdz.cpu().numpy(), ON.border_sums(dz).reshape(9, Cout)),
              e_dw=rel_err(dw.cpu().numpy().reshape(Cout, 9, Cin), pack_conv(dw_ref)))
-    r["ok"] = bool(r["e_sdz"] < 1e-5 and r["e_dw"] < 1e-4)
+    r["ok"] = bool(r["e_sdz"] < 1e-5 and r["e_dw"] < 1e-3)
     return r
 
 
