@@ -18,6 +18,7 @@ def all_cases():
     d.update(G.CASES)
     d.update(K.PENDING_CASES)          # written but not yet run on a B200: only selected by `--pending` or by name
     d.update(G.PENDING_CASES)
+    d.update(G.PROBE_CASES)           # report-only measurements: only selected by `--probe` or by name
     return d
 
 
@@ -38,8 +39,11 @@ if __name__ == "__main__":
     import kernel_cases as K
     pending = dict(K.PENDING_CASES)
     pending.update(G.PENDING_CASES)
+    pending.update(G.PROBE_CASES)
     if pat == "--pending":
-        pat = ",".join(pending)
+        pat = ",".join(k for k in pending if k not in G.PROBE_CASES)
+    elif pat == "--probe":
+        pat = ",".join(G.PROBE_CASES)
     elif not pat:
         cases = {k: v for k, v in cases.items() if k not in pending}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
@@ -49,7 +53,7 @@ if __name__ == "__main__":
             continue
         t0 = time.time()
         try:
-            p = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=300)
+            p = subprocess.run([sys.executable, __file__, "--one", name], capture_output=True, text=True, timeout=int(os.environ.get("UB_CASE_TIMEOUT", "300")))
             res = None
             for line in p.stdout.splitlines():
                 if line.startswith("RESULT "):
@@ -61,7 +65,7 @@ if __name__ == "__main__":
         res["secs"] = round(time.time() - t0, 1)
         report[name] = res
         print(("PASS " if res.get("ok") else "FAIL ") + name + " " + json.dumps(res)[:600], flush=True)
-        with open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w") as f:
+        with open(os.path.join(ROOT, "gpurun_out", os.environ.get("UB_PROBE_OUT", "probe.json")), "w") as f:
             json.dump(report, f, indent=1)
     nfail = sum(1 for r in report.values() if not r.get("ok"))
     print(f"{len(report) - nfail}/{len(report)} cases passed")

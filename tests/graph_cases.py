@@ -43,6 +43,12 @@ TOL = {"bf16": dict(softmax=1e-2, loss=1e-2, grad=1e-2, stat=1e-2, uncond=0.25, 
        "fp32": dict(softmax=1e-4, loss=1e-4, grad=1e-4, stat=1e-4, uncond=0.25, agree=0.9995)}
 
 
+# bf16 product path, one training step at Keras-initial weights, shapes with >= 512 BatchNorm samples per channel everywhere
+# (2 x 1 x 256 x 256 and larger): absolute bounds against the fp64 oracle.  Measured on B200 (profiles/r02_parity.md); the oracle's
+# own bf16-storage emulation sits at logits 0.095, softmax rms 0.026, gradients 0.05-0.09 relative L2 per kernel (conditioned).
+BF16_BOUNDS_256 = dict(logits=0.25, sm_rms=0.05, stat=0.02, grad_l2=0.15, grad_l2_worst=0.2, agree=0.95)
+
+
 def rel(got, ref, floor=0.0):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
@@ -86,14 +92,29 @@ def oracle_pattern(taps, dmt):
     return relu, pool
 
 
-def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None):
+def cuda_logits(m, N, H, W):
+    """what the Softmax layer consumes (UNet/model.py:136-142): BatchNorm (batch statistics of the last training forward) of the
+    ReLU'd 1x1 conv, rebuilt from the head's saved fp32 activation"""
+    L = m.layers["head"]
+    K = m.number_classes
+    a = m._b("a:head")[:N * H * W * K].view(N, H, W, K).double()
+    o = L.off_stat
+    mean, rstd = m.mean[o:o + K].double(), m.rstd[o:o + K].double()
+    gamma, beta = m.P[L.off_gamma:L.off_gamma + K].double(), m.P[L.off_beta:L.off_beta + K].double()
+    return ((a - mean) * rstd * gamma + beta).cpu().numpy()
+
+
+def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=False, absolute=None, floor=False):
     """one training step: softmax / loss / accuracy / BN moving statistics vs the oracle; all 92 gradients vs the
-    oracle conditioned on the CUDA path's activation pattern"""
+    oracle conditioned on the CUDA path's activation pattern.  learn: image and labels are correlated (the oracle's
+    synthetic_batch, the shape of bench.py's workload) instead of independent noise"""
     from unetb200.model import UNet
     tol = TOL[precision]
     gb = gb or N
     p = O.init_params(C, K, seed=seed, base=64, randomize_affine=True)
     x, lab, dm = make_inputs(N, C, H, W, K, seed)
+    if learn:
+        x, lab = O.synthetic_batch(N, C, H, W, K, seed=seed)
     oh = np.eye(K, dtype=np.int32)[lab]
     m = UNet(K, gb, C, learning_rate=1e-3, precision=precision, seed=0)
     m.load_oracle_params({k: v.numpy() for k, v in p.items()})
@@ -112,6 +133,7 @@ def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None):
 
     r = {}
     r["e_softmax"] = rel(sm, ref["softmax"].numpy())
+    r["e_logits"] = rel(cuda_logits(m, N, H, W), ref["logits"].numpy())
     r["argmax_agree"] = float((sm.argmax(-1) == ref["softmax"].numpy().argmax(-1)).mean())
     r["e_loss"] = abs(float(met[0]) - float(ref["loss"])) / abs(float(ref["loss"]))
     r["e_acc"] = abs(float(met[1]) - float(ref["acc"]))
@@ -136,41 +158,67 @@ def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None):
                        and r["e_grad"] < tol["grad"] and r["e_grad_uncond"] < tol["uncond"] and r["argmax_agree"] >= tol["agree"]
                        and r["e_acc"] < 0.01 and r["e_loss_cond"] < 1e-3)
         return r
-    # ---- bf16: noise-floor criterion against the bf16-storage emulation of the oracle (module docstring)
+    # ---- bf16: per-tensor relative L2 against the fp64 oracle, conditioned and unconditioned
+    l2 = lambda a, b: float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+    rms = lambda a, b: float(np.sqrt(np.mean((np.asarray(a, dtype=np.float64) - b) ** 2)))
+    sm64 = ref["softmax"].numpy()
+    r["sm_rms"] = rms(sm, sm64)
+    kern = [n for n in refc["grads"] if not (n.startswith("up") and n.endswith("/bias"))]
+    l2c = {n: l2(grads[n], refc["grads"][n].numpy()) for n in kern}
+    l2u = {n: l2(grads[n], ref["grads"][n].numpy()) for n in kern}
+    num_g = sum(float(np.sum((grads[n] - refc["grads"][n].numpy()) ** 2)) for n in kern)
+    den_g = sum(float(np.sum(refc["grads"][n].numpy() ** 2)) for n in kern)
+    r["grad_l2"] = float(np.sqrt(num_g / den_g))
+    wl = max((n for n in kern if n.endswith("/kernel")), key=lambda n: l2c[n])
+    r["grad_l2_worst_kernel"], r["grad_l2_worst_kernel_name"] = l2c[wl], wl
+    r["grad_l2_uncond_worst_kernel"] = max(l2u[n] for n in kern if n.endswith("/kernel"))
+    zb = max(rel(grads[f"up{l}/bias"], 0 * grads[f"up{l}/bias"], float(np.abs(refc["grads"][f"up{l}/kernel"].numpy()).max())) for l in (1, 2, 3, 4))
+    r["e_zero_bias"] = zb
+    if os.environ.get("UB_VERBOSE"):
+        r["grad_l2_cond_per"] = {k: float(f"{v:.3g}") for k, v in l2c.items() if k.endswith("kernel")}
+        r["grad_l2_uncond_per"] = {k: float(f"{v:.3g}") for k, v in l2u.items() if k.endswith("kernel")}
+    base_ok = bool(r["e_loss"] < tol["loss"] and r["e_acc"] < 0.01 and r["e_loss_cond"] < 1e-3 and zb < 1e-2)
+    if absolute is not None:
+        # fixed bounds measured on B200 at a shape whose BatchNorm statistics are well conditioned (profiles/r02_parity.md):
+        # north_star's 1e-2 holds for the loss; softmax / logits / gradients sit at the bf16-storage floor of this graph
+        r["bounds"] = absolute
+        r["ok"] = bool(base_ok and r["e_logits"] <= absolute["logits"] and r["sm_rms"] <= absolute["sm_rms"]
+                       and r["e_stat"] <= absolute["stat"] and r["grad_l2"] <= absolute["grad_l2"]
+                       and r["grad_l2_worst_kernel"] <= absolute["grad_l2_worst"] and r["argmax_agree"] >= absolute["agree"])
+        if not floor:
+            return r
+    # ---- noise-floor criterion against the bf16-storage emulation of the oracle (module docstring)
     taps = {}
     emu = O.train_step_grads(p, xt, oht, gb, dmt, taps=taps, storage="bf16")
     relu_e, pool_e = oracle_pattern(taps, dmt)
     refe = O.train_step_grads(p, xt, oht, gb, dmt, relu_masks=relu_e, pool_idx=pool_e)
-    sm64, sme = ref["softmax"].numpy(), emu["softmax"].numpy()
-    rms = lambda a, b: float(np.sqrt(np.mean((np.asarray(a, dtype=np.float64) - b) ** 2)))
-    r["sm_rms"], r["sm_rms_floor"] = rms(sm, sm64), rms(sme, sm64)
+    sme = emu["softmax"].numpy()
+    r["sm_rms_floor"] = rms(sme, sm64)
     r["sm_max_floor"] = rel(sme, sm64)
+    r["logits_floor"] = rel(emu["logits"].numpy(), ref["logits"].numpy())
     r["stat_floor"] = max(rel(emu["new_stats"][k].numpy(), v.numpy()) for k, v in ref["new_stats"].items())
     r["agree_floor"] = float((sme.argmax(-1) == sm64.argmax(-1)).mean())
-    l2 = lambda a, b: float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-300))
-    worst_ratio, worst_name, num_g, num_e, den_g, den_e = 0.0, "", 0.0, 0.0, 0.0, 0.0
+    worst_ratio, worst_name, num_e, den_e = 0.0, "", 0.0, 0.0
     per = {}
-    for n in refc["grads"]:
-        if n.startswith("up") and n.endswith("/bias"):
-            continue
-        bg, be = refc["grads"][n].numpy(), refe["grads"][n].numpy()
-        eg, ee = l2(grads[n], bg), l2(emu["grads"][n].numpy(), be)
-        per[n] = (eg, ee)
-        num_g += float(np.sum((grads[n] - bg) ** 2)); den_g += float(np.sum(bg ** 2))
+    for n in kern:
+        be = refe["grads"][n].numpy()
+        ee = l2(emu["grads"][n].numpy(), be)
+        per[n] = (l2c[n], ee)
         num_e += float(np.sum((emu["grads"][n].numpy() - be) ** 2)); den_e += float(np.sum(be ** 2))
-        ratio = eg / (ee + 2e-3)
+        ratio = l2c[n] / (ee + 2e-3)
         if ratio > worst_ratio:
             worst_ratio, worst_name = ratio, n
-    r["grad_l2"], r["grad_l2_floor"] = float(np.sqrt(num_g / den_g)), float(np.sqrt(num_e / den_e))
+    r["grad_l2_floor"] = float(np.sqrt(num_e / den_e))
+    r["grad_l2_floor_worst_kernel"] = max(v[1] for k, v in per.items() if k.endswith("/kernel"))
     r["grad_worst_ratio"], r["grad_worst_ratio_name"] = worst_ratio, worst_name
-    zb = max(rel(grads[f"up{l}/bias"], 0 * grads[f"up{l}/bias"], float(np.abs(refc["grads"][f"up{l}/kernel"].numpy()).max())) for l in (1, 2, 3, 4))
-    r["e_zero_bias"] = zb
     if os.environ.get("UB_VERBOSE"):
         r["grad_l2_per"] = {k: (float(f"{a:.3g}"), float(f"{b:.3g}")) for k, (a, b) in per.items() if k.endswith("kernel")}
-    r["ok"] = bool(r["e_loss"] < tol["loss"] and r["e_acc"] < 0.01 and r["e_loss_cond"] < 1e-3
+    if absolute is not None:
+        return r
+    r["ok"] = bool(base_ok
                    and r["sm_rms"] <= 1.5 * r["sm_rms_floor"] + 1e-4 and r["e_softmax"] <= 2.0 * r["sm_max_floor"] + 1e-3
                    and r["e_stat"] <= 2.0 * r["stat_floor"] + 1e-3 and r["argmax_agree"] >= r["agree_floor"] - 0.02
-                   and r["grad_l2"] <= 1.25 * r["grad_l2_floor"] + 1e-3 and worst_ratio <= 1.6 and zb < 1e-2)
+                   and r["grad_l2"] <= 1.25 * r["grad_l2_floor"] + 1e-3 and worst_ratio <= 1.6)
     return r
 
 
@@ -204,6 +252,79 @@ def case_curve(precision="bf16", N=4, C=1, H=64, W=64, K=2, steps=100, lr=1e-3, 
     out["ok"] = bool(out["dev_first10"] < 2e-2 and out["dev_mean"] < 5e-2 and out["dev_max"] < 0.25 and ref[-1] < 0.8 * ref[0]
                      and got[-1] < 0.8 * got[0])
     return out
+
+
+def learnable_batch(N, C, H, W, rng, K=2):
+    """an image whose label can be learnt from it: label = argmax of smooth random fields (K = 2: one field thresholded at 0),
+    image channels = a mix of the fields plus noise"""
+    from scipy.ndimage import gaussian_filter
+    f = gaussian_filter(rng.normal(size=(N, K - 1 if K == 2 else K, H, W)), sigma=(0, 0, 3, 3))
+    f = f / f.std()
+    lab = (f[:, 0] > 0).astype(np.uint8) if K == 2 else f.argmax(1).astype(np.uint8)
+    mix = rng.normal(size=(C, f.shape[1]))
+    x = (np.einsum("ck,nkhw->nchw", mix, f) * 2.0 + rng.normal(size=(N, C, H, W)) * 0.5).astype(np.float32)
+    return x, lab
+
+
+def case_trained(C=1, K=2, steps=300, N=8, S=128, seed=51, n_eval=2, s_eval=256, bounds=None):
+    """The regime the reference is used in: a TRAINED network.  `steps` optimisation steps of the bf16 product path on a
+    learnable synthetic task, then -- at those weights and moving statistics, exported to the fp64 oracle --
+      (1) inference (training=False) on fresh images: softmax / logits max error and per-pixel argmax agreement
+          (north_star: >= 99.9 %), UNet/inference.py:105-107;
+      (2) one more training step (dropout off): loss, logits, and all gradients, conditioned and unconditioned."""
+    from unetb200.model import UNet
+    rng = np.random.default_rng(seed)
+    m = UNet(K, N, C, learning_rate=1e-3, precision="bf16", seed=seed)
+    losses = []
+    for s in range(steps):
+        x, lab = learnable_batch(N, C, S, S, rng, K)
+        loss = m.train_step(torch.tensor(x), torch.tensor(lab))      # a view of the metrics buffer: read it now or never
+        if s >= steps - 10:
+            losses.append(float(loss.item()))
+    p = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in m.export_params().items()}
+    r = dict(train_loss_last10=float(np.mean(losses)))
+    # (1) inference
+    x, lab = learnable_batch(n_eval, C, s_eval, s_eval, rng, K)
+    sm = m.get_keras_model()(x)
+    ref = O.test_step(p, torch.tensor(x, dtype=torch.float64), torch.tensor(np.eye(K, dtype=np.int32)[lab]), n_eval)
+    sm64 = ref["softmax"].numpy()
+    r["infer_e_softmax"] = float(np.abs(sm - sm64).max())
+    r["infer_sm_rms"] = float(np.sqrt(np.mean((sm - sm64) ** 2)))
+    r["infer_argmax_agree"] = float((sm.argmax(-1) == sm64.argmax(-1)).mean())
+    r["infer_acc_ref"] = float(ref["acc"])
+    loss = float(m.test_step((torch.tensor(x), torch.tensor(lab))).cpu()) * (m.global_batch_size / n_eval)
+    r["infer_e_loss"] = abs(loss - float(ref["loss"])) / float(ref["loss"])
+    # (2) a training step at the trained weights
+    m2 = UNet(K, n_eval, C, learning_rate=1e-3, precision="bf16", seed=0)
+    m2.load_oracle_params({k: v.numpy() for k, v in p.items()})
+    oh = np.eye(K, dtype=np.int32)[lab]
+    m2.train_step(torch.tensor(x), torch.tensor(lab), dropout_masks={}, apply_update=False, keep_softmax=True)
+    torch.cuda.synchronize()
+    grads = m2.export_grads()
+    relu, pool = m2.export_activation_pattern(n_eval, s_eval, s_eval)
+    xt, oht = torch.tensor(x, dtype=torch.float64), torch.tensor(oh)
+    tr = O.train_step_grads(p, xt, oht, n_eval)
+    trc = O.train_step_grads(p, xt, oht, n_eval, relu_masks=relu, pool_idx=pool)
+    smt = m2._b("softmax")[:n_eval * s_eval * s_eval * K].view(n_eval, s_eval, s_eval, K).cpu().numpy()
+    r["train_e_loss"] = abs(float(m2.metrics[0]) - float(tr["loss"])) / float(tr["loss"])
+    r["train_e_logits"] = rel(cuda_logits(m2, n_eval, s_eval, s_eval), tr["logits"].numpy())
+    r["train_e_softmax"] = float(np.abs(smt - tr["softmax"].numpy()).max())
+    r["train_argmax_agree"] = float((smt.argmax(-1) == tr["softmax"].numpy().argmax(-1)).mean())
+    l2 = lambda a, b: float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-300))
+    kern = [n for n in tr["grads"] if n.endswith("/kernel")]
+    l2c = {n: l2(grads[n], trc["grads"][n].numpy()) for n in kern}
+    l2u = {n: l2(grads[n], tr["grads"][n].numpy()) for n in kern}
+    mxc = {n: rel(grads[n], trc["grads"][n].numpy()) for n in kern}
+    r["grad_l2_cond_worst"], r["grad_l2_uncond_worst"], r["grad_max_cond_worst"] = max(l2c.values()), max(l2u.values()), max(mxc.values())
+    if os.environ.get("UB_VERBOSE"):
+        r["grad_l2_cond_per"] = {k: float(f"{v:.3g}") for k, v in l2c.items()}
+        r["grad_l2_uncond_per"] = {k: float(f"{v:.3g}") for k, v in l2u.items()}
+    b = bounds or dict(agree=0.999, infer_softmax=0.1, grad_l2=0.2)
+    r["bounds"] = b
+    r["ok"] = bool(r["infer_argmax_agree"] >= b["agree"] and r["infer_e_softmax"] <= b["infer_softmax"] and r["infer_e_loss"] < 1e-2
+                   and r["train_e_loss"] < 1e-2 and r["grad_l2_cond_worst"] <= b["grad_l2"]
+                   and r["train_loss_last10"] < 0.5)
+    return r
 
 
 def load_gold(name):
@@ -545,6 +666,17 @@ PENDING_CASES = {
     "fold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8)),
     "fold_golden_c1_k2_bf16": _with_fold(lambda: case_golden("graph_c1_k2", "bf16")),
     "fold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=200)),
+}
+
+
+# report-only measurements (tests/gpu_probe.py --probe): the bf16 product path against fp64 and against the oracle's
+# bf16-storage emulation at shapes whose BatchNorm statistics are well conditioned; results go to profiles/r02_parity.md
+PROBE_CASES = {
+    "probe_smoke_shape": lambda: case_live("bf16", N=2, C=1, H=64, W=48, K=2, seed=3, floor=True),
+    "probe_256_n2": lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, floor=True),
+    "probe_256_n4_learn": lambda: case_live("bf16", N=4, C=1, H=256, W=256, K=2, seed=4, learn=True, floor=True),
+    "probe_trained": lambda: case_trained(),
+    "probe_fold_256_n2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, floor=True)),
 }
 
 

@@ -788,6 +788,125 @@ def case_published_known_answers():
     return r
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# conv3x3 at the layer shapes of the benchmark (config 2: 16 x 512 x 512 input): the persistent tile loops, the 256-pixel
+# super-tiles at full width and the weight-gradient split counts of the shapes bench.py runs.  The numpy oracle cannot finish
+# these sizes in seconds, so it is evaluated on a SAMPLE of output pixels / weight rows (borders, tile seams and random
+# positions), and the full tensors are covered by size-independent properties: the BatchNorm statistics partials must equal the
+# column sums of the stored output (every tile counted exactly once), nothing is left unwritten (NaN pre-fill).
+def _sample_pixels(rng, N, H, W, count=3000):
+    n = rng.integers(0, N, count)
+    h = rng.integers(0, H, count)
+    w = rng.integers(0, W, count)
+    # image corners / edges and the seams of the 16 x 16 super-tiles
+    edge_h = np.array([0, 0, H - 1, H - 1, 0, H - 1, 15, 16, 17, H // 2])
+    edge_w = np.array([0, W - 1, 0, W - 1, W // 2, 1, 15, 16, W - 2, 7])
+    k = len(edge_h)
+    h[:k], w[:k] = edge_h % H, edge_w % W
+    h[k:2 * k], w[k:2 * k], n[k:2 * k] = edge_h % H, edge_w % W, N - 1
+    return n, h, w
+
+
+def _gather_taps(x, n, h, w, flip=False):
+    """x float [N,H,W,C] -> [S, 9, C] values at (h + dh - 1, w + dw - 1) (flip: (h - dh + 1, w - dw + 1)), zero outside"""
+    N, H, W, C = x.shape
+    out = np.zeros((len(n), 9, C), dtype=np.float64)
+    for t in range(9):
+        dh, dw = t // 3 - 1, t % 3 - 1
+        hh, ww = (h - dh, w - dw) if flip else (h + dh, w + dw)
+        ok = (hh >= 0) & (hh < H) & (ww >= 0) & (ww < W)
+        out[ok, t] = x[n[ok], hh[ok], ww[ok]]
+    return out
+
+
+def case_conv3x3_layer(C0, C1, Cout, N, H, W, seed=30, n_ci=6):
+    """fwd (+ statistics), dgrad (the fused-reduction variant where the step uses it) and wgrad of one conv layer at its config-2 shape"""
+    C = _C()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    Cin = C0 + C1
+    r = {}
+    x = torch.randn((N, H, W, Cin), generator=g, device="cuda", dtype=torch.float32).clamp_(min=-0.5).to(torch.bfloat16)   # ReLU-ish, non-zero mean
+    dz = torch.randn((N, H, W, Cout), generator=g, device="cuda", dtype=torch.float32).to(torch.bfloat16)
+    w = bf16_round(rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin))
+    b = rng.normal(size=(Cout,)).astype(np.float32)
+    x0 = x[..., :C0].contiguous()
+    x1 = x[..., C0:].contiguous() if C1 else None
+    xh = x.float().cpu().numpy()
+    dzh = dz.float().cpu().numpy()
+    n, h, ww_ = _sample_pixels(rng, N, H, W)
+    # ---- forward
+    out = torch.full((N, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    partial = torch.empty(C.UB_STATS_ROWS * 2 * Cout, dtype=torch.float32, device="cuda")
+    C.call("ub_conv3x3_fwd", x0, C0, x1, C1, dev(pack_conv(w), torch.bfloat16), dev(b, torch.float32), out, partial, N, H, W, Cout, 1, stream())
+    torch.cuda.synchronize()
+    ref = np.maximum(np.einsum("stc,tco->so", _gather_taps(xh, n, h, ww_), w.reshape(9, Cin, Cout)) + b.astype(np.float64), 0)
+    got = out[torch.as_tensor(n, device="cuda"), torch.as_tensor(h, device="cuda"), torch.as_tensor(ww_, device="cuda")].double().cpu().numpy()
+    r["fwd_err"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+    r["fwd_finite"] = bool(torch.isfinite(out).all())
+    s, q = stats_from_partial(partial, Cout)
+    od = out.double()
+    r["fwd_err_sum"] = rel_err(s, od.sum((0, 1, 2)).cpu().numpy())
+    r["fwd_err_sq"] = rel_err(q, (od * od).sum((0, 1, 2)).cpu().numpy())
+    del od, out
+    # ---- dgrad (weights scaled for the transposed contraction)
+    wd = bf16_round(w * np.sqrt(Cin / Cout))
+    wt = torch.empty(Cin * 9 * Cout, dtype=torch.bfloat16, device="cuda")
+    C.call("ub_transpose_pack", dev(pack_conv(wd), torch.float32), wt, Cout, 9, Cin, 1, 0, C.UB_BF16, stream())
+    dx0 = torch.full((N, H, W, C0), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dx1 = torch.full((N, H, W, C1), float("nan"), dtype=torch.bfloat16, device="cuda") if C1 else None
+    fused = Cout >= 128                               # unetb200.model.UNet._conv_bwd: where the step fuses the BatchNorm-backward sums
+    if fused:
+        Cr = C1 if C1 else C0
+        a = x1 if C1 else x0                          # stands in for the saved activation of the tensor being differentiated
+        mean = torch.full((Cr,), 0.3, device="cuda")
+        rstd = torch.linspace(0.5, 2.0, Cr, device="cuda")
+        red = torch.full((C.UB_STATS_ROWS * 2 * Cr,), float("nan"), dtype=torch.float32, device="cuda")
+        C.call("ub_conv3x3_dgrad_bnred", dz, Cout, wt, dx0, C0, dx1, C1, N, H, W, a, mean, rstd, red, stream())
+    else:
+        C.call("ub_conv3x3_dgrad", dz, Cout, wt, dx0, C0, dx1, C1, N, H, W, stream())
+    torch.cuda.synchronize()
+    ref = np.einsum("sto,tco->sc", _gather_taps(dzh, n, h, ww_, flip=True), wd.reshape(9, Cin, Cout))
+    idx = (torch.as_tensor(n, device="cuda"), torch.as_tensor(h, device="cuda"), torch.as_tensor(ww_, device="cuda"))
+    got = dx0[idx].double().cpu().numpy()
+    if C1:
+        got = np.concatenate([got, dx1[idx].double().cpu().numpy()], -1)
+    r["dgrad_err"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+    r["dgrad_finite"] = bool(torch.isfinite(dx0).all() and (dx1 is None or torch.isfinite(dx1).all()))
+    if fused:
+        dy = (dx1 if C1 else dx0).double()
+        s, q = stats_from_partial(red, Cr)
+        r["red_err_sum"] = rel_err(s, dy.sum((0, 1, 2)).cpu().numpy())
+        r["red_err_q"] = rel_err(q, ((dy * (a.double() - mean.double())).sum((0, 1, 2)) * rstd.double()).cpu().numpy())
+        del dy
+    del dx0, dx1
+    # ---- wgrad: every tap and output channel of a few input channels (first / last of each source, random)
+    nbytes = C.lib.ub_conv3x3_wgrad_workspace_bytes(C0, C1, Cout, N, H, W)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    dw = torch.full((Cout, 9, Cin), float("nan"), dtype=torch.float32, device="cuda")
+    C.call("ub_conv3x3_wgrad", x0, C0, x1, C1, dz, Cout, dw, ws, nbytes, N, H, W, stream())
+    torch.cuda.synchronize()
+    cis = sorted(set([0, C0 - 1, Cin - 1, C0 % Cin] + [int(v) for v in rng.integers(0, Cin, n_ci)]))
+    ref = np.zeros((9, len(cis), Cout))
+    for i in range(N):
+        xs = np.zeros((9, len(cis), H, W))
+        xi = xh[i][..., cis].astype(np.float64).transpose(2, 0, 1)        # [ci, H, W]
+        for t in range(9):
+            dh, dw_ = t // 3 - 1, t % 3 - 1
+            hs, he, ws_, we = max(0, -dh), min(H, H - dh), max(0, -dw_), min(W, W - dw_)
+            xs[t, :, hs:he, ws_:we] = xi[:, hs + dh:he + dh, ws_ + dw_:we + dw_]
+        ref += (xs.reshape(9 * len(cis), H * W) @ dzh[i].reshape(H * W, Cout).astype(np.float64)).reshape(9, len(cis), Cout)
+    got = dw.double().cpu().numpy()[:, :, cis].transpose(1, 2, 0)          # [tap, ci, co]
+    r["wgrad_err"] = float(np.abs(got - ref).max() / np.abs(ref).max())
+    r["wgrad_finite"] = bool(torch.isfinite(dw).all())
+    r["ws_bytes"] = int(nbytes)
+    r["ok"] = bool(r["fwd_err"] < 1e-2 and r["fwd_err_sum"] < 1e-4 and r["fwd_err_sq"] < 1e-4 and r["fwd_finite"]
+                   and r["dgrad_err"] < 1e-2 and r["dgrad_finite"] and r.get("red_err_sum", 0) < 1e-4 and r.get("red_err_q", 0) < 1e-4
+                   and r["wgrad_err"] < 1e-3 and r["wgrad_finite"])
+    return r
+
+
 PENDING_CASES = {
     "published_known_answers": case_published_known_answers,
     "head_fold_k2": case_head_fold,
@@ -805,6 +924,13 @@ PENDING_CASES = {
 
 
 CASES = {
+    # tcgen05 implicit GEMMs at the benchmark's layer shapes, sampled oracle + full-tensor checksums
+    "layer_enc1b_16x512": lambda: case_conv3x3_layer(64, 0, 64, 16, 512, 512),
+    "layer_dec1a_16x512": lambda: case_conv3x3_layer(64, 64, 64, 16, 512, 512, seed=31),
+    "layer_enc2a_16x256": lambda: case_conv3x3_layer(64, 0, 128, 16, 256, 256, seed=32),
+    "layer_enc3b_16x128": lambda: case_conv3x3_layer(256, 0, 256, 16, 128, 128, seed=33),
+    "layer_dec4a_16x64": lambda: case_conv3x3_layer(512, 512, 512, 16, 64, 64, seed=34),
+    "layer_botb_16x32": lambda: case_conv3x3_layer(1024, 0, 1024, 16, 32, 32, seed=35),
     # tcgen05 implicit GEMMs
     "conv_fwd_64_64": lambda: case_conv3x3_fwd(64, 0, 64),
     "conv_fwd_128_128": lambda: case_conv3x3_fwd(128, 0, 128),
