@@ -97,6 +97,29 @@ class ClockSampler:
         self._t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        # NVML in-process (a sample every ~5 ms, so that even a 0.5 s timed region carries dozens); nvidia-smi as the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates in PCI order and ignores CUDA_VISIBLE_DEVICES: map the CUDA ordinal through the visible list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = [pynvml.nvmlClocksEventReasonHwSlowdown, pynvml.nvmlClocksEventReasonHwThermalSlowdown,
+                    pynvml.nvmlClocksEventReasonSwThermalSlowdown, pynvml.nvmlClocksEventReasonSwPowerCap]
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append([str(sm), str(mx)] + ["Active" if rs & b else "Not Active" for b in bits])
+                self._stop.wait(0.005)
+            return
+        except Exception:
+            pass
         while not self._stop.is_set():
             try:
                 o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -308,7 +331,11 @@ def run_cuda(args):
         model.profile = None
         if args.layers:
             write_layer_table(args.layers, layer_ms)
+    dp_check = None
     if dp:
+        dp.barrier()
+        # data-parallel numerics on the live ranks: all-reduced G == sum of per-rank gradients, parameters identical after Adam
+        dp_check = dp.verify_step(model, dx[0], dl[0])
         dp.barrier()
 
     def finish():
@@ -319,9 +346,11 @@ def run_cuda(args):
         gc.collect()
         torch.cuda.synchronize(dev)
         if dp:
-            dp.barrier()
+            clean = dp.shutdown(model)
+            sys.stderr.write(f"rank {rank}: process group teardown {'clean' if clean else 'TIMED OUT'}\n")
             sys.stderr.flush()
-            os._exit(0)
+            if not clean:
+                os._exit(0)
 
     if rank != 0:
         finish()
@@ -368,6 +397,7 @@ def run_cuda(args):
         "cpu_baseline": cpu,
         "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(kern_ms.items(), key=lambda kv: -kv[1])},
         "final_loss": final_loss,
+        "dp_check": dp_check,
     }
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     finish()

@@ -130,13 +130,99 @@ class DataParallel:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t
 
-    def average_moving_stats(self, model):
-        """ON_READ / MEAN aggregation of the BN moving statistics"""
-        if self.world_size > 1:
+    def moving_stats_averaged(self, model):
+        """ON_READ / MEAN aggregation of the BN moving statistics: a context in which model.MM / model.MV hold
+        the mean over replicas (for a checkpoint or an evaluation); each replica's own statistics are put back on exit, as
+        reading a tf ON_READ variable leaves the per-replica values untouched."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            if self.world_size == 1:
+                yield
+                return
+            keep = (model.MM.clone(), model.MV.clone())
             for t in (model.MM, model.MV):
                 dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 t.div_(self.world_size)
             model._inference_stale = True
+            try:
+                yield
+            finally:
+                model.MM.copy_(keep[0])
+                model.MV.copy_(keep[1])
+                model._inference_stale = True
+        return ctx()
+
+    def verify_step(self, model, images, labels):
+        """Numerical self-check of the data-parallel step (UNet/model.py:223, :230-235) on live ranks: runs the public
+        train_step (bucketed all-reduce overlapped with backward; CUDA-graph replay when enabled), then repeats the same step
+        on each rank WITHOUT the all-reduce from the same state and with the same dropout masks, all-gathers those local
+        gradients and compares their sum with the all-reduced gradient buffer; also checks that the updated parameters are
+        bit-identical on every rank.  The model state is restored afterwards.  Returns a dict (same on all ranks)."""
+        x = model._prep_images(images)
+        N, _, H, W = x.shape
+        lab = model._prep_labels(labels, N, H, W).clone()
+        names = ("P", "M", "V", "MM", "MV")
+        keep = {a: getattr(model, a).clone() for a in names}
+        sc = model.step_count
+
+        def restore():
+            for a, t in keep.items():
+                getattr(model, a).copy_(t)
+            model.step_count = sc
+            model._weights_changed()
+
+        out = {"world_size": self.world_size}
+        grads = {}
+        for mode in ("graph", "eager"):
+            use_graph = model.use_graph
+            model.use_graph = use_graph and mode == "graph"
+            reps = 3 if mode == "graph" else 1          # first call per shape runs eagerly, the second captures, the third replays
+            for _ in range(reps):
+                restore()
+                model.train_step(x, lab)
+            model.use_graph = use_graph
+            torch.cuda.synchronize()
+            grads[mode] = model.G.clone()
+            p_after = model.P.clone()
+            chk = p_after.view(torch.int32).to(torch.int64).sum().reshape(1)
+            allc = [torch.empty_like(chk) for _ in range(self.world_size)]
+            if self.world_size > 1:
+                dist.all_gather(allc, chk)
+            else:
+                allc = [chk]
+            out[f"params_identical_{mode}"] = bool(all(int(c) == int(allc[0]) for c in allc))
+        # the same step without the collective
+        restore()
+        model.step_count = sc + 1
+        dm = model._make_drop_masks(N, H, W)
+        d, model.dist = model.dist, None
+        try:
+            model._step_body(x, lab, N, H, W, dm, False, False, False)
+        finally:
+            model.dist = d
+        torch.cuda.synchronize()
+        local = model.G.clone()
+        parts = [torch.empty_like(local) for _ in range(self.world_size)]
+        if self.world_size > 1:
+            dist.all_gather(parts, local)
+        else:
+            parts = [local]
+        total = torch.zeros_like(local, dtype=torch.float64)
+        for t in parts:
+            total += t.double()
+        den = float(total.norm())
+        for mode, g in grads.items():
+            out[f"grad_rel_l2_{mode}"] = float((g.double() - total).norm()) / max(den, 1e-300)
+            out[f"grad_max_abs_{mode}"] = float((g.double() - total).abs().max())
+        out["grad_max_ref"] = float(total.abs().max())
+        out["graph_vs_eager_bit_identical"] = bool(torch.equal(grads["graph"], grads["eager"]))
+        out["local_grad_norms"] = [float(t.double().norm()) for t in parts]
+        restore()
+        out["ok"] = bool(out["grad_rel_l2_graph"] < 1e-5 and out["grad_rel_l2_eager"] < 1e-5 and out["params_identical_graph"]
+                         and out["params_identical_eager"])
+        return out
 
     def broadcast_params(self, model):
         """replicas start from rank 0's variables, as MirroredStrategy guarantees"""
@@ -149,11 +235,22 @@ class DataParallel:
         if self.world_size > 1:
             dist.barrier()
 
-    def shutdown(self, timeout_s=30.0):
-        """tear the process group down; bounded, because destroying a communicator whose kernels were captured in CUDA graphs
-        has been seen to block (release the graphs first: UNet._graphs.clear())"""
-        if dist.is_initialized():
-            import threading
-            t = threading.Thread(target=dist.destroy_process_group, daemon=True)
-            t.start()
-            t.join(timeout_s)
+    def shutdown(self, model=None, timeout_s=60.0):
+        """tear the process group down in dependency order: the captured step graphs hold NCCL kernels of this communicator, so
+        they go first; then the device is drained, the ranks meet, and the group is destroyed.  A watchdog bounds the destroy
+        (returns False if it had to give up) so that a wedged peer cannot hang a GPU box."""
+        if not dist.is_initialized():
+            return True
+        if model is not None:
+            model._graphs.clear()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        import threading
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(timeout_s)
+        return not t.is_alive()

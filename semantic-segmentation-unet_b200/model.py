@@ -130,6 +130,11 @@ class UNet:
     def _ensure(self, name, numel, dtype):
         t = self._buf.get(name)
         if t is None or t.numel() < numel or t.dtype != dtype:
+            if t is not None and self._graphs:
+                # captured step graphs hold the old pointer: drop them (they are re-captured on the next step of their shape)
+                # before the old allocation can be handed out again
+                torch.cuda.synchronize(self.device)
+                self._graphs.clear()
             t = torch.empty(max(int(numel), 16), dtype=dtype, device=self.device)
             self._buf[name] = t
         return t

@@ -245,11 +245,12 @@ def train_model(output_folder, batch_size, reader_count, train_lmdb_filepath, te
 
             if (len(test_loss) - 1) == int(np.argmin(test_loss)):
                 print('Test loss improved: {}, saving checkpoint'.format(np.min(test_loss)))
-                if strategy is not None:
-                    strategy.average_moving_stats(unet_model)          # ON_READ / MEAN aggregation
-                if is_chief:
-                    os.makedirs(os.path.join(output_folder, 'checkpoint'), exist_ok=True)
-                    unet_model.save_checkpoint(os.path.join(output_folder, 'checkpoint', "ckpt"))
+                import contextlib
+                # ON_READ / MEAN aggregation of the moving statistics for the checkpoint only: replicas keep their own
+                with (strategy.moving_stats_averaged(unet_model) if strategy is not None else contextlib.nullcontext()):
+                    if is_chief:
+                        os.makedirs(os.path.join(output_folder, 'checkpoint'), exist_ok=True)
+                        unet_model.save_checkpoint(os.path.join(output_folder, 'checkpoint', "ckpt"))
 
             print('Best Current Epoch Selection:')
             print('Test Loss:')
@@ -271,12 +272,7 @@ def train_model(output_folder, batch_size, reader_count, train_lmdb_filepath, te
         print('Shutting down test_reader')
         test_reader.shutdown()
         if strategy is not None:
-            try:
-                unet_model._graphs.clear()          # captured NCCL kernels must be released before the communicator
-                torch.cuda.synchronize()
-            except NameError:
-                pass
-            strategy.shutdown()
+            strategy.shutdown(locals().get("unet_model"))
 
 
 def main(argv=None):

@@ -67,10 +67,12 @@ def _worker(rank, world, port, q):
         contiguous = covered[0][0] == 0 and covered[-1][1] == m.n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
         loss = dp.reduce_sum(torch.tensor(float(rank + 1)))
         m.MM.fill_(float(rank))
-        dp.average_moving_stats(m)
+        with dp.moving_stats_averaged(m):
+            mm_avg = float(m.MM[0])
+        mm_after = float(m.MM[0])
         m.P.fill_(float(rank + 5))
         dp.broadcast_params(m)
-        q.put((rank, ok_sum, contiguous, nb, dp.allreduce_calls, float(loss), float(m.MM[0]), float(m.P[0]), m.changed,
+        q.put((rank, ok_sum, contiguous, nb, dp.allreduce_calls, float(loss), (mm_avg, mm_after), float(m.P[0]), m.changed,
                dp.num_replicas_in_sync, bool(torch.equal(mine, others[rank]))))
     finally:
         dp.shutdown()
@@ -101,7 +103,7 @@ def test_bucketed_allreduce_world2_gloo():
         assert ok_sum, "bucketed all-reduce != sum of per-replica gradients"
         assert contiguous and nb >= 2 and calls == nb
         assert loss == 3.0                       # SUM of per-replica losses
-        assert mm == 0.5                         # MEAN of moving statistics
+        assert mm == (0.5, float(rank))          # MEAN of moving statistics while read; each replica's own value afterwards
         assert p0 == 5.0 and changed == 1        # rank 0's variables broadcast
         assert nrep == 2 and same
 
