@@ -37,6 +37,7 @@ extern "C" {
 #define UB_STATS_ROWS 592   /* 148 SMs x 4: rows of every "partial" buffer */
 #define UB_MAX_CLASSES 8    /* number_classes supported by the head kernels */
 #define UB_ZSCORE_BLOCKS 256
+#define UB_BORDER_CHUNKS 64  /* ub_border_sums: scratch = UB_BORDER_CHUNKS * 8 * C floats */
 
 const char* ub_last_error(void);
 int ub_version(void);
@@ -219,7 +220,7 @@ int ub_aug_chanmix(float* x, const double* mix, int N, int C, long long plane, c
  *   2 last); scale_out / shift_out = float[C0+C1] (s, t) for ub_wgrad_fold_fix.
  * ub_conv3x3_fwd_cases: ub_conv3x3_fwd with that bias table (H, W >= 2).
  * ub_border_sums: sdz = float[9][C], sum of dz over the output pixels whose tap neighbour is inside the image; total = float[C]
- *   sum of dz over all pixels (the bias gradient); scratch = 8 * C floats.
+ *   sum of dz over all pixels (the bias gradient); scratch = UB_BORDER_CHUNKS * 8 * C floats.
  * ub_wgrad_fold_fix: dw [Cout][9][Cin] (weight gradient computed with x = a) <- scale[ci] * dw + shift[ci] * sdz[tap][co]. */
 int ub_fold_conv3_weights(const float* w, int Cout, int C0, const float* mean0, const float* rstd0, const float* gamma0, const float* beta0,
                           int C1, const float* mean1, const float* rstd1, const float* gamma1, const float* beta1, const float* bias,

@@ -7,9 +7,8 @@
 //   ub_wgrad_fold_fix      dW = s[ci] * dW_a + t[ci] * Sdz[tap][co]      (dW_a = weight gradient computed on `a`)
 // The algebra is proven in fp64 in oracle/unet_numpy.py (fold_weights, border_case_bias, border_sums, conv_wgrad_folded).
 //   ub_fold_head_weights / ub_head_wgrad_fold_fix   the same for the 1x1 head (no padding: a single bias vector)
-// STATUS: compiled, wired into the training step behind UNet.fold_bn (default False) and covered by parity cases
-// (tests/kernel_cases.py and tests/graph_cases.py PENDING_CASES), but not yet run on a B200 -- the GPU budget of the round
-// ended first.
+// Parity: tests/kernel_cases.py (fold_weights_*, conv_fwd_folded_*, wgrad_folded_*, head_fold_*) and the whole-graph cases under
+// UB_FOLD_BN=1 (tests/graph_cases.py fold_*), green on B200.
 #include "common.cuh"
 
 namespace {
@@ -82,16 +81,21 @@ __global__ void __launch_bounds__(TPB) fold_conv3_kernel(const float* __restrict
   }
 }
 
-// raw[s][c]: s = 0 top row, 1 bottom row, 2 left column, 3 right column, 4..7 corners (tl, tr, bl, br); NHWC dz
+// raw[chunk][s][c]: s = 0 top row, 1 bottom row, 2 left column, 3 right column, 4..7 corners (tl, tr, bl, br); NHWC dz.
+// The strips hold N * (2 W + 2 H) pixels of C channels: a few MB, but spread over the whole tensor -- the work is split over
+// UB_BORDER_CHUNKS blocks per strip so that enough independent loads are in flight (the first version walked a strip with 4 pixel
+// lanes per 64 channels: 2048 dependent iterations, 0.5 ms per launch at 16 x 512 x 512).
 template <typename T>
 __global__ void __launch_bounds__(TPB) border_strips_kernel(const T* __restrict__ dz, float* __restrict__ raw, int N, int H, int W, int C) {
   const int s = blockIdx.y;
   const int c = blockIdx.x * 64 + (threadIdx.x & 63);
   const int g = threadIdx.x >> 6;          // 4 pixel lanes
   const long long count = s < 2 ? (long long)N * W : (s < 4 ? (long long)N * H : N);
-  double acc = 0.0;
+  const long long lanes = 4ll * gridDim.z;
+  float acc = 0.f;
   if (c < C) {
-    for (long long p = g; p < count; p += 4) {
+#pragma unroll 4
+    for (long long p = (long long)blockIdx.z * 4 + g; p < count; p += lanes) {
       int n, h, w;
       if (s < 2) {
         n = (int)(p / W);
@@ -106,29 +110,34 @@ __global__ void __launch_bounds__(TPB) border_strips_kernel(const T* __restrict_
         h = (s == 4 || s == 5) ? 0 : H - 1;
         w = (s == 4 || s == 6) ? 0 : W - 1;
       }
-      acc += (double)(float)dz[(((long long)n * H + h) * W + w) * C + c];
+      acc += (float)dz[(((long long)n * H + h) * W + w) * C + c];
     }
   }
-  __shared__ double sh[4][64];
+  __shared__ float sh[4][64];
   sh[g][threadIdx.x & 63] = acc;
   __syncthreads();
-  if (g == 0 && c < C) raw[(size_t)s * C + c] = (float)(sh[0][threadIdx.x] + sh[1][threadIdx.x] + sh[2][threadIdx.x] + sh[3][threadIdx.x]);
+  if (g == 0 && c < C)
+    raw[((size_t)blockIdx.z * 8 + s) * C + c] = (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
 }
 
 // sdz[tap][c] = total - (row strip excluded by the tap) - (column strip excluded by the tap) + (their common corner)
-__global__ void border_finish_kernel(const float* __restrict__ raw, const float* __restrict__ total, float* __restrict__ sdz, int C) {
+__global__ void border_finish_kernel(const float* __restrict__ raw, const float* __restrict__ total, float* __restrict__ sdz, int C, int chunks) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float tot = total[c];
+  double r[8] = {};
+  for (int k = 0; k < chunks; ++k)
+#pragma unroll
+    for (int s = 0; s < 8; ++s) r[s] += (double)raw[((size_t)k * 8 + s) * C + c];
+  const double tot = (double)total[c];
   for (int dy = 0; dy < 3; ++dy)
     for (int dx = 0; dx < 3; ++dx) {
-      float v = tot;
-      if (dy == 0) v -= raw[0 * C + c];
-      if (dy == 2) v -= raw[1 * C + c];
-      if (dx == 0) v -= raw[2 * C + c];
-      if (dx == 2) v -= raw[3 * C + c];
-      if (dy != 1 && dx != 1) v += raw[(4 + (dy == 2 ? 2 : 0) + (dx == 2 ? 1 : 0)) * C + c];
-      sdz[(size_t)(dy * 3 + dx) * C + c] = v;
+      double v = tot;
+      if (dy == 0) v -= r[0];
+      if (dy == 2) v -= r[1];
+      if (dx == 0) v -= r[2];
+      if (dx == 2) v -= r[3];
+      if (dy != 1 && dx != 1) v += r[4 + (dy == 2 ? 2 : 0) + (dx == 2 ? 1 : 0)];
+      sdz[(size_t)(dy * 3 + dx) * C + c] = (float)v;
     }
 }
 
@@ -208,13 +217,18 @@ int ub_fold_conv3_weights(const float* w, int Cout, int C0, const float* mean0, 
 }
 
 int ub_border_sums(const void* dz, const float* total, float* sdz, float* scratch, int N, int H, int W, int C, int dtype, cudaStream_t stream) {
-  UB_CHECK_ARG(dz && total && sdz && scratch && N > 0 && H >= 2 && W >= 2 && C > 0, "border_sums: bad args (H, W >= 2; scratch = 8 * C floats)");
-  const dim3 grid((C + 63) / 64, 8);
+  UB_CHECK_ARG(dz && total && sdz && scratch && N > 0 && H >= 2 && W >= 2 && C > 0,
+               "border_sums: bad args (H, W >= 2; scratch = UB_BORDER_CHUNKS * 8 * C floats)");
+  long long longest = (long long)N * (H > W ? H : W);
+  int chunks = (int)((longest + 63) / 64);           // >= 16 pixels per lane where the strip is long enough
+  if (chunks > UB_BORDER_CHUNKS) chunks = UB_BORDER_CHUNKS;
+  if (chunks < 1) chunks = 1;
+  const dim3 grid((C + 63) / 64, 8, chunks);
   if (dtype == UB_BF16) border_strips_kernel<__nv_bfloat16><<<grid, TPB, 0, stream>>>((const __nv_bfloat16*)dz, scratch, N, H, W, C);
   else if (dtype == UB_F32) border_strips_kernel<float><<<grid, TPB, 0, stream>>>((const float*)dz, scratch, N, H, W, C);
   else UB_CHECK_ARG(false, "border_sums: bad dtype %d", dtype);
   UB_LAUNCH_CHECK();
-  border_finish_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, total, sdz, C);
+  border_finish_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, total, sdz, C, chunks);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -782,7 +782,7 @@ class UNet:
             if L.fold is not None:
                 # dW = s[ci] * dW_a + t[ci] * (sum of dz over the pixels whose tap neighbour is inside); the total is the bias gradient
                 sdz = self._ensure("fold_sdz", 9 * 2048, torch.float32)
-                scr = self._ensure("fold_scr", 8 * 2048, torch.float32)
+                scr = self._ensure("fold_scr", _C.MACROS["UB_BORDER_CHUNKS"] * 8 * 2048, torch.float32)
                 self._call("ub_border_sums", dz, self.G[L.off_b:L.off_b + L.cout], sdz, scr, N, h, w, L.cout, self.act_code)
                 self._call("ub_wgrad_fold_fix", dw, self._b("fold_s:" + L.name), self._b("fold_t:" + L.name), sdz, L.cout, L.cin)
 

@@ -46,7 +46,10 @@ TOL = {"bf16": dict(softmax=1e-2, loss=1e-2, grad=1e-2, stat=1e-2, uncond=0.25, 
 # bf16 product path, one training step at Keras-initial weights, shapes with >= 512 BatchNorm samples per channel everywhere
 # (2 x 1 x 256 x 256 and larger): absolute bounds against the fp64 oracle.  Measured on B200 (profiles/r02_parity.md); the oracle's
 # own bf16-storage emulation sits at logits 0.095, softmax rms 0.026, gradients 0.05-0.09 relative L2 per kernel (conditioned).
-BF16_BOUNDS_256 = dict(logits=0.25, sm_rms=0.05, stat=0.02, grad_l2=0.15, grad_l2_worst=0.2, agree=0.95)
+BF16_BOUNDS_256 = dict(logits=0.15, sm_rms=0.04, stat=0.02, grad_l2=0.09, grad_l2_worst=0.13, agree=0.96)
+# the same path at TRAINED weights (case_trained): north_star's bounds hold -- logits / softmax / conditioned gradients <= 1e-2-ish,
+# argmax agreement >= 99.9 % (measured: logits 1.9e-3, softmax 2.9e-3, worst kernel gradient 1.1e-2 rel. L2, agreement 99.98 %)
+TRAINED_BOUNDS = dict(agree=0.999, infer_softmax=1e-2, logits=1e-2, grad_l2=2e-2)
 
 
 def rel(got, ref, floor=0.0):
@@ -261,9 +264,31 @@ def learnable_batch(N, C, H, W, rng, K=2):
     f = gaussian_filter(rng.normal(size=(N, K - 1 if K == 2 else K, H, W)), sigma=(0, 0, 3, 3))
     f = f / f.std()
     lab = (f[:, 0] > 0).astype(np.uint8) if K == 2 else f.argmax(1).astype(np.uint8)
-    mix = rng.normal(size=(C, f.shape[1]))
+    mix = np.cos(1.0 + np.arange(C)[:, None] * 1.7 + np.arange(f.shape[1])[None, :] * 0.9)          # the SAME image/label relation in every batch
     x = (np.einsum("ck,nkhw->nchw", mix, f) * 2.0 + rng.normal(size=(N, C, H, W)) * 0.5).astype(np.float32)
     return x, lab
+
+
+_TRAINED = {}
+
+
+def trained_model(C=1, K=2, steps=300, N=8, S=128, seed=51):
+    """(model, fp64 parameter dict incl. moving statistics, rng, last-10 training loss): `steps` optimisation steps of the bf16
+    product path on the learnable synthetic task -- the regime the reference's inference.py runs in.  Cached per process."""
+    from unetb200.model import UNet
+    key = (C, K, steps, N, S, seed)
+    if key not in _TRAINED:
+        rng = np.random.default_rng(seed)
+        m = UNet(K, N, C, learning_rate=1e-3, precision="bf16", seed=seed)
+        losses = []
+        for s in range(steps):
+            x, lab = learnable_batch(N, C, S, S, rng, K)
+            loss = m.train_step(torch.tensor(x), torch.tensor(lab))      # a view of the metrics buffer: read it now or never
+            if s >= steps - 10:
+                losses.append(float(loss.item()))
+        p = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in m.export_params().items()}
+        _TRAINED[key] = (m, p, rng, float(np.mean(losses)))
+    return _TRAINED[key]
 
 
 def case_trained(C=1, K=2, steps=300, N=8, S=128, seed=51, n_eval=2, s_eval=256, bounds=None):
@@ -271,18 +296,11 @@ def case_trained(C=1, K=2, steps=300, N=8, S=128, seed=51, n_eval=2, s_eval=256,
     learnable synthetic task, then -- at those weights and moving statistics, exported to the fp64 oracle --
       (1) inference (training=False) on fresh images: softmax / logits max error and per-pixel argmax agreement
           (north_star: >= 99.9 %), UNet/inference.py:105-107;
-      (2) one more training step (dropout off): loss, logits, and all gradients, conditioned and unconditioned."""
+      (2) one more training step (dropout off): loss, logits, and all gradients, conditioned and unconditioned
+          (north_star: <= 1e-2)."""
     from unetb200.model import UNet
-    rng = np.random.default_rng(seed)
-    m = UNet(K, N, C, learning_rate=1e-3, precision="bf16", seed=seed)
-    losses = []
-    for s in range(steps):
-        x, lab = learnable_batch(N, C, S, S, rng, K)
-        loss = m.train_step(torch.tensor(x), torch.tensor(lab))      # a view of the metrics buffer: read it now or never
-        if s >= steps - 10:
-            losses.append(float(loss.item()))
-    p = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in m.export_params().items()}
-    r = dict(train_loss_last10=float(np.mean(losses)))
+    m, p, rng, last10 = trained_model(C, K, steps, N, S, seed)
+    r = dict(train_loss_last10=last10)
     # (1) inference
     x, lab = learnable_batch(n_eval, C, s_eval, s_eval, rng, K)
     sm = m.get_keras_model()(x)
@@ -319,11 +337,11 @@ def case_trained(C=1, K=2, steps=300, N=8, S=128, seed=51, n_eval=2, s_eval=256,
     if os.environ.get("UB_VERBOSE"):
         r["grad_l2_cond_per"] = {k: float(f"{v:.3g}") for k, v in l2c.items()}
         r["grad_l2_uncond_per"] = {k: float(f"{v:.3g}") for k, v in l2u.items()}
-    b = bounds or dict(agree=0.999, infer_softmax=0.1, grad_l2=0.2)
+    b = bounds or TRAINED_BOUNDS
     r["bounds"] = b
     r["ok"] = bool(r["infer_argmax_agree"] >= b["agree"] and r["infer_e_softmax"] <= b["infer_softmax"] and r["infer_e_loss"] < 1e-2
-                   and r["train_e_loss"] < 1e-2 and r["grad_l2_cond_worst"] <= b["grad_l2"]
-                   and r["train_loss_last10"] < 0.5)
+                   and r["train_e_loss"] < 1e-2 and r["train_e_logits"] <= b["logits"] and r["grad_l2_cond_worst"] <= b["grad_l2"]
+                   and r["train_argmax_agree"] >= b["agree"] and r["train_loss_last10"] < 0.5)
     return r
 
 
@@ -400,7 +418,10 @@ def case_inference(precision):
     tol = TOL[precision]
     r = dict(e_softmax=rel(sm, ref["softmax"].numpy()), e_loss=abs(loss - float(ref["loss"])) / float(ref["loss"]),
              argmax_agree=float((sm.argmax(-1) == ref["softmax"].numpy().argmax(-1)).mean()))
-    r["ok"] = bool(r["e_softmax"] < tol["softmax"] and r["e_loss"] < tol["loss"] and sm.shape == (N, H, W, K))
+    # argmax agreement at these RANDOM weights (softmax within a few 1e-3 of uniform at many pixels) is reported; the north_star
+    # bound (>= 99.9 %) is asserted in fp32 here and, for the bf16 product path, at trained weights in case_trained / case_tiled_inference
+    r["ok"] = bool(r["e_softmax"] < tol["softmax"] and r["e_loss"] < tol["loss"] and sm.shape == (N, H, W, K)
+                   and (precision != "fp32" or r["argmax_agree"] >= 0.999))
     return r
 
 
@@ -412,18 +433,23 @@ def case_tiled_inference(precision):
     from unetb200.model import UNet
     import unetb200.inference as I
     C, K = 1, 2
-    p = O.init_params(C, K, seed=7, base=64, randomize_affine=True)
     rng = np.random.default_rng(7)
-    for k in p:
-        if k.endswith("moving_mean"):
-            p[k] = torch.tensor(rng.normal(0.3, 0.1, size=p[k].shape))
-        if k.endswith("moving_var"):
-            p[k] = torch.tensor(rng.uniform(0.5, 1.5, size=p[k].shape))
+    from scipy.ndimage import gaussian_filter
+    if precision == "bf16":
+        # trained weights and an image of the training distribution: the regime in which the per-pixel argmax is well defined
+        _, p, _, _ = trained_model(C, K)
+        img = learnable_batch(1, C, 400, 336, rng, K)[0][0, 0]
+    else:
+        p = O.init_params(C, K, seed=7, base=64, randomize_affine=True)
+        for k in p:
+            if k.endswith("moving_mean"):
+                p[k] = torch.tensor(rng.normal(0.3, 0.1, size=p[k].shape))
+            if k.endswith("moving_var"):
+                p[k] = torch.tensor(rng.uniform(0.5, 1.5, size=p[k].shape))
+        img = gaussian_filter(rng.normal(size=(400, 336)), 3).astype(np.float32)
+        img = (img / img.std()).astype(np.float32)
     m = UNet(K, 1, C, precision=precision, seed=0)
     m.load_oracle_params({k: v.numpy() for k, v in p.items()})
-    from scipy.ndimage import gaussian_filter
-    img = gaussian_filter(rng.normal(size=(400, 336)), 3).astype(np.float32)
-    img = (img / img.std()).astype(np.float32)
     r = {}
     got = I._inference_tiling(img, m, 288)
     ref = O.inference_tiling(img, m.get_keras_model(), 288, 96)
@@ -438,10 +464,10 @@ def case_tiled_inference(precision):
     r["whole_agree"] = float((got3 == ref3).mean())
     r["fg_fraction"] = float((ref == 1).mean())
     ok = r["shape_ok"] and min(r["tiling_agree"], r["ragged_agree"], r["whole_agree"]) >= 0.999 and got2.shape == ragged.shape
-    if precision == "fp32":
-        ref64 = O.inference_tiling(img.astype(np.float64), O.make_model_fn(p), 288, 96)
-        r["oracle_agree"] = float((got == ref64).mean())
-        ok = ok and r["oracle_agree"] >= 0.999
+    # numerics: the CUDA tiler + CUDA model against the reference's tile loop around the fp64 ORACLE model (north_star >= 99.9 %)
+    ref64 = O.inference_tiling(img.astype(np.float64), O.make_model_fn(p), 288, 96)
+    r["oracle_agree"] = float((got == ref64).mean())
+    ok = ok and r["oracle_agree"] >= 0.999
     # file path: uint16 TIFF -> GPU z-score -> mask, against the host z-score + oracle tiler around the CUDA model
     raw = np.clip(np.round(3000 + 400 * img), 0, 65535).astype(np.uint16)
     with tempfile.TemporaryDirectory() as d:
@@ -659,14 +685,7 @@ def case_banded_inference():
     return dict(agree=agree, fg=float((ref == 1).float().mean()), ok=bool(agree == 1.0))
 
 
-# written after the round's GPU budget had run out: not yet run on a B200, not collected by pytest (tests/gpu_probe.py --pending)
-PENDING_CASES = {
-    "banded_inference": case_banded_inference,
-    "fold_live_bf16_c1k2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23)),
-    "fold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8)),
-    "fold_golden_c1_k2_bf16": _with_fold(lambda: case_golden("graph_c1_k2", "bf16")),
-    "fold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=200)),
-}
+PENDING_CASES = {}
 
 
 # report-only measurements (tests/gpu_probe.py --probe): the bf16 product path against fp64 and against the oracle's
@@ -690,8 +709,8 @@ CASES = {
     "tiled_inference_fp32": lambda: case_tiled_inference("fp32"),
     "live_fp32_c1k2": lambda: case_live("fp32", N=2, C=1, H=64, W=48, K=2, seed=21),
     "live_fp32_c3k8": lambda: case_live("fp32", N=1, C=3, H=80, W=112, K=8, seed=22, gb=4),
-    "live_bf16_c1k2": lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23),
-    "live_bf16_c3k8": lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8),
+    "live_bf16_c1k2": lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True),
+    "live_bf16_c3k8": lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True),
     "golden_c1_k2_fp32": lambda: case_golden("graph_c1_k2", "fp32"),
     "golden_c3_k8_fp32": lambda: case_golden("graph_c3_k8", "fp32"),
     "golden_c1_k2_bf16": lambda: case_golden("graph_c1_k2", "bf16"),
@@ -699,4 +718,16 @@ CASES = {
     "curve_bf16": lambda: case_curve("bf16", steps=200),          # north_star: loss curve over the first 200 steps
     "inference_fp32": lambda: case_inference("fp32"),
     "inference_bf16": lambda: case_inference("bf16"),
+    # bf16 product path at a shape with well-conditioned BatchNorm statistics: absolute bounds (also what smoke() runs)
+    "wellcond_bf16_n2_256": lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256),
+    # ... and at trained weights: north_star's 1e-2 / 99.9 %
+    "trained_bf16": case_trained,
+    # row-band sharded inference == tile-sharded inference on one rank
+    "banded_inference": case_banded_inference,
+    # BatchNorm folded into the consumer convolutions (UB_FOLD_BN=1)
+    "fold_live_bf16_c1k2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True)),
+    "fold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True)),
+    "fold_wellcond_bf16_n2_256": _with_fold(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256)),
+    "fold_golden_c1_k2_bf16": _with_fold(lambda: case_golden("graph_c1_k2", "bf16")),
+    "fold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=200)),
 }

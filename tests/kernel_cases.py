@@ -705,7 +705,7 @@ def case_wgrad_folded(C0=64, C1=0, Cout=64, N=2, H=24, W=40, seed=32, identity0=
     C.call("ub_conv3x3_wgrad", dev(a[..., :C0], torch.bfloat16), C0, dev(a[..., C0:], torch.bfloat16) if C1 else None, C1, dzd, Cout, dw, ws, nb, N, H, W, stream())
     total = dev(dz.sum((0, 1, 2)), torch.float32)
     sdz = torch.empty((9, Cout), device="cuda")
-    scratch = torch.empty(8 * Cout, device="cuda")
+    scratch = torch.empty(C.MACROS["UB_BORDER_CHUNKS"] * 8 * Cout, device="cuda")
     C.call("ub_border_sums", dzd, total, sdz, scratch, N, H, W, Cout, C.UB_BF16, stream())
     C.call("ub_wgrad_fold_fix", dw, sc, sh, sdz, Cout, Cin, stream())
     torch.cuda.synchronize()
@@ -907,20 +907,7 @@ def case_conv3x3_layer(C0, C1, Cout, N, H, W, seed=30, n_ci=6):
     return r
 
 
-PENDING_CASES = {
-    "published_known_answers": case_published_known_answers,
-    "head_fold_k2": case_head_fold,
-    "head_fold_k8": lambda: case_head_fold(8, P=513),
-    "bn_pool_noy": case_bn_pool_noy,
-    "fold_weights_64": case_fold_weights,
-    "fold_weights_cat_128+128_256": lambda: case_fold_weights(128, 128, 256, identity0=True),
-    "conv_fwd_folded_64_64": case_conv_fwd_folded,
-    "conv_fwd_folded_128_128": lambda: case_conv_fwd_folded(128, 0, 128, N=1, H=20, W=13),
-    "conv_fwd_folded_cat_64+64_64": lambda: case_conv_fwd_folded(64, 64, 64, identity0=True),
-    "conv_fwd_folded_2x2": lambda: case_conv_fwd_folded(64, 0, 64, N=1, H=2, W=2),
-    "wgrad_folded_64_64": case_wgrad_folded,
-    "wgrad_folded_cat_128+128_128": lambda: case_wgrad_folded(128, 128, 128, N=1, H=16, W=24, identity0=True),
-}
+PENDING_CASES = {}
 
 
 CASES = {
@@ -983,4 +970,17 @@ CASES = {
     "augment_c3_u8": lambda: case_augment(3, "u8", N=2, H=64, W=48, seed=1),
     "augment_c2_f32_norot": lambda: case_augment(2, "f32", N=2, H=32, W=32, seed=2, rotation=False),
     "augment_noise": case_augment_noise,
+    # BatchNorm fold kernels (csrc/fold.cu), y-less pool, folded head, published known answers
+    "published_known_answers": case_published_known_answers,
+    "head_fold_k2": case_head_fold,
+    "head_fold_k8": lambda: case_head_fold(8, P=513),
+    "bn_pool_noy": case_bn_pool_noy,
+    "fold_weights_64": case_fold_weights,
+    "fold_weights_cat_128+128_256": lambda: case_fold_weights(128, 128, 256, identity0=True),
+    "conv_fwd_folded_64_64": case_conv_fwd_folded,
+    "conv_fwd_folded_128_128": lambda: case_conv_fwd_folded(128, 0, 128, N=1, H=20, W=13),
+    "conv_fwd_folded_cat_64+64_64": lambda: case_conv_fwd_folded(64, 64, 64, identity0=True),
+    "conv_fwd_folded_2x2": lambda: case_conv_fwd_folded(64, 0, 64, N=1, H=2, W=2),
+    "wgrad_folded_64_64": case_wgrad_folded,
+    "wgrad_folded_cat_128+128_128": lambda: case_wgrad_folded(128, 128, 128, N=1, H=16, W=24, identity0=True),
 }
