@@ -125,6 +125,14 @@ int ub_deconv2x2_fwd_affine(const void* x, int Cin, const void* w, const float* 
                             int N, int h, int w_in, int Cout, cudaStream_t stream);
 int ub_conv_first_fwd_affine(const float* x_nchw, const float* w, const float* bias, const float* scale, const float* shift, void* out,
                              int N, int H, int W, int Cin, int dtype, cudaStream_t stream);
+/* The same layer for N equal-sized inference tiles read IN PLACE from the resident normalised image (the tile loop of
+ * UNet/inference.py:56-105 without one copy per tile): img fp32 [Cin][>= img_h rows][row_pitch], plane_stride floats between
+ * channels; tile n = rows [origin_yx[2n], +H) x columns [origin_yx[2n+1], +W).  Source coordinates >= img_h / img_w (the
+ * unpadded extent) are mirrored without repeating the edge -- np.pad(mode='reflect') to a multiple of 16, inference.py:46 --
+ * and positions outside the tile are zero ('same' padding of the tile).  W % 4 == 0. */
+int ub_conv_first_fwd_affine_tiles(const float* img, const int* origin_yx, int img_h, int img_w, long long row_pitch, long long plane_stride,
+                                   const float* w, const float* bias, const float* scale, const float* shift, void* out, int N, int H, int W,
+                                   int Cin, int dtype, cudaStream_t stream);
 int ub_maxpool2x2_fwd(const void* y, void* pooled, int N, int H, int W, int C, int dtype, cudaStream_t stream);
 /* scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale */
 int ub_bn_fold(const float* gamma, const float* beta, const float* moving_mean, const float* moving_var, float* scale, float* shift,

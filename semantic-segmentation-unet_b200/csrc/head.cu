@@ -228,6 +228,90 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* 
   }
 }
 
+// Inference tiles read IN PLACE from the resident, normalised image (UNet/inference.py:46, :97-105): tile n covers image rows
+// [origin[2n], +H) and columns [origin[2n+1], +W) of img [CIN][rows >= img_h][pitch]; source coordinates past the unpadded extent
+// (img_h, img_w) are mirrored without repeating the edge (np.pad mode='reflect', the bottom/right padding to a multiple of 16), and
+// positions outside the TILE are zero (the tile is convolved as an image of its own, 'same' padding).  Same strip mining as above.
+__device__ __forceinline__ int reflect_index(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }
+
+template <typename T, int CIN>
+__global__ void __launch_bounds__(TPB) conv_first_fwd_tiles_kernel(const float* __restrict__ img, const int* __restrict__ origin, int img_h,
+                                                                   int img_w, long long pitch, long long plane_stride,
+                                                                   const float* __restrict__ w, const float* __restrict__ bias,
+                                                                   const float* __restrict__ post_scale, const float* __restrict__ post_shift,
+                                                                   T* __restrict__ out, int N, int H, int W) {
+  __shared__ float ws[9 * CIN][64];
+  for (int i = threadIdx.x; i < 64 * 9 * CIN; i += TPB) {
+    const int co = i / (9 * CIN), k = i % (9 * CIN);
+    ws[k][co] = w[i];
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float b[8], psc[8], psh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    b[i] = bias[sub * 8 + i];
+    psc[i] = post_scale[sub * 8 + i];
+    psh[i] = post_shift[sub * 8 + i];
+  }
+  const int W4 = W >> 2;
+  const long long strips = (long long)N * H * W4;
+  for (long long st = (long long)blockIdx.x * 32 + pl; st < strips; st += (long long)gridDim.x * 32) {
+    const int w0 = (int)(st % W4) * 4;
+    const long long t = st / W4;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const int oy = __ldg(origin + 2 * n), ox = __ldg(origin + 2 * n + 1);
+    float o[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[q][i] = b[i];
+    const int sx = ox + w0;
+    const bool vec = (sx + 4 <= img_w) && (((pitch | sx) & 3) == 0);
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* xp = img + (long long)ci * plane_stride;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = h + r - 1;
+        float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (hh >= 0 && hh < H) {
+          const float* row = xp + (long long)reflect_index(oy + hh, img_h) * pitch;
+          if (vec) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(row + sx));
+            v[1] = m.x; v[2] = m.y; v[3] = m.z; v[4] = m.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[1 + q] = __ldg(row + reflect_index(sx + q, img_w));
+          }
+          if (w0 > 0) v[0] = __ldg(row + reflect_index(sx - 1, img_w));
+          if (w0 + 4 < W) v[5] = __ldg(row + reflect_index(sx + 4, img_w));
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int k = (r * 3 + c) * CIN + ci;
+          const float4 wa = *reinterpret_cast<const float4*>(&ws[k][sub * 8]);
+          const float4 wb = *reinterpret_cast<const float4*>(&ws[k][sub * 8 + 4]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float xv = v[q + c];
+            o[q][0] += xv * wa.x; o[q][1] += xv * wa.y; o[q][2] += xv * wa.z; o[q][3] += xv * wa.w;
+            o[q][4] += xv * wb.x; o[q][5] += xv * wb.y; o[q][6] += xv * wb.z; o[q][7] += xv * wb.w;
+          }
+        }
+      }
+    }
+    const long long px0 = ((long long)n * H + h) * W + w0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[q][i] = fmaf(fmaxf(o[q][i], 0.f), psc[i], psh[i]);
+      st8<T>(out + (px0 + q) * 64 + sub * 8, o[q]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(TPB, 2) conv_first_wgrad_strip_kernel(const float* __restrict__ x, const T* __restrict__ dz,
                                                                      float* __restrict__ partial, int N, int H, int W, int CIN) {
@@ -792,6 +876,23 @@ int ub_conv_first_fwd_affine(const float* x_nchw, const float* w, const float* b
                              int N, int H, int W, int Cin, int dtype, cudaStream_t stream) {
   UB_CHECK_ARG(scale && shift, "conv_first_fwd_affine: null pointer");
   return conv_first_impl(x_nchw, w, bias, scale, shift, out, nullptr, N, H, W, Cin, dtype, stream);
+}
+
+int ub_conv_first_fwd_affine_tiles(const float* img, const int* origin_yx, int img_h, int img_w, long long row_pitch, long long plane_stride,
+                                   const float* w, const float* bias, const float* scale, const float* shift, void* out, int N, int H, int W,
+                                   int Cin, int dtype, cudaStream_t stream) {
+  UB_CHECK_ARG(img && origin_yx && w && bias && scale && shift && out, "conv_first_fwd_affine_tiles: null pointer");
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_fwd_affine_tiles: Cin=%d must be in [1,4]", Cin);
+  UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0 && W % 4 == 0, "conv_first_fwd_affine_tiles: tile width must be a multiple of 4 (got %d x %d)", H, W);
+  UB_CHECK_SHAPE(img_h >= 2 && img_w >= 2 && row_pitch >= img_w, "conv_first_fwd_affine_tiles: bad image extent %d x %d, pitch %lld", img_h, img_w,
+                 row_pitch);
+  UB_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && plane_stride % 4 == 0, "conv_first_fwd_affine_tiles: image must be 16-byte aligned");
+  const long long P = (long long)N * H * W;
+  const int grid = grid_for(P / 4, 32 * 4, UB_STATS_ROWS);
+  UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_tiles_kernel<T, CIN><<<grid, TPB, 0, stream>>>(img, origin_yx, img_h, img_w, row_pitch, plane_stride,
+                                                                                                        w, bias, scale, shift, (T*)out, N, H, W))));
+  UB_LAUNCH_CHECK();
+  return UB_OK;
 }
 
 static int conv_first_impl(const float* x_nchw, const float* w, const float* bias, const float* post_scale, const float* post_shift, void* out,

@@ -77,11 +77,9 @@ def _pad_amounts(h, w):
     return (SIZE_FACTOR - h % SIZE_FACTOR) % SIZE_FACTOR, (SIZE_FACTOR - w % SIZE_FACTOR) % SIZE_FACTOR
 
 
-def _to_device_chw(img_hwc, device, pad_y, pad_x):
-    """host HWC (any dtype) -> device CHW float32, reflect-padded bottom/right (np.pad(mode='reflect'), inference.py:46)"""
+def _to_device_chw(img_hwc, device):
+    """host HWC (any dtype) -> device CHW float32 (unpadded: the tile reader mirrors past the image edge)"""
     import torch
-    if pad_y or pad_x:
-        img_hwc = np.pad(img_hwc, pad_width=((0, pad_y), (0, pad_x), (0, 0)), mode='reflect')
     chw = np.ascontiguousarray(img_hwc.transpose((2, 0, 1)))
     t = torch.from_numpy(chw)
     if device.type == "cuda":
@@ -89,38 +87,47 @@ def _to_device_chw(img_hwc, device, pad_y, pad_x):
     return t.to(torch.float32) if t.dtype != torch.float32 else t
 
 
+def _run_tiles(img_chw, img_h, tiles, unet_model, mask, mask_ld, tile_batch, row0=0, zrow0=0):
+    """Forward `tiles` (tile_plan entries in the coordinates of the PADDED image) and write each zone's argmax into `mask`.
+    img_chw [C, rows, W]: rows [row0, row0 + rows) of the normalised UNPADDED image, img_h = its total height; the tiles are read
+    in place (UNet.predict_tiles_from), grouped by shape so that equal-sized tiles share a forward.  zrow0: image row of mask row 0."""
+    import torch
+    if not tiles:
+        return
+    dev = img_chw.device
+    groups = {}
+    for t in tiles:
+        groups.setdefault((t["y1"] - t["y0"], t["x1"] - t["x0"]), []).append(t)
+    order = [t for shape in groups for t in groups[shape]]
+    geo = torch.from_numpy(np.array([[t["cy0"], t["cy1"], t["cx0"], t["cx1"], t["dy"] - zrow0, t["dx"]] for t in order], dtype=np.int32)).to(dev)
+    org = torch.from_numpy(np.array([[t["y0"] - row0, t["x0"]] for t in order], dtype=np.int32)).to(dev)
+    k = 0
+    for (h, w), ts in groups.items():
+        for s in range(0, len(ts), tile_batch):
+            n = min(tile_batch, len(ts) - s)
+            unet_model.predict_tiles_from(img_chw, img_h - row0, img_chw.shape[2], org[k:k + n], n, h, w, geo[k:k + n], mask, mask_ld)
+            k += n
+
+
 def segment_device(img_chw, unet_model, tile_size=TILE_SIZE, radius=None, tile_batch=TILE_BATCH, dist=None):
-    """img_chw: NORMALISED float32 device tensor [C, H, W], H and W multiples of 16.  Returns the uint8 device mask
-    [H, W].  tile_size None = one forward of the whole image.  With `dist` (unetb200.dist.DataParallel, world > 1) the tiles are sharded round-robin and the mask is
-    SUM-reduced (zones are disjoint, unowned pixels are zero)."""
+    """img_chw: NORMALISED float32 device tensor [C, H, W] (unpadded).  Returns the uint8 device mask [Hp, Wp] of the image
+    reflect-padded bottom/right to multiples of 16 (UNet/inference.py:29-46; callers crop [:H, :W]); the padding is never
+    materialised.  tile_size None = one forward of the whole image.  With `dist` (unetb200.dist.DataParallel, world > 1) the tiles
+    are sharded round-robin and the mask is SUM-reduced (zones are disjoint, unowned pixels are zero)."""
     import torch
     C, H, W = img_chw.shape
+    pad_y, pad_x = _pad_amounts(H, W)
+    Hp, Wp = H + pad_y, W + pad_x
     dev = img_chw.device
-    mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    mask = torch.zeros((Hp, Wp), dtype=torch.uint8, device=dev)
     if tile_size is None:                       # single-shot path (UNet/inference.py:139-173)
-        plan = [dict(y0=0, y1=H, x0=0, x1=W, cy0=0, cy1=H, cx0=0, cx1=W, dy=0, dx=0)]
+        plan = [dict(y0=0, y1=Hp, x0=0, x1=Wp, cy0=0, cy1=Hp, cx0=0, cx1=Wp, dy=0, dx=0)]
     else:
         if radius is None:
             radius = unet_model.estimate_radius()
-        plan = tile_plan(H, W, tile_size, radius)
+        plan = tile_plan(Hp, Wp, tile_size, radius)
     rank, world = (dist.rank, dist.world_size) if dist is not None else (0, 1)
-    mine = plan[rank::world]
-    groups = {}
-    for t in mine:
-        groups.setdefault((t["y1"] - t["y0"], t["x1"] - t["x0"]), []).append(t)
-    order = [t for shape in groups for t in groups[shape]]
-    if order:
-        geo_host = np.array([[t["cy0"], t["cy1"], t["cx0"], t["cx1"], t["dy"], t["dx"]] for t in order], dtype=np.int32)
-        geo = torch.from_numpy(geo_host).to(dev)
-        k = 0
-        for (h, w), tiles in groups.items():
-            xb = torch.empty((min(tile_batch, len(tiles)), C, h, w), dtype=torch.float32, device=dev)
-            for s in range(0, len(tiles), tile_batch):
-                chunk = tiles[s:s + tile_batch]
-                for b, t in enumerate(chunk):
-                    xb[b].copy_(img_chw[:, t["y0"]:t["y1"], t["x0"]:t["x1"]])
-                unet_model.predict_tiles_into(xb[:len(chunk)], geo[k:k + len(chunk)], mask, W)
-                k += len(chunk)
+    _run_tiles(img_chw, H, plan[rank::world], unet_model, mask, Wp, tile_batch)
     if world > 1:
         import torch.distributed as td
         td.all_reduce(mask, op=td.ReduceOp.SUM)
@@ -148,11 +155,11 @@ def band_plan(height, width, tile_size, radius, world):
 
 
 def segment_banded(raw_host, unet_model, dist, tile_size=TILE_SIZE, radius=None, tile_batch=TILE_BATCH, out_host=None):
-    """Tiled inference of one image with the ROWS sharded over the ranks of `dist` (NOT YET RUN ON A B200; segment_device is the
-    verified path).  raw_host: pinned host tensor [C, H, W] of raw pixels (uint8 / uint16-as-int16 bits / float32), the same on
-    every rank.  Each rank uploads its band, the per-channel z-score statistics of the UNPADDED image (UNet/inference.py:206) are
-    summed over the owned rows and all-reduced (2 doubles per channel), the band is normalised, reflect-padded where it touches
-    the bottom / right edge (inference.py:46), segmented, and the band masks are sent to rank 0.
+    """Tiled inference of one image with the ROWS sharded over the ranks of `dist`.  raw_host: pinned host tensor [C, H, W] of raw
+    pixels (uint8 / uint16-as-int16 bits / float32), the same on every rank.  Each rank uploads its band, the per-channel z-score
+    statistics of the UNPADDED image (UNet/inference.py:206) are summed over the owned rows and all-reduced (2 doubles per channel),
+    the band is normalised and segmented (the reflect padding of the bottom / right edge, inference.py:46, is mirror indexing
+    inside the tile reader), and the band masks are sent to rank 0.
     Returns the uint8 device mask [H, W] on rank 0 (None elsewhere); if `out_host` (pinned uint8 [H, W]) is given rank 0 copies it."""
     import torch
     import torch.distributed as td
@@ -184,25 +191,11 @@ def segment_banded(raw_host, unet_model, dist, tile_size=TILE_SIZE, radius=None,
     if b["tiles"]:
         x = torch.empty((C, y1 - y0, W), dtype=torch.float32, device=dev)
         _C.call("ub_zscore_apply_sums", raw, code, x, sums, float(H) * float(W), C, (y1 - y0) * W, st)
-        bot = b["y1"] - y1                                       # padded rows below the image that this band's tiles read
-        if bot or pad_x:
-            x = torch.nn.functional.pad(x[None], (0, pad_x, 0, bot), mode="reflect")[0].contiguous()
         zr = b["zy1"] - b["zy0"]
         band_mask = torch.zeros((zr, Wp), dtype=torch.uint8, device=dev)
-        groups = {}
-        for t in b["tiles"]:
-            groups.setdefault((t["y1"] - t["y0"], t["x1"] - t["x0"]), []).append(t)
-        order = [t for shape in groups for t in groups[shape]]
-        geo = torch.from_numpy(np.array([[t["cy0"], t["cy1"], t["cx0"], t["cx1"], t["dy"] - b["zy0"], t["dx"]] for t in order], dtype=np.int32)).to(dev)
-        k = 0
-        for (h, w), tiles in groups.items():
-            xb = torch.empty((min(tile_batch, len(tiles)), C, h, w), dtype=torch.float32, device=dev)
-            for s0 in range(0, len(tiles), tile_batch):
-                chunk = tiles[s0:s0 + tile_batch]
-                for i, t in enumerate(chunk):
-                    xb[i].copy_(x[:, t["y0"] - b["y0"]:t["y1"] - b["y0"], t["x0"]:t["x1"]])
-                unet_model.predict_tiles_into(xb[:len(chunk)], geo[k:k + len(chunk)], band_mask, Wp)
-                k += len(chunk)
+        # tiles are read in place from the band; rows / columns of the padding are mirrored by the reader (the last band holds the
+        # image's bottom rows, which is where the mirrored rows come from)
+        _run_tiles(x, H, b["tiles"], unet_model, band_mask, Wp, tile_batch, row0=y0, zrow0=b["zy0"])
     # assemble on rank 0: bands are disjoint row ranges of the padded mask
     if rank == 0:
         mask = torch.empty((Hp, Wp), dtype=torch.uint8, device=dev)
@@ -244,7 +237,7 @@ def _segment_normalised_host(img, unet_model, tile_size):
     if pad_x:
         print('image width needs to be a multiple of {}, padding with reflect'.format(SIZE_FACTOR))
     dev = unet_model.device
-    x = _to_device_chw(img.astype(np.float32, copy=False), dev, pad_y, pad_x)
+    x = _to_device_chw(img.astype(np.float32, copy=False), dev)
     mask = segment_device(x, unet_model, tile_size, dist=getattr(unet_model, "dist", None))
     out = mask.cpu().numpy().astype(np.int32)
     return out[:h0, :w0]
@@ -295,9 +288,6 @@ def segment_file(img_filepath, unet_model):
     chw = np.array(raw.transpose((2, 0, 1)), order="C")      # writable copy (PIL hands out read-only buffers)
     t = torch.from_numpy(chw).pin_memory().to(dev, non_blocking=True)
     x = zscore_device(t, unet_model)          # statistics of the UNPADDED image, as the reference (inference.py:206)
-    pad_y, pad_x = _pad_amounts(h0, w0)
-    if pad_y or pad_x:
-        x = torch.nn.functional.pad(x[None], (0, pad_x, 0, pad_y), mode='reflect')[0].contiguous()
     if h0 > TILE_SIZE or w0 > TILE_SIZE:       # inference.py:209
         mask = segment_device(x, unet_model, TILE_SIZE, dist=getattr(unet_model, "dist", None))
     else:

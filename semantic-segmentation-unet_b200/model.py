@@ -504,8 +504,10 @@ class UNet:
                        drop, N, h, w, L.cout, self.act_code)
         return y
 
-    def _forward(self, x, N, H, W, training, drop_masks=None):
-        """x: fp32 NCHW device tensor, contiguous.  Leaves y:dec1b ready for the head; returns nothing."""
+    def _forward(self, x, N, H, W, training, drop_masks=None, view=None):
+        """x: fp32 NCHW device tensor, contiguous.  Leaves y:dec1b ready for the head; returns nothing.
+        view (bf16 inference only, x = None): (img [C, rows, pitch] fp32, img_h, img_w, origins int32 [N, 2]) -- the N tiles are read
+        in place from the resident normalised image, mirrored past (img_h, img_w) (ub_conv_first_fwd_affine_tiles)."""
         if H % self.SIZE_FACTOR or W % self.SIZE_FACTOR:
             raise IOError(f"Input image tile size needs to be a multiple of {self.SIZE_FACTOR} to allow integer sized downscaled feature maps")
         self._alloc(N, H, W, training)
@@ -517,7 +519,8 @@ class UNet:
                 self._call("ub_bn_fold", gamma, beta, self.MM[o:o + c], self.MV[o:o + c], self.FS[o:o + c], self.FB[o:o + c], c, BN_EPS)
             self._inference_stale = False
         if not training and self.precision == "bf16":
-            return self._forward_folded(x, N, H, W)
+            return self._forward_folded(x, N, H, W, view)
+        assert view is None, "tile views are an inference feature of the bf16 path"
         if training and self.fold_bn and self.precision == "bf16":
             return self._forward_train_folded(x, N, H, W, drop_masks or {})
         for L in self.layers.values():
@@ -649,7 +652,7 @@ class UNet:
                 cur = self._bn_apply(Lb, N, h, w, True)
         return cur
 
-    def _forward_folded(self, x, N, H, W):
+    def _forward_folded(self, x, N, H, W, view=None):
         """Inference forward of the bf16 path (training=False: UNet/model.py:240, inference.py:105): the BatchNorm moving
         statistics are folded into each producer's epilogue (y = act(conv + b) * scale + shift), so every activation
         is written once; max-pool is a plain pool.  Leaves y:dec1b ready for the head."""
@@ -670,8 +673,13 @@ class UNet:
         self._cur = "enc1a"
         sc, sh = fold(L)
         cur = self._b("y:enc1a")
-        self._call("ub_conv_first_fwd_affine", x, self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], sc, sh, cur,
-                   N, H, W, self.number_channels, self.act_code)
+        if view is not None:
+            img, img_h, img_w, origins = view
+            self._call("ub_conv_first_fwd_affine_tiles", img, origins, img_h, img_w, img.stride(1), img.stride(0),
+                       self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], sc, sh, cur, N, H, W, self.number_channels, self.act_code)
+        else:
+            self._call("ub_conv_first_fwd_affine", x, self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], sc, sh, cur,
+                       N, H, W, self.number_channels, self.act_code)
         for lvl in (1, 2, 3, 4):
             h, w = self._dims(H, W, lvl)
             if lvl > 1:
@@ -1133,6 +1141,29 @@ class UNet:
         self._cur = "head"
         self._call("ub_head_argmax", self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K],
                    self.FS[o:o + K], self.FB[o:o + K], K, N, H, W, geo, mask, mask_ld, None, self.act_code)
+
+    def predict_tiles_from(self, img, img_h, img_w, origins, n, h, w, geo, mask, mask_ld):
+        """The same for `n` tiles of h x w read IN PLACE from the resident normalised image `img` [C, rows, pitch] (fp32): tile i
+        starts at (origins[i, 0], origins[i, 1]); rows / columns at or beyond the unpadded extent (img_h, img_w) are mirrored
+        (the reflect padding to a multiple of 16, UNet/inference.py:46).  No per-tile copy, no padded copy of the image."""
+        if self.precision != "bf16":
+            # fp32 check mode: materialise the tiles (mirror indices computed here), then the plain path
+            ys = torch.arange(h, device=img.device)
+            xs = torch.arange(w, device=img.device)
+            tiles = []
+            for oy, ox in origins[:n].tolist():
+                yy, xx = ys + oy, xs + ox
+                yy = torch.where(yy < img_h, yy, 2 * (img_h - 1) - yy)
+                xx = torch.where(xx < img_w, xx, 2 * (img_w - 1) - xx)
+                tiles.append(img[:, yy][:, :, xx])
+            return self.predict_tiles_into(torch.stack(tiles).contiguous(), geo, mask, mask_ld)
+        self._forward(None, n, h, w, False, view=(img, int(img_h), int(img_w), origins))
+        L = self.layers["head"]
+        K = self.number_classes
+        o = L.off_stat
+        self._cur = "head"
+        self._call("ub_head_argmax", self._b("y:dec1b"), self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + K],
+                   self.FS[o:o + K], self.FB[o:o + K], K, n, h, w, geo, mask, mask_ld, None, self.act_code)
 
     # ------------------------------------------------------------------------------------------------ checkpoint
     def state_dict(self):

