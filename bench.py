@@ -74,7 +74,7 @@ def step_flops(batch=None, **kw):
     return batch * fwd, batch * train, fam
 
 
-FAMILY = {"ub_conv3x3_fwd": "igemm_fwd", "ub_conv3x3_dgrad": "igemm_fwd", "ub_conv3x3_dgrad_bnred": "igemm_fwd", "ub_deconv2x2_fwd": "igemm_fwd", "ub_deconv2x2_dgrad": "igemm_fwd",
+FAMILY = {"ub_conv3x3_fwd": "igemm_fwd", "ub_conv3x3_fwd_cases": "igemm_fwd", "ub_conv3x3_dgrad": "igemm_fwd", "ub_conv3x3_dgrad_bnred": "igemm_fwd", "ub_deconv2x2_fwd": "igemm_fwd", "ub_deconv2x2_dgrad": "igemm_fwd",
           "ub_conv3x3_wgrad": "igemm_wgrad", "ub_deconv2x2_wgrad": "igemm_wgrad"}
 
 
@@ -388,7 +388,7 @@ def run_cuda(args):
             f = FAMILY.get(name)
             if f:
                 fam_ms[f] = fam_ms.get(f, 0.0) + t / nprof
-            if name == "ub_conv3x3_fwd":
+            if name in ("ub_conv3x3_fwd", "ub_conv3x3_fwd_cases"):
                 fam_ms["conv3_fwd"] = fam_ms.get("conv3_fwd", 0.0) + t / nprof
             layer_ms[(layer, name)] = layer_ms.get((layer, name), 0.0) + t / nprof
         model.profile = None

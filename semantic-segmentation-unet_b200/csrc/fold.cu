@@ -120,25 +120,38 @@ __global__ void __launch_bounds__(TPB) border_strips_kernel(const T* __restrict_
     raw[((size_t)blockIdx.z * 8 + s) * C + c] = (sh[0][threadIdx.x] + sh[1][threadIdx.x]) + (sh[2][threadIdx.x] + sh[3][threadIdx.x]);
 }
 
-// sdz[tap][c] = total - (row strip excluded by the tap) - (column strip excluded by the tap) + (their common corner)
-__global__ void border_finish_kernel(const float* __restrict__ raw, const float* __restrict__ total, float* __restrict__ sdz, int C, int chunks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double r[8] = {};
-  for (int k = 0; k < chunks; ++k)
+// sdz[tap][c] = total - (row strip excluded by the tap) - (column strip excluded by the tap) + (their common corner).
+// One block = 32 channels x 8 strips; the chunk partials of a (strip, channel) are summed by one thread with all loads of an
+// 8-chunk group issued before the first add (64 dependent L2 round trips per thread made the first version 88 us per launch).
+__global__ void __launch_bounds__(256) border_finish_kernel(const float* __restrict__ raw, const float* __restrict__ total, float* __restrict__ sdz,
+                                                            int C, int chunks) {
+  __shared__ double r[8][32];
+  const int lane = threadIdx.x & 31, s = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (c < C) {
+    for (int k0 = 0; k0 < chunks; k0 += 8) {
+      float v[8];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) r[s] += (double)raw[((size_t)k * 8 + s) * C + c];
-  const double tot = (double)total[c];
-  for (int dy = 0; dy < 3; ++dy)
-    for (int dx = 0; dx < 3; ++dx) {
-      double v = tot;
-      if (dy == 0) v -= r[0];
-      if (dy == 2) v -= r[1];
-      if (dx == 0) v -= r[2];
-      if (dx == 2) v -= r[3];
-      if (dy != 1 && dx != 1) v += r[4 + (dy == 2 ? 2 : 0) + (dx == 2 ? 1 : 0)];
-      sdz[(size_t)(dy * 3 + dx) * C + c] = (float)v;
+      for (int u = 0; u < 8; ++u) v[u] = (k0 + u < chunks) ? __ldg(raw + ((size_t)(k0 + u) * 8 + s) * C + c) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += (double)v[u];
     }
+  }
+  r[s][lane] = acc;
+  __syncthreads();
+  if (c >= C) return;
+  const double tot = (double)total[c];
+  for (int tap = s; tap < 9; tap += 8) {
+    const int dy = tap / 3, dx = tap % 3;
+    double v = tot;
+    if (dy == 0) v -= r[0][lane];
+    if (dy == 2) v -= r[1][lane];
+    if (dx == 0) v -= r[2][lane];
+    if (dx == 2) v -= r[3][lane];
+    if (dy != 1 && dx != 1) v += r[4 + (dy == 2 ? 2 : 0) + (dx == 2 ? 1 : 0)][lane];
+    sdz[(size_t)tap * C + c] = (float)v;
+  }
 }
 
 __global__ void __launch_bounds__(TPB) wgrad_fold_fix_kernel(float* __restrict__ dw, const float* __restrict__ scale,
@@ -228,7 +241,7 @@ int ub_border_sums(const void* dz, const float* total, float* sdz, float* scratc
   else if (dtype == UB_F32) border_strips_kernel<float><<<grid, TPB, 0, stream>>>((const float*)dz, scratch, N, H, W, C);
   else UB_CHECK_ARG(false, "border_sums: bad dtype %d", dtype);
   UB_LAUNCH_CHECK();
-  border_finish_kernel<<<(C + 127) / 128, 128, 0, stream>>>(scratch, total, sdz, C, chunks);
+  border_finish_kernel<<<(C + 31) / 32, 256, 0, stream>>>(scratch, total, sdz, C, chunks);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_tiles_kernel(const float* 
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[q][i] = b[i];
     const int sx = ox + w0;
-    const bool vec = (sx + 4 <= img_w) && (((pitch | sx) & 3) == 0);
+    const bool vec = (sx + 4 <= img_w) && (((pitch | plane_stride | sx) & 3) == 0);      // 16-byte aligned rows in every channel plane
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
       const float* xp = img + (long long)ci * plane_stride;
@@ -886,7 +886,8 @@ int ub_conv_first_fwd_affine_tiles(const float* img, const int* origin_yx, int i
   UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0 && W % 4 == 0, "conv_first_fwd_affine_tiles: tile width must be a multiple of 4 (got %d x %d)", H, W);
   UB_CHECK_SHAPE(img_h >= 2 && img_w >= 2 && row_pitch >= img_w, "conv_first_fwd_affine_tiles: bad image extent %d x %d, pitch %lld", img_h, img_w,
                  row_pitch);
-  UB_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && plane_stride % 4 == 0, "conv_first_fwd_affine_tiles: image must be 16-byte aligned");
+  UB_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0, "conv_first_fwd_affine_tiles: image base must be 16-byte aligned");
+  UB_CHECK_ARG(Cin == 1 || plane_stride >= (long long)img_h * row_pitch, "conv_first_fwd_affine_tiles: channel planes overlap");
   const long long P = (long long)N * H * W;
   const int grid = grid_for(P / 4, 32 * 4, UB_STATS_ROWS);
   UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_tiles_kernel<T, CIN><<<grid, TPB, 0, stream>>>(img, origin_yx, img_h, img_w, row_pitch, plane_stride,

@@ -79,10 +79,10 @@ class UNet:
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
         self.fuse_bn_reduce_ew = os.environ.get("UB_FUSE_EW", "0") == "1"   # ... and in the pool-backward / head-backward passes
-        # bf16 training forward with the producers' BatchNorm folded into the consumer convolutions (_forward_train_folded).
-        # Written at the end of round 1: kernels compiled and parity cases in tests/kernel_cases.py PENDING_CASES, not yet run on a
-        # B200 -- stays off until they have been.
-        self.fold_bn = os.environ.get("UB_FOLD_BN", "0") == "1"
+        # bf16 training forward with the producers' BatchNorm folded into the consumer convolutions (_forward_train_folded):
+        # 17 of the 22 BatchNorm-apply passes disappear.  Parity green on B200 (fold_* cases), 23.91 -> 22.75 ms per config-2 step
+        # (profiles/r02_fold_ab.md); UB_FOLD_BN=0 restores the y-materialising forward for A/B runs.
+        self.fold_bn = os.environ.get("UB_FOLD_BN", "1") == "1"
         self._build_layout()
         self.class_weights = None
         if class_weights is not None:
@@ -675,7 +675,9 @@ class UNet:
         cur = self._b("y:enc1a")
         if view is not None:
             img, img_h, img_w, origins = view
-            self._call("ub_conv_first_fwd_affine_tiles", img, origins, img_h, img_w, img.stride(1), img.stride(0),
+            pitch = img.stride(1)
+            plane = img.stride(0) if img.shape[0] > 1 else img.shape[1] * pitch      # the stride of a size-1 dimension is arbitrary
+            self._call("ub_conv_first_fwd_affine_tiles", img, origins, img_h, img_w, pitch, plane,
                        self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], sc, sh, cur, N, H, W, self.number_channels, self.act_code)
         else:
             self._call("ub_conv_first_fwd_affine", x, self.P[L.off_w:L.off_w + L.n_w], self.P[L.off_b:L.off_b + L.cout], sc, sh, cur,

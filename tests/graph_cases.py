@@ -192,7 +192,7 @@ def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=Fals
             return r
     # ---- noise-floor criterion against the bf16-storage emulation of the oracle (module docstring)
     taps = {}
-    emu = O.train_step_grads(p, xt, oht, gb, dmt, taps=taps, storage="bf16")
+    emu = O.train_step_grads(p, xt, oht, gb, dmt, taps=taps, storage="bf16_fold" if m.fold_bn else "bf16")      # same storage points as the path under test
     relu_e, pool_e = oracle_pattern(taps, dmt)
     refe = O.train_step_grads(p, xt, oht, gb, dmt, relu_masks=relu_e, pool_idx=pool_e)
     sme = emu["softmax"].numpy()
@@ -649,11 +649,25 @@ def case_reader_augmented():
     return r
 
 
-def _with_fold(fn):
-    """run a graph case with the folded-BatchNorm training forward (UNet.fold_bn via UB_FOLD_BN=1)"""
+def case_config1_refdata(steps=60):
+    """BASELINE.json configs[0]: the reference's own data/ fixture (100 image / mask pairs) through unetb200.build_lmdb, then batch-8
+    training -- the CUDA path's loss curve against the oracle's curve on the same records, weights, dropout masks and order
+    (tools/config1.py; the oracle curve is the committed fixture tests/golden/config1_oracle_curve.json).  The database is derived
+    from the reference's data and is not committed: it is built in the development container (`tools/config1.py prepare`) and travels
+    with the working tree; where it is absent the case reports `skipped`."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import config1
+    if not os.path.exists(os.path.join(config1.REF, "train-HES.lmdb", "data.mdb")) or not os.path.exists(config1.CURVE):
+        return dict(ok=True, skipped="tests/golden/_refdata not present (built from /root/reference/data by tools/config1.py prepare)")
+    return config1.cuda(steps)
+
+
+def _with_fold(fn, value="0"):
+    """run a graph case with UB_FOLD_BN=value: "0" = the y-materialising training forward (every BatchNorm output written), the
+    default ("1") folds the producers' BatchNorm into the consumer convolutions (UNet.fold_bn)"""
     def run():
         old = os.environ.get("UB_FOLD_BN")
-        os.environ["UB_FOLD_BN"] = "1"
+        os.environ["UB_FOLD_BN"] = value
         try:
             return fn()
         finally:
@@ -701,7 +715,7 @@ PROBE_CASES = {
     "probe_256_n2": lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, floor=True),
     "probe_256_n4_learn": lambda: case_live("bf16", N=4, C=1, H=256, W=256, K=2, seed=4, learn=True, floor=True),
     "probe_trained": lambda: case_trained(),
-    "probe_fold_256_n2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, floor=True)),
+    "probe_nofold_256_n2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, floor=True)),
 }
 
 
@@ -728,12 +742,14 @@ CASES = {
     "wellcond_bf16_n2_256": lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256),
     # ... and at trained weights: north_star's 1e-2 / 99.9 %
     "trained_bf16": case_trained,
+    # the reference's data/ fixture -> build_lmdb -> 60 training steps, loss curve vs the oracle's
+    "config1_refdata": case_config1_refdata,
     # row-band sharded inference == tile-sharded inference on one rank
     "banded_inference": case_banded_inference,
-    # BatchNorm folded into the consumer convolutions (UB_FOLD_BN=1)
-    "fold_live_bf16_c1k2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True)),
-    "fold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True)),
-    "fold_wellcond_bf16_n2_256": _with_fold(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256)),
-    "fold_golden_c1_k2_bf16": _with_fold(lambda: case_golden("graph_c1_k2", "bf16")),
-    "fold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=200)),
+    # the y-materialising training forward (UB_FOLD_BN=0; the default folds BatchNorm into the consumer convolutions)
+    "nofold_live_bf16_c1k2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True)),
+    "nofold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True)),
+    "nofold_wellcond_bf16_n2_256": _with_fold(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256)),
+    "nofold_golden_c1_k2_bf16": _with_fold(lambda: case_golden("graph_c1_k2", "bf16")),
+    "nofold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=100)),
 }

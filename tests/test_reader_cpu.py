@@ -47,6 +47,35 @@ def test_lmdb_roundtrip_large_values_and_multilevel_tree(tmp_path):
         L.write(str(tmp_path / "dup"), [(b"a", b"1"), (b"a", b"2")])
 
 
+def test_image_mask_pair_against_the_reference_descriptor():
+    """encode_pair / decode_pair against the reference's OWN message definition: the serialized descriptor embedded in
+    UNet/isg_ai_pb2.py:22 (fixture tests/golden/isg_ai_descriptor.bin, extracted by tests/golden/make_descriptor.py), loaded through
+    descriptor_pool.AddSerializedFile -- the records build_lmdb.py:44-59 writes and imagereader.py:269-281 parses."""
+    import os
+    from google.protobuf import descriptor_pool, message_factory
+    raw = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "isg_ai_descriptor.bin"), "rb").read()
+    pool = descriptor_pool.DescriptorPool()
+    pool.AddSerializedFile(raw)
+    cls = message_factory.GetMessageClass(pool.FindMessageTypeByName("isg_ai.ImageMaskPair"))
+    rng = np.random.default_rng(3)
+    for img, mask in [(rng.integers(0, 65535, size=(32, 48, 1)).astype(np.uint16), rng.integers(0, 2, size=(32, 48)).astype(np.uint8)),
+                      (rng.integers(0, 255, size=(16, 16, 3)).astype(np.uint8), rng.integers(0, 8, size=(16, 16)).astype(np.uint8))]:
+        # the writer of the reference (build_lmdb.py:44-59)
+        ref = cls()
+        ref.channels, ref.img_height, ref.img_width = img.shape[2], img.shape[0], img.shape[1]
+        ref.image, ref.mask = img.tobytes(), mask.tobytes()
+        ref.img_type, ref.mask_type = img.dtype.str, mask.dtype.str
+        ref.labels = np.unique(mask).astype(np.uint8).tobytes()
+        theirs = ref.SerializeToString()
+        mine = R.encode_pair(img, mask)
+        assert mine == theirs                                         # byte-identical record
+        d = R.decode_pair(theirs)                                     # and the reference's bytes parse with the hand-written codec
+        got = np.frombuffer(d["image"], dtype=d["img_type"]).reshape(d["img_height"], d["img_width"], d["channels"])
+        assert np.array_equal(got, img) and np.array_equal(np.frombuffer(d["mask"], dtype=d["mask_type"]).reshape(mask.shape), mask)
+        back = cls.FromString(mine)                                   # the reader of the reference (imagereader.py:269-281)
+        assert np.array_equal(np.frombuffer(back.image, dtype=back.img_type).reshape(back.img_height, back.img_width, back.channels), img)
+
+
 def test_image_mask_pair_wire_format_matches_protobuf_runtime():
     """encode_pair / decode_pair against google.protobuf's own encoder for the message of UNet/isg_ai.proto:16-31
     (descriptor rebuilt here field by field; the reference's generated module is not importable under protobuf >= 4)"""

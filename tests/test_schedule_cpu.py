@@ -65,9 +65,10 @@ def _count(names):
 
 
 @pytest.mark.parametrize("overlap", [False, True])
-def test_default_training_schedule(overlap):
+def test_unfolded_training_schedule(overlap):
     m = DryUNet(2, 1, 1, precision="bf16", seed=0)
     m.overlap_wgrad = overlap
+    m.fold_bn = False                     # UB_FOLD_BN=0: every BatchNorm output is materialised
     c = _count(_step(m))
     assert c["ub_conv3x3_fwd"] == 17 and c["ub_conv_first_fwd"] == 1 and c["ub_deconv2x2_fwd"] == 4 and c["ub_head_fwd"] == 1
     assert c["ub_conv3x3_wgrad"] == 17 and c["ub_deconv2x2_wgrad"] == 4 and c["ub_conv_first_wgrad"] == 1
@@ -85,10 +86,11 @@ def test_default_training_schedule(overlap):
 def test_optional_schedules():
     m = DryUNet(2, 1, 1, precision="bf16", seed=0)
     m.fuse_bn_reduce_ew = True
+    m.fold_bn = False
     c = _count(_step(m))
     assert c["ub_maxpool2x2_bwd_add_bnred"] == 4 and c["ub_head_bwd_apply_bnred"] == 1 and "ub_maxpool2x2_bwd_add" not in c
     m = DryUNet(2, 1, 1, precision="bf16", seed=0)
-    m.fold_bn = True
+    assert m.fold_bn                      # the default schedule folds BatchNorm into the consumer convolutions
     names = _step(m)
     c = _count(names)
     # 17 producers lose their BatchNorm-apply pass (13 conv/deconv layers, enc1b-3b behind a y-less pool, dec1b behind the folded
