@@ -52,6 +52,13 @@ long long ub_host_crc32c(const void* data, long long n, long long crc);
  * partial[UB_STATS_ROWS][2][Cout] sum / sum-of-squares of the activated output for the BatchNorm of model.py:36. */
 int ub_conv3x3_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, void* out,
                    float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream);
+/* The same forward (bias_cases != 0: `bias` is the [9][Cout] border-case table of ub_conv3x3_fwd_cases) followed IN THE SAME LAUNCH by
+ * the finalisation of the BatchNormalization that follows the conv (UNet/model.py:36): the last CTA to finish reduces the partial rows
+ * in a fixed order (fp64) and writes mean / rstd (biased variance, eps) and the momentum update of the moving statistics (unbiased
+ * variance; nullable) -- no separate ub_bn_finalize launch.  counter: one zero-initialised device word, left zero. */
+int ub_conv3x3_fwd_bn(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, int bias_cases, void* out,
+                      float* stats, int N, int H, int W, int Cout, int relu, float* mean, float* rstd, float* moving_mean,
+                      float* moving_var, float momentum, float eps, unsigned int* counter, cudaStream_t stream);
 /* Gradient w.r.t. the conv input (tape.gradient, UNet/model.py:219).  w_t = ub_transpose_pack(w, flip=1).
  * Channels [0,C0) go to dx0 and [C0,C0+C1) to dx1 (gradient of the concat; C1 == 0 or C1 == C0). */
 int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H,
@@ -69,6 +76,10 @@ int ub_conv3x3_wgrad(const void* x0, int C0, const void* x1, int C1, const void*
  * stats: partial[UB_STATS_ROWS][2][4*Cout] (finalise with groups = 4). */
 int ub_deconv2x2_fwd(const void* x, int Cin, const void* w, const float* bias, void* out, float* stats, int N, int h,
                      int w_in, int Cout, cudaStream_t stream);
+/* ... with the BatchNormalization of UNet/model.py:47 finalised by the last CTA (see ub_conv3x3_fwd_bn). */
+int ub_deconv2x2_fwd_bn(const void* x, int Cin, const void* w, const float* bias, void* out, float* stats, int N, int h, int w_in,
+                        int Cout, float* mean, float* rstd, float* moving_mean, float* moving_var, float momentum, float eps,
+                        unsigned int* counter, cudaStream_t stream);
 int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int w_in,
                        cudaStream_t stream);
 long long ub_deconv2x2_wgrad_workspace_bytes(int Cin, int Cout, int N, int h, int w_in);

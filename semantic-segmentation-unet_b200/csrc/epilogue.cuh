@@ -30,7 +30,47 @@ struct EpiParams {
   float* red_out;            // [UB_STATS_ROWS][2][red_ncols]
   int red_blk_begin;         // first 64-column block of the output that belongs to the BatchNorm'd tensor (concat dgrad: C0 / 64)
   int red_ncols;
+  // FIN (forward with statistics): the LAST CTA to finish sums the partial rows of every column in a fixed order (fp64) and
+  // finalises the BatchNorm that follows -- mean, rstd and the moving statistics -- so that no separate ub_bn_finalize launch (and
+  // no zero-fill of unused partial rows) sits between this kernel and its consumer.  fin_counter: zero-initialised, reset by the
+  // last CTA.  Channel c gathers the columns g * (ncols / fin_groups) + c (deconv: 4 column groups per channel).
+  float* fin_mean;           // null = off
+  float* fin_rstd;
+  float* fin_moving_mean;    // nullable
+  float* fin_moving_var;
+  unsigned int* fin_counter;
+  double fin_count;          // samples per channel (N * H * W of the BatchNorm'd tensor)
+  float fin_momentum, fin_eps;
+  int fin_groups;
+  int fin_rows;              // partial rows written by this launch (gridDim.x / n_tiles)
 };
+
+// host-side description of the BatchNorm a forward launch finalises itself (EpiParams::fin_*)
+struct BnFin {
+  float* mean;
+  float* rstd;
+  float* moving_mean;
+  float* moving_var;
+  double count;
+  float momentum, eps;
+  int groups;
+  unsigned int* counter;
+};
+inline void epi_set_fin(EpiParams& ep, const BnFin& f, int rows) {
+  ep.fin_mean = f.mean;
+  ep.fin_rstd = f.rstd;
+  ep.fin_moving_mean = f.moving_mean;
+  ep.fin_moving_var = f.moving_var;
+  ep.fin_counter = f.counter;
+  ep.fin_count = f.count;
+  ep.fin_momentum = f.momentum;
+  ep.fin_eps = f.eps;
+  ep.fin_groups = f.groups;
+  ep.fin_rows = rows;
+}
+
+// bytes of epilogue scratch the fused finalise needs: 256 x 8 doubles of row-lane partials + 2 x ncols doubles of column totals
+__host__ __device__ constexpr int epi_fin_bytes(int ncols) { return 256 * 8 * 8 + 2 * ncols * 8; }
 
 // RED: 0 = off, 1 = one `a`-tile buffer (fetched at the start of its part), 2 = two buffers (fetched one part ahead)
 // CASEB: the bias is a [9][ncols] table indexed by the pixel's border case (3 row cases x 3 column cases) -- the forward
@@ -322,6 +362,87 @@ struct Epilogue {
         for (int g = 0; g < ROW_GROUPS; ++g) t += st[(g * 2 + which) * BLOCK_N + c];
         ep.stats[((size_t)stats_row * 2 + which) * ep.ncols + n_tile * BLOCK_N + c] = t;
       }
+      if (ep.fin_mean) finalize_last_cta(st);
     }
+  }
+
+  // see EpiParams::fin_*.  Called by all epilogue threads after this CTA's partial row has been written.
+  __device__ __forceinline__ void finalize_last_cta(float* scratch) {
+    __threadfence();                                   // this thread's partial-row stores are visible device-wide ...
+    named_bar_sync(1, EPI_THREADS);
+    volatile unsigned int* slot = reinterpret_cast<volatile unsigned int*>(scratch);
+    if (et == 0) *slot = atomicAdd(ep.fin_counter, 1u);   // ... before this CTA is counted as done
+    named_bar_sync(1, EPI_THREADS);
+    const unsigned int ticket = *slot;
+    if (ticket != gridDim.x - 1) return;               // uniform over the CTA
+    __threadfence();
+    named_bar_sync(1, EPI_THREADS);                    // everyone has read the ticket before the scratch is reused
+    const int ncols = ep.ncols, rows = ep.fin_rows;
+    const int Q = ncols >> 2;                          // float4 column quads (ncols is a multiple of 64)
+    const int QC = Q < EPI_THREADS ? Q : EPI_THREADS;  // quads handled concurrently; Q and EPI_THREADS are powers of two or Q > 256
+    const int RL = EPI_THREADS / QC;                   // row lanes per quad (1 when Q >= 256)
+    double* part = reinterpret_cast<double*>(scratch);                 // [RL][QC][8]
+    double* tot = part + EPI_THREADS * 8;                              // [2][ncols]
+    const int q0 = et % QC, rl = et / QC;
+    for (int q = q0; q < Q; q += QC) {
+      double acc[8] = {};
+      if (rl < RL) {
+        for (int r0 = rl; r0 < rows; r0 += RL * 4) {
+          float4 v[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * RL;
+            if (r < rows) {
+              v[u][0] = __ldcg(reinterpret_cast<const float4*>(ep.stats + ((size_t)r * 2 + 0) * ncols) + q);
+              v[u][1] = __ldcg(reinterpret_cast<const float4*>(ep.stats + ((size_t)r * 2 + 1) * ncols) + q);
+            } else {
+              v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc[0] += (double)v[u][0].x; acc[1] += (double)v[u][0].y; acc[2] += (double)v[u][0].z; acc[3] += (double)v[u][0].w;
+            acc[4] += (double)v[u][1].x; acc[5] += (double)v[u][1].y; acc[6] += (double)v[u][1].z; acc[7] += (double)v[u][1].w;
+          }
+        }
+      }
+      if (RL > 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) part[((size_t)rl * QC + q0) * 8 + i] = acc[i];
+        named_bar_sync(1, EPI_THREADS);                // RL > 1 implies Q <= 128: one pass of the q loop, the barrier is uniform
+        if (rl == 0) {
+          for (int l = 1; l < RL; ++l)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += part[((size_t)l * QC + q0) * 8 + i];
+        }
+      }
+      if (rl == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tot[q * 4 + i] = acc[i];
+          tot[ncols + q * 4 + i] = acc[4 + i];
+        }
+      }
+    }
+    named_bar_sync(1, EPI_THREADS);
+    const int C = ncols / ep.fin_groups;
+    for (int c = et; c < C; c += EPI_THREADS) {
+      double sum = 0.0, sq = 0.0;
+      for (int g = 0; g < ep.fin_groups; ++g) {
+        sum += tot[g * C + c];
+        sq += tot[ncols + g * C + c];
+      }
+      const double mu = sum / ep.fin_count;
+      double var = sq / ep.fin_count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      ep.fin_mean[c] = (float)mu;
+      ep.fin_rstd[c] = (float)(1.0 / sqrt(var + (double)ep.fin_eps));
+      if (ep.fin_moving_mean) {
+        const double unb = ep.fin_count > 1.0 ? var * (ep.fin_count / (ep.fin_count - 1.0)) : var;
+        ep.fin_moving_mean[c] = ep.fin_momentum * ep.fin_moving_mean[c] + (1.f - ep.fin_momentum) * (float)mu;
+        ep.fin_moving_var[c] = ep.fin_momentum * ep.fin_moving_var[c] + (1.f - ep.fin_momentum) * (float)unb;
+      }
+    }
+    if (et == 0) *ep.fin_counter = 0u;                 // ready for the next launch
   }
 };

@@ -55,6 +55,7 @@ struct Conv3Params {
   int ncols;
   int b_resident;
   const void* w_base;        // host-side only: weight matrix [ncols][9 * Cin] for the tensor map
+  const BnFin* fin;          // host-side only: BatchNorm to finalise in the last CTA (forward with statistics), or null
 };
 
 template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED, int CASEB = 0>
@@ -284,10 +285,17 @@ int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_
   if (grid <= 0) grid = p.n_tiles;
   if (grid > total) grid = total;            // total is a multiple of n_tiles
   UB_CHECK_SHAPE(grid / p.n_tiles <= UB_STATS_ROWS, "conv3: stats rows");
-  if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  const BnFin* fin = p.fin;
+  p.fin = nullptr;
+  const bool fused = fin && p.ep.stats && epi_fin_bytes(p.ncols) <= OUT_BUFS * L::E::OUT_BYTES;
+  if (fused) epi_set_fin(p.ep, *fin, (int)(grid / p.n_tiles));           // the last CTA reads exactly the rows this grid writes: no zero-fill
+  else if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
   if (RED) UB_CUDA(cudaMemsetAsync(p.ep.red_out, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ep.red_ncols, stream));
   kern<<<(int)grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);
   UB_LAUNCH_CHECK();
+  if (fin && !fused)
+    return ub_bn_finalize(p.ep.stats, p.ncols, fin->groups, (long long)fin->count, fin->mean, fin->rstd, fin->moving_mean, fin->moving_var,
+                          fin->momentum, fin->eps, stream);
   return UB_OK;
 }
 
@@ -348,9 +356,10 @@ int out_map(CUtensorMap* m, const void* base, int C, int W, int H, int N) {
 // Called by the extern "C" entry points in igemm_fwd.cu.
 int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* post_scale,
                       const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream,
-                      int bias_cases) {
+                      int bias_cases, const BnFin* fin) {
   Conv3Params p;
   memset(&p, 0, sizeof(p));
+  p.fin = fin;
   int rc;
   const void* a_base[2] = {x0, x1};
   const int a_ch[2] = {C0, C1};

@@ -43,6 +43,7 @@ struct IgemmFwdParams {
   int blocks_per_omap;
   EpiParams ep;       // bias (index = column % bias_mod), relu, stats [UB_STATS_ROWS][2][ncols]
   int ncols;
+  const BnFin* fin;   // host-side only: BatchNorm to finalise in the last CTA (forward with statistics), or null
 };
 
 template <int BLOCK_N, int STAGES>
@@ -210,9 +211,16 @@ int launch_t(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
   if (grid <= 0) grid = p.n_tiles;
   if (grid > p.total_tiles) grid = p.total_tiles;
   UB_CHECK_SHAPE(grid / p.n_tiles <= UB_STATS_ROWS, "igemm: stats rows");
-  if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  const BnFin* fin = p.fin;
+  p.fin = nullptr;
+  const bool fused = fin && p.ep.stats && epi_fin_bytes(p.ncols) <= L::E::OUT_BYTES;
+  if (fused) epi_set_fin(p.ep, *fin, grid / p.n_tiles);
+  else if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
   kern<<<grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);
   UB_LAUNCH_CHECK();
+  if (fin && !fused)
+    return ub_bn_finalize(p.ep.stats, p.ncols, fin->groups, (long long)fin->count, fin->mean, fin->rstd, fin->moving_mean, fin->moving_var,
+                          fin->momentum, fin->eps, stream);
   return UB_OK;
 }
 
@@ -252,7 +260,7 @@ int strided_map(CUtensorMap* m, const void* base, int C, int w, int h, int N, in
 // halo-patch kernels (igemm_conv3.cu)
 int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, const float* post_scale,
                       const float* post_shift, void* out, float* stats, int N, int H, int W, int Cout, int relu, cudaStream_t stream,
-                      int bias_cases = 0);
+                      int bias_cases = 0, const BnFin* fin = nullptr);
 int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C0, void* dx1, int C1, int N, int H, int W,
                         const void* red_a, const float* red_mean, const float* red_rstd, float* red_partial, cudaStream_t stream);
 static bool legacy_conv3() {
@@ -353,7 +361,7 @@ int ub_conv3x3_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, int C
 }
 
 static int deconv_fwd_impl(const void* x, int Cin, const void* w, const float* bias, const float* scale, const float* shift, void* out,
-                           float* stats, int N, int h, int wd, int Cout, cudaStream_t stream);
+                           float* stats, int N, int h, int wd, int Cout, cudaStream_t stream, const BnFin* fin = nullptr);
 
 /* dgrad fused with the backward-BatchNorm reduction of the tensor whose gradient it writes (the last output: dx1 of a
  * concat dgrad, else dx0): partial[UB_STATS_ROWS][2][C] = {sum dy, rstd * sum dy * (a - mean)} -- replaces ub_bn_bwd_reduce */
@@ -376,8 +384,44 @@ int ub_deconv2x2_fwd_affine(const void* x, int Cin, const void* w, const float* 
   return deconv_fwd_impl(x, Cin, w, bias, scale, shift, out, nullptr, N, h, wd, Cout, stream);
 }
 
+static BnFin make_fin(float* mean, float* rstd, float* moving_mean, float* moving_var, double count, float momentum, float eps, int groups,
+                      unsigned int* counter) {
+  BnFin f;
+  f.mean = mean;
+  f.rstd = rstd;
+  f.moving_mean = moving_mean;
+  f.moving_var = moving_var;
+  f.count = count;
+  f.momentum = momentum;
+  f.eps = eps;
+  f.groups = groups;
+  f.counter = counter;
+  return f;
+}
+
+int ub_conv3x3_fwd_bn(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias, int bias_cases, void* out, float* stats,
+                      int N, int H, int W, int Cout, int relu, float* mean, float* rstd, float* moving_mean, float* moving_var, float momentum,
+                      float eps, unsigned int* counter, cudaStream_t stream) {
+  UB_CHECK_ARG(x0 && w && out && stats && mean && rstd && counter && (!bias_cases || bias), "conv3x3_fwd_bn: null pointer");
+  UB_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "conv3x3_fwd_bn: moving_mean and moving_var go together");
+  UB_CHECK_SHAPE(C0 > 0 && C0 % 64 == 0 && C1 >= 0 && C1 % 64 == 0 && Cout % 64 == 0 && (C1 == 0 || x1),
+                 "conv3x3_fwd_bn: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0 && (!bias_cases || (H >= 2 && W >= 2)), "conv3x3_fwd_bn: bad N/H/W");
+  const BnFin f = make_fin(mean, rstd, moving_mean, moving_var, (double)N * H * W, momentum, eps, 1, counter);
+  return ub_conv3_halo_fwd(x0, C0, x1, C1, w, bias, nullptr, nullptr, out, stats, N, H, W, Cout, relu, stream, bias_cases ? 1 : 0, &f);
+}
+
+int ub_deconv2x2_fwd_bn(const void* x, int Cin, const void* w, const float* bias, void* out, float* stats, int N, int h, int wd, int Cout,
+                        float* mean, float* rstd, float* moving_mean, float* moving_var, float momentum, float eps, unsigned int* counter,
+                        cudaStream_t stream) {
+  UB_CHECK_ARG(stats && mean && rstd && counter, "deconv2x2_fwd_bn: null pointer");
+  UB_CHECK_ARG((moving_mean == nullptr) == (moving_var == nullptr), "deconv2x2_fwd_bn: moving_mean and moving_var go together");
+  const BnFin f = make_fin(mean, rstd, moving_mean, moving_var, 4.0 * N * h * wd, momentum, eps, 4, counter);
+  return deconv_fwd_impl(x, Cin, w, bias, nullptr, nullptr, out, stats, N, h, wd, Cout, stream, &f);
+}
+
 static int deconv_fwd_impl(const void* x, int Cin, const void* w, const float* bias, const float* scale, const float* shift, void* out,
-                           float* stats, int N, int h, int wd, int Cout, cudaStream_t stream) {
+                           float* stats, int N, int h, int wd, int Cout, cudaStream_t stream, const BnFin* fin) {
   UB_CHECK_ARG(x && w && out, "deconv2x2_fwd: null pointer");
   UB_CHECK_SHAPE(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "deconv2x2_fwd: channels must be multiples of 64");
   IgemmFwdParams p;
@@ -401,6 +445,7 @@ static int deconv_fwd_impl(const void* x, int Cin, const void* w, const float* b
   p.ep.relu = 0;
   p.ep.stats = stats;
   p.ncols = ncols;
+  p.fin = fin;
   return launch(p, N, stream);
 }
 

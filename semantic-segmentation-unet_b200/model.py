@@ -78,6 +78,7 @@ class UNet:
         self._graphs = {}
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
+        self.fuse_finalize = os.environ.get("UB_FUSE_FINALIZE", "1") == "1"   # bf16 path: the forward's last CTA finalises the BatchNorm statistics
         self.fuse_bn_reduce_ew = os.environ.get("UB_FUSE_EW", "0") == "1"   # ... and in the pool-backward / head-backward passes
         # bf16 training forward with the producers' BatchNorm folded into the consumer convolutions (_forward_train_folded):
         # 17 of the 22 BatchNorm-apply passes disappear.  Parity green on B200 (fold_* cases), 23.91 -> 22.75 ms per config-2 step
@@ -199,6 +200,7 @@ class UNet:
         self.partial_red = torch.zeros(_C.UB_STATS_ROWS * 2 * 1024, dtype=torch.float32, device=dev)   # BN-backward sums produced by a fused dgrad
         self._red_ready = None                                                                          # layer whose sums partial_red holds
         self.red = torch.zeros(4096, dtype=torch.float32, device=dev)
+        self.fin_counter = torch.zeros(4, dtype=torch.int32, device=dev)           # ub_*_fwd_bn: CTAs done (left zero by every launch)
 
     def trainable_count(self):
         return sum(L.n_w + 3 * L.cout for L in self.layers.values())
@@ -481,6 +483,9 @@ class UNet:
         a = self._b("a:" + L.name)
         bias = self.P[L.off_b:L.off_b + L.cout]
         L.c0, L.c1 = c0, c1
+        if self.precision == "bf16" and training and self.fuse_finalize:
+            self._conv_fwd_bn(L, x0, c0, x1, c1, self._wptr(L), bias, 0, a, N, h, w)
+            return a
         if self.precision == "bf16":
             self._call("ub_conv3x3_fwd", x0, c0, x1, c1, self._wptr(L), bias, a, self.partial if training else None,
                        N, h, w, L.cout, 1)
@@ -491,6 +496,13 @@ class UNet:
         if training:
             self._finalize(L, L.cout, 1, N * h * w)
         return a
+
+    def _conv_fwd_bn(self, L, x0, c0, x1, c1, wt, bias, bias_cases, a, N, h, w):
+        """conv3x3 + bias + relu and, in the same launch, the batch statistics -> mean / rstd / moving statistics of the BatchNorm that
+        follows (the last CTA finalises: no ub_bn_finalize launch, no zero-fill of partial rows)"""
+        o, c = L.off_stat, L.cout
+        self._call("ub_conv3x3_fwd_bn", x0, c0, x1, c1, wt, bias, bias_cases, a, self.partial, N, h, w, L.cout, 1,
+                   self.mean[o:o + c], self.rstd[o:o + c], self.MM[o:o + c], self.MV[o:o + c], BN_MOMENTUM, BN_EPS, self.fin_counter)
 
     def _bn_apply(self, L, N, h, w, training, drop=None, pool_lvl=None):
         self._cur = L.name
@@ -503,6 +515,11 @@ class UNet:
             self._call("ub_bn_apply_pool", a, y, self._b(f"pool{pool_lvl}"), self._b(f"idx{pool_lvl}"), mean, rstd, gamma, beta,
                        drop, N, h, w, L.cout, self.act_code)
         return y
+
+    def _deconv_fwd_bn(self, Lu, x, z, N, hi, wi):
+        o, c = Lu.off_stat, Lu.cout
+        self._call("ub_deconv2x2_fwd_bn", x, Lu.cin, self._wptr(Lu), self.P[Lu.off_b:Lu.off_b + c], z, self.partial, N, hi, wi, c,
+                   self.mean[o:o + c], self.rstd[o:o + c], self.MM[o:o + c], self.MV[o:o + c], BN_MOMENTUM, BN_EPS, self.fin_counter)
 
     def _forward(self, x, N, H, W, training, drop_masks=None, view=None):
         """x: fp32 NCHW device tensor, contiguous.  Leaves y:dec1b ready for the head; returns nothing.
@@ -559,7 +576,9 @@ class UNet:
             self._cur = Lu.name
             z = self._b("a:" + Lu.name)
             bias = self.P[Lu.off_b:Lu.off_b + Lu.cout]
-            if self.precision == "bf16":
+            if self.precision == "bf16" and training and self.fuse_finalize:
+                self._deconv_fwd_bn(Lu, cur, z, N, hi, wi)
+            elif self.precision == "bf16":
                 self._call("ub_deconv2x2_fwd", cur, Lu.cin, self._wptr(Lu), bias, z, self.partial if training else None,
                            N, hi, wi, Lu.cout)
                 if training:
@@ -597,6 +616,9 @@ class UNet:
             return mean, rstd, gamma, beta
 
         self._call("ub_fold_conv3_weights", self._w(L), L.cout, c0, *vecs(p0), c1, *vecs(p1), self.P[L.off_b:L.off_b + L.cout], wf, b9, sc, sh)
+        if self.fuse_finalize:
+            self._conv_fwd_bn(L, x0, c0, x1, c1, wf, b9, 1, a, N, h, w)
+            return a
         self._call("ub_conv3x3_fwd_cases", x0, c0, x1, c1, wf, b9, a, self.partial, N, h, w, L.cout, 1)
         self._finalize(L, L.cout, 1, N * h * w)
         return a
@@ -638,9 +660,12 @@ class UNet:
             h, w = self._dims(H, W, lvl)
             Lu, La, Lb = Ls[f"up{lvl}"], Ls[f"dec{lvl}a"], Ls[f"dec{lvl}b"]
             self._cur = Lu.name
-            self._call("ub_deconv2x2_fwd", cur, Lu.cin, self._wptr(Lu), self.P[Lu.off_b:Lu.off_b + Lu.cout], self._b("a:" + Lu.name), self.partial,
-                       N, hi, wi, Lu.cout)
-            self._finalize(Lu, 4 * Lu.cout, 4, N * h * w)
+            if self.fuse_finalize:
+                self._deconv_fwd_bn(Lu, cur, self._b("a:" + Lu.name), N, hi, wi)
+            else:
+                self._call("ub_deconv2x2_fwd", cur, Lu.cin, self._wptr(Lu), self.P[Lu.off_b:Lu.off_b + Lu.cout], self._b("a:" + Lu.name), self.partial,
+                           N, hi, wi, Lu.cout)
+                self._finalize(Lu, 4 * Lu.cout, 4, N * h * w)
             # concat [skip, up] (model.py:117): both BatchNorms are folded, except the level-4 skip (dropout: a real y tensor)
             Ls_skip = Ls[f"enc{lvl}b"]
             if lvl == 4:

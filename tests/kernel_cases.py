@@ -907,6 +907,82 @@ def case_conv3x3_layer(C0, C1, Cout, N, H, W, seed=30, n_ci=6):
     return r
 
 
+def case_conv_fwd_bn(C0=64, C1=0, Cout=64, N=2, H=24, W=40, cases=False, seed=50):
+    """ub_conv3x3_fwd_bn: the forward's last CTA finalises the BatchNorm that follows -- mean / rstd / moving statistics against the
+    numpy oracle on the stored (bf16) output; launched twice (the CTA counter must come back to zero)"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    Cin = C0 + C1
+    x = bf16_round(rng.normal(size=(N, H, W, Cin)))
+    w = bf16_round(rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cin))
+    nb = 9 if cases else 1
+    b = rng.normal(size=(nb, Cout)).astype(np.float32)
+    x0 = dev(x[..., :C0], torch.bfloat16)
+    x1 = dev(x[..., C0:], torch.bfloat16) if C1 else None
+    out = torch.full((N, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    partial = torch.full((C.UB_STATS_ROWS * 2 * Cout,), float("nan"), dtype=torch.float32, device="cuda")      # no zero-fill needed
+    mean = torch.full((Cout,), float("nan"), device="cuda")
+    rstd = torch.full((Cout,), float("nan"), device="cuda")
+    mm0, mv0 = rng.normal(size=Cout).astype(np.float32), rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+    counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+    r = {}
+    for rep in range(2):
+        mm, mv = dev(mm0, torch.float32), dev(mv0, torch.float32)
+        C.call("ub_conv3x3_fwd_bn", x0, C0, x1, C1, dev(pack_conv(w), torch.bfloat16), dev(b, torch.float32), 1 if cases else 0, out, partial,
+               N, H, W, Cout, 1, mean, rstd, mm, mv, 0.99, 1e-3, counter, stream())
+        torch.cuda.synchronize()
+        got = out.double().cpu().numpy()
+        M = N * H * W
+        mu, var = got.mean((0, 1, 2)), got.var((0, 1, 2))
+        r[f"e_mean{rep}"] = rel_err(mean.cpu().numpy(), mu)
+        r[f"e_rstd{rep}"] = rel_err(rstd.cpu().numpy(), 1 / np.sqrt(var + 1e-3))
+        r[f"e_mm{rep}"] = rel_err(mm.cpu().numpy(), 0.99 * mm0 + 0.01 * mu)
+        r[f"e_mv{rep}"] = rel_err(mv.cpu().numpy(), 0.99 * mv0 + 0.01 * var * M / (M - 1))
+        r[f"counter{rep}"] = int(counter[0])
+    ref = ON.conv_fwd(x, w, np.zeros(Cout))
+    if cases:
+        hh = np.where(np.arange(H) == 0, 0, np.where(np.arange(H) == H - 1, 2, 1))
+        ww = np.where(np.arange(W) == 0, 0, np.where(np.arange(W) == W - 1, 2, 1))
+        ref = ref + b.astype(np.float64)[hh[:, None] * 3 + ww[None, :]][None]
+    else:
+        ref = ref + b[0].astype(np.float64)
+    r["err"] = rel_err(got, np.maximum(ref, 0))
+    r["ok"] = bool(r["err"] < 1e-2 and all(r[f"{k}{rep}"] < 2e-5 for k in ("e_mean", "e_rstd", "e_mm", "e_mv") for rep in range(2))
+                   and r["counter0"] == 0 and r["counter1"] == 0)
+    return r
+
+
+def case_deconv_fwd_bn(Cin=128, Cout=64, N=2, h=12, w=20, seed=51):
+    """ub_deconv2x2_fwd_bn: four column groups per channel finalised by the last CTA"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    x = bf16_round(rng.normal(size=(N, h, w, Cin)))
+    wt = bf16_round(rng.normal(size=(2, 2, Cout, Cin)) / np.sqrt(Cin))
+    b = rng.normal(size=(Cout,)).astype(np.float32)
+    out = torch.full((N, 2 * h, 2 * w, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    partial = torch.full((C.UB_STATS_ROWS * 2 * 4 * Cout,), float("nan"), dtype=torch.float32, device="cuda")
+    mean = torch.full((Cout,), float("nan"), device="cuda")
+    rstd = torch.full((Cout,), float("nan"), device="cuda")
+    counter = torch.zeros(4, dtype=torch.int32, device="cuda")
+    r = {}
+    for rep in range(2):
+        mm, mv = torch.zeros(Cout, device="cuda"), torch.ones(Cout, device="cuda")
+        C.call("ub_deconv2x2_fwd_bn", dev(x, torch.bfloat16), Cin, dev(pack_deconv(wt), torch.bfloat16), dev(b, torch.float32), out, partial,
+               N, h, w, Cout, mean, rstd, mm, mv, 0.99, 1e-3, counter, stream())
+        torch.cuda.synchronize()
+        got = out.double().cpu().numpy()
+        M = N * 4 * h * w
+        mu, var = got.mean((0, 1, 2)), got.var((0, 1, 2))
+        r[f"e_mean{rep}"] = float(np.abs(mean.cpu().numpy() - mu).max() / np.sqrt(var).max())
+        r[f"e_rstd{rep}"] = rel_err(rstd.cpu().numpy(), 1 / np.sqrt(var + 1e-3))
+        r[f"e_mv{rep}"] = rel_err(mv.cpu().numpy(), 0.99 + 0.01 * var * M / (M - 1))
+        r[f"counter{rep}"] = int(counter[0])
+    r["err"] = rel_err(got, ON.deconv_fwd(x, wt, b.astype(np.float64)))
+    r["ok"] = bool(r["err"] < 1e-2 and all(r[f"{k}{rep}"] < 2e-5 for k in ("e_mean", "e_rstd", "e_mv") for rep in range(2))
+                   and r["counter0"] == 0 and r["counter1"] == 0)
+    return r
+
+
 def case_conv_first_tiles(Cin=1, H=1000, W=1190, seed=44):
     """ub_conv_first_fwd_affine_tiles (tiles read in place, mirrored past the image edge) == ub_conv_first_fwd_affine on tiles cut
     from the explicitly reflect-padded image (np.pad(mode='reflect'), UNet/inference.py:46): bit-exact"""
@@ -1012,4 +1088,13 @@ CASES = {
     "wgrad_folded_cat_128+128_128": lambda: case_wgrad_folded(128, 128, 128, N=1, H=16, W=24, identity0=True),
     "conv_first_tiles_c1": case_conv_first_tiles,
     "conv_first_tiles_c3": lambda: case_conv_first_tiles(3, H=330, W=1030, seed=45),
+    # forward launches that finalise their BatchNorm in the last CTA
+    "conv_fwd_bn_64_64": case_conv_fwd_bn,
+    "conv_fwd_bn_cat_64+64_128_cases": lambda: case_conv_fwd_bn(64, 64, 128, cases=True, seed=52),
+    "conv_fwd_bn_256_1024": lambda: case_conv_fwd_bn(256, 0, 1024, N=1, H=16, W=24, seed=53),
+    "conv_fwd_bn_64_64_big": lambda: case_conv_fwd_bn(64, 0, 64, N=4, H=128, W=128, cases=True, seed=54),
+    "conv_fwd_bn_2x2": lambda: case_conv_fwd_bn(64, 0, 64, N=1, H=2, W=2, cases=True, seed=55),
+    "deconv_fwd_bn_128_64": case_deconv_fwd_bn,
+    "deconv_fwd_bn_1024_512": lambda: case_deconv_fwd_bn(1024, 512, N=1, h=8, w=12, seed=56),
+    "deconv_fwd_bn_256_128": lambda: case_deconv_fwd_bn(256, 128, N=3, h=32, w=32, seed=57),
 }

@@ -15,6 +15,7 @@ from unetb200 import model as M
 class DryUNet(M.UNet):
     def __init__(self, *a, **kw):
         self.calls = []
+        self.args = []
         real = torch.cuda.is_available
         torch.cuda.is_available = lambda: True
         try:
@@ -46,6 +47,7 @@ class DryUNet(M.UNet):
         assert params[-1][0] is ctypes.c_void_p
         self.launches += 1
         self.calls.append((name, self._cur))
+        self.args.append(args)
         return 0
 
 
@@ -53,6 +55,7 @@ def _step(m, N=1, C_=1, H=32, W=48, K=2):
     x = torch.zeros((N, C_, H, W), dtype=torch.float32)
     lab = torch.zeros((N, H, W), dtype=torch.uint8)
     m.calls.clear()
+    m.args.clear()
     m.train_step(x, lab)
     return [n for n, _ in m.calls]
 
@@ -70,10 +73,12 @@ def test_unfolded_training_schedule(overlap):
     m.overlap_wgrad = overlap
     m.fold_bn = False                     # UB_FOLD_BN=0: every BatchNorm output is materialised
     c = _count(_step(m))
-    assert c["ub_conv3x3_fwd"] == 17 and c["ub_conv_first_fwd"] == 1 and c["ub_deconv2x2_fwd"] == 4 and c["ub_head_fwd"] == 1
+    # the tcgen05 forwards finalise their BatchNorm in the same launch (ub_*_fwd_bn); the first layer and the head keep ub_bn_finalize
+    assert c["ub_conv3x3_fwd_bn"] == 17 and c["ub_conv_first_fwd"] == 1 and c["ub_deconv2x2_fwd_bn"] == 4 and c["ub_head_fwd"] == 1
+    assert "ub_conv3x3_fwd" not in c and "ub_deconv2x2_fwd" not in c
     assert c["ub_conv3x3_wgrad"] == 17 and c["ub_deconv2x2_wgrad"] == 4 and c["ub_conv_first_wgrad"] == 1
     assert c.get("ub_conv3x3_dgrad", 0) + c.get("ub_conv3x3_dgrad_bnred", 0) == 17 and c["ub_deconv2x2_dgrad"] == 4
-    assert c["ub_bn_apply"] + c["ub_bn_apply_pool"] == 22 and c["ub_bn_bwd_apply"] == 22 and c["ub_bn_finalize"] == 23
+    assert c["ub_bn_apply"] + c["ub_bn_apply_pool"] == 22 and c["ub_bn_bwd_apply"] == 22 and c["ub_bn_finalize"] == 2
     assert c["ub_adam"] == 1 and c["ub_transpose_pack_multi"] == 1 and c["ub_maxpool2x2_bwd_add"] == 4
     assert "ub_fold_conv3_weights" not in c and "ub_maxpool2x2_bwd_add_bnred" not in c
     # the fp32 check mode and the class-weighted 3-channel, 8-class configuration walk the same graph
@@ -81,6 +86,14 @@ def test_unfolded_training_schedule(overlap):
         mm = DryUNet(shape[4], 1, shape[1], seed=0, **kw)
         mm.overlap_wgrad = overlap
         assert len(_step(mm, *shape)) > 150
+
+
+def test_separate_finalize_schedule():
+    m = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    m.fuse_finalize = False               # UB_FUSE_FINALIZE=0
+    c = _count(_step(m))
+    assert c["ub_conv3x3_fwd_cases"] == 13 and c["ub_conv3x3_fwd"] == 4 and c["ub_deconv2x2_fwd"] == 4 and c["ub_bn_finalize"] == 23
+    assert "ub_conv3x3_fwd_bn" not in c
 
 
 def test_optional_schedules():
@@ -95,11 +108,11 @@ def test_optional_schedules():
     c = _count(names)
     # 17 producers lose their BatchNorm-apply pass (13 conv/deconv layers, enc1b-3b behind a y-less pool, dec1b behind the folded
     # head); the 13 consumer convs fold the weights, use the case bias and fix the weight gradient
-    assert c["ub_fold_conv3_weights"] == 13 and c["ub_conv3x3_fwd_cases"] == 13 and c["ub_conv3x3_fwd"] == 4
+    assert c["ub_fold_conv3_weights"] == 13 and c["ub_conv3x3_fwd_bn"] == 17 and "ub_conv3x3_fwd_cases" not in c
     assert c["ub_bn_apply"] == 4 and c["ub_bn_apply_pool"] == 1 and c["ub_bn_pool"] == 3          # botb, dec2b-4b | enc4b | enc1b-3b
     assert c["ub_border_sums"] == 13 and c["ub_wgrad_fold_fix"] == 13 and c["ub_conv3x3_wgrad"] == 17
     assert c["ub_fold_head_weights"] == 1 and c["ub_head_wgrad_fold_fix"] == 1 and c["ub_head_fwd"] == 1
-    folded = {l for n, l in m.calls if n == "ub_conv3x3_fwd_cases"}
+    folded = {l for (n, l), a in zip(m.calls, m.args) if n == "ub_conv3x3_fwd_bn" and a[6] == 1}
     assert folded == {"enc1b", "enc2b", "enc3b", "enc4b", "botb", "dec4a", "dec4b", "dec3a", "dec3b", "dec2a", "dec2b", "dec1a", "dec1b"}
     # back to the default schedule on the same object
     m.fold_bn = False
