@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(TPB) zscore_apply_kernel(const TI* __restrict_
 }
 
 // ---- z-score in two halves (image split across ranks: each rank sums the rows it owns, the sums are all-reduced, then
-// every rank normalises its band with the GLOBAL statistics; unetb200.inference.segment_banded) -----------------------------
+// every rank normalises its band with the GLOBAL statistics; unetb200.inference.segment_sharded) -----------------------------
 template <typename TI>
 __global__ void __launch_bounds__(TPB) zscore_part_stats_kernel(const TI* __restrict__ x, double* __restrict__ partial, long long plane,
                                                                 long long plane_stride) {

@@ -8,6 +8,8 @@
 //                output mask (UNet/inference.py:105-129), optional softmax for the model-call contract
 // Thread mapping for the 64-channel tensors: 8 threads per pixel x 8 channels each (128-bit bf16 accesses, a warp
 // covers 4 pixels = 512 contiguous bytes); class-dimension reductions use warp shuffles.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(TPB) head_bwd_reduce_kernel(const float* __res
 
 // pass 2: dz_k = gamma_k rstd_k (dy_k - dbeta_k/P - xhat_k dgamma_k/P) [a_k > 0]
 //         dx[p][c] = sum_k w[k][c] dz_k   ;   partial[row] = { dW[k][c] (K*64), db[k] (K) }
-template <typename T, int K, bool RED>
+template <typename T, int K, bool RED, int PPI = 2>
 __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ a, const T* __restrict__ x,
                                                              const float* __restrict__ w, const float* __restrict__ mean,
                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -642,15 +644,17 @@ __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __rest
     db[k] = dbeta[k] * invP;
     dg[k] = dgamma[k] * invP;
   }
-  const long long iters = (P + 63) / 64;
+  // PPI pixels per thread per iteration: PPI 16-byte loads of x in flight (94 registers allow 2 blocks per SM: with PPI = 2 the kernel
+  // was latency-bound at 3.1 TB/s, profiles/r01_kernels.md)
+  const long long iters = (P + 32 * PPI - 1) / (32 * PPI);
   for (long long it = blockIdx.x; it < iters; it += gridDim.x) {
-    long long px[2];
-    bool ok[2];
-    float f[2][8] = {};
-    float av[2][K], dv[2][K];
+    long long px[PPI];
+    bool ok[PPI];
+    float f[PPI][8] = {};
+    float av[PPI][K], dv[PPI][K];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      px[u] = it * 64 + u * 32 + pl;
+    for (int u = 0; u < PPI; ++u) {
+      px[u] = it * (32 * PPI) + u * 32 + pl;
       ok[u] = px[u] < P;
       if (ok[u]) {
         ld8<T>(x + px[u] * 64 + sub * 8, f[u]);
@@ -662,7 +666,7 @@ __global__ void __launch_bounds__(TPB) head_bwd_apply_kernel(const float* __rest
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < PPI; ++u) {
       if (ok[u]) {
         float o[8] = {};
 #pragma unroll
@@ -997,9 +1001,19 @@ static int head_bwd_apply_launch(const float* dy, const float* a, const void* x,
                                               dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx, partial, P, (const T*)red_a, red_mean,
                                               red_rstd, red_out))));
   } else {
-    UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_bwd_apply_kernel<T, KK, false><<<grid, TPB, 0, stream>>>(
-                                              dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx, partial, P, nullptr, nullptr, nullptr,
-                                              nullptr))));
+    static int ppi = -1;
+    if (ppi < 0) {
+      const char* e = getenv("UB_HEAD_PPI");          // A/B switch: pixels per thread per iteration (2 = round-1 kernel)
+      ppi = e ? atoi(e) : 4;
+    }
+    if (ppi == 4 && K <= 4)
+      UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_bwd_apply_kernel<T, (KK <= 4 ? KK : 1), false, 4><<<grid, TPB, 0, stream>>>(
+                                                dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx, partial, P, nullptr, nullptr, nullptr,
+                                                nullptr))));
+    else
+      UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_bwd_apply_kernel<T, KK, false><<<grid, TPB, 0, stream>>>(
+                                                dy, a, (const T*)x, w, mean, rstd, gamma, dbeta, dgamma, (T*)dx, partial, P, nullptr, nullptr, nullptr,
+                                                nullptr))));
   }
   UB_LAUNCH_CHECK();
   return UB_OK;

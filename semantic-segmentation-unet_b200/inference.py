@@ -13,7 +13,8 @@ Reference behaviour kept (file:line under /root/reference/UNet):
 What is new underneath: the image is uploaded ONCE, normalised on the GPU (ub_zscore), equal-shaped tiles are batched
 through the folded inference forward, the argmax of every tile's zone is written by the head kernel straight into a
 uint8 device mask (no softmax round trip, no per-tile H2D/D2H), and tiles are sharded round-robin over the ranks of a
-torchrun job (the zones are made disjoint first -- see tile_plan -- so the shards combine with one SUM reduce).
+torchrun job (the zones are made disjoint first -- see tile_plan -- so the shards combine with one SUM reduce); segment_sharded
+additionally uploads and normalises only the rows a rank's tiles read.
 """
 from __future__ import annotations
 
@@ -134,33 +135,36 @@ def segment_device(img_chw, unet_model, tile_size=TILE_SIZE, radius=None, tile_b
     return mask
 
 
-def band_plan(height, width, tile_size, radius, world):
-    """Row-band sharding of the tile plan: rank r owns a contiguous run of tile ROWS, i.e. the zone rows [zy0, zy1) across the
-    whole width, and needs the image rows [y0, y1) (its zones plus halo).  Zones of different ranks are disjoint and cover the
-    image, so each rank uploads / normalises / segments only its band and the mask is assembled by concatenating bands --
-    instead of every rank uploading the whole image and all-reducing the whole mask (segment_device)."""
+def shard_plan(height, width, tile_size, radius, world):
+    """Sharding of the tile plan over `world` ranks: rank r owns a contiguous RUN of tiles in row-major order (equal counts to within
+    one tile: 625 tiles over 8 ranks = 78 or 79 each -- whole tile rows would give 3 or 4 rows of 25, a 28 % imbalance).  Per rank:
+      tiles          its tiles (tile_plan entries, coordinates of the padded image)
+      y0, y1         image rows its tiles read (zones plus halo): the only rows it uploads and normalises
+      sy0, sy1       full-width rows whose pixels it contributes to the whole-image z-score statistics: the zone rows of the tile rows
+                     whose FIRST tile lies in its run (disjoint over ranks, covering the image, inside [y0, y1))"""
     plan = tile_plan(height, width, tile_size, radius)
-    rows = sorted({t["dy"] for t in plan})
     out = []
     for r in range(world):
-        lo, hi = (len(rows) * r) // world, (len(rows) * (r + 1)) // world
-        mine_rows = set(rows[lo:hi])
-        tiles = [t for t in plan if t["dy"] in mine_rows]
+        lo, hi = (len(plan) * r) // world, (len(plan) * (r + 1)) // world
+        tiles = plan[lo:hi]
         if not tiles:
-            out.append(dict(tiles=[], y0=0, y1=0, zy0=0, zy1=0))
+            out.append(dict(tiles=[], y0=0, y1=0, sy0=0, sy1=0))
             continue
-        out.append(dict(tiles=tiles, y0=min(t["y0"] for t in tiles), y1=max(t["y1"] for t in tiles), zy0=min(t["dy"] for t in tiles),
-                        zy1=max(t["dy"] + t["cy1"] - t["cy0"] for t in tiles)))
+        starts = [t for t in tiles if t["dx"] == 0]
+        sy0 = min((t["dy"] for t in starts), default=0)
+        sy1 = max((t["dy"] + t["cy1"] - t["cy0"] for t in starts), default=0)
+        out.append(dict(tiles=tiles, y0=min(t["y0"] for t in tiles), y1=max(t["y1"] for t in tiles), sy0=sy0, sy1=sy1))
     return out
 
 
-def segment_banded(raw_host, unet_model, dist, tile_size=TILE_SIZE, radius=None, tile_batch=TILE_BATCH, out_host=None):
-    """Tiled inference of one image with the ROWS sharded over the ranks of `dist`.  raw_host: pinned host tensor [C, H, W] of raw
-    pixels (uint8 / uint16-as-int16 bits / float32), the same on every rank.  Each rank uploads its band, the per-channel z-score
-    statistics of the UNPADDED image (UNet/inference.py:206) are summed over the owned rows and all-reduced (2 doubles per channel),
-    the band is normalised and segmented (the reflect padding of the bottom / right edge, inference.py:46, is mirror indexing
-    inside the tile reader), and the band masks are sent to rank 0.
-    Returns the uint8 device mask [H, W] on rank 0 (None elsewhere); if `out_host` (pinned uint8 [H, W]) is given rank 0 copies it."""
+def segment_sharded(raw_host, unet_model, dist, tile_size=TILE_SIZE, radius=None, tile_batch=TILE_BATCH, out_host=None):
+    """Tiled inference of one image with the TILES sharded over the ranks of `dist` (shard_plan).  raw_host: pinned host tensor
+    [C, H, W] of raw pixels (uint8 / uint16-as-int16 bits / float32), the same on every rank.  Each rank uploads only the rows its
+    tiles read; the per-channel z-score statistics of the UNPADDED image (UNet/inference.py:206) are summed over disjoint row ranges
+    and all-reduced (2 doubles per channel); the rows are normalised and the tiles segmented in place (the reflect padding of the
+    bottom / right edge, inference.py:46, is mirror indexing inside the tile reader); zones are disjoint, so one SUM all-reduce of
+    the uint8 mask over NVLink assembles the result on every rank.
+    Returns the uint8 device mask [H, W]; if `out_host` (pinned uint8 [H, W]) is given, rank 0 copies it there."""
     import torch
     import torch.distributed as td
     from . import _C
@@ -171,47 +175,32 @@ def segment_banded(raw_host, unet_model, dist, tile_size=TILE_SIZE, radius=None,
     Hp, Wp = H + pad_y, W + pad_x
     if radius is None:
         radius = unet_model.estimate_radius()
-    bands = band_plan(Hp, Wp, tile_size, radius, world)
-    b = bands[rank]
+    b = shard_plan(Hp, Wp, tile_size, radius, world)[rank]
     code = {torch.uint8: 0, torch.int16: 1, torch.float32: 2}[raw_host.dtype]
     st = unet_model._stream()
     sums = torch.zeros((C, 2), dtype=torch.float64, device=dev)
-    band_mask = None
+    mask = torch.zeros((Hp, Wp), dtype=torch.uint8, device=dev)
     if b["tiles"]:
         y0, y1 = b["y0"], min(b["y1"], H)                       # rows that exist in the unpadded image
         raw = torch.empty((C, y1 - y0, W), dtype=raw_host.dtype, device=dev)
-        for c in range(C):                                       # each channel's band is one contiguous chunk of the host image
+        for c in range(C):                                       # each channel's rows are one contiguous chunk of the host image
             raw[c].copy_(raw_host[c, y0:y1], non_blocking=True)
-        oz0, oz1 = b["zy0"], min(b["zy1"], H)                    # owned rows of the unpadded image: they carry the statistics
+        s0, s1 = b["sy0"], min(b["sy1"], H)                      # rows of the unpadded image that carry this rank's share of the statistics
         scratch = torch.empty(C * _C.UB_ZSCORE_BLOCKS * 2, dtype=torch.float64, device=dev)
-        if oz1 > oz0:
-            _C.call("ub_zscore_sums", raw[:, oz0 - y0:], code, sums, scratch, C, (oz1 - oz0) * W, (y1 - y0) * W, st)
+        if s1 > s0:
+            _C.call("ub_zscore_sums", raw[:, s0 - y0:], code, sums, scratch, C, (s1 - s0) * W, (y1 - y0) * W, st)
     if world > 1:
         td.all_reduce(sums, op=td.ReduceOp.SUM)
     if b["tiles"]:
         x = torch.empty((C, y1 - y0, W), dtype=torch.float32, device=dev)
         _C.call("ub_zscore_apply_sums", raw, code, x, sums, float(H) * float(W), C, (y1 - y0) * W, st)
-        zr = b["zy1"] - b["zy0"]
-        band_mask = torch.zeros((zr, Wp), dtype=torch.uint8, device=dev)
-        # tiles are read in place from the band; rows / columns of the padding are mirrored by the reader (the last band holds the
-        # image's bottom rows, which is where the mirrored rows come from)
-        _run_tiles(x, H, b["tiles"], unet_model, band_mask, Wp, tile_batch, row0=y0, zrow0=b["zy0"])
-    # assemble on rank 0: bands are disjoint row ranges of the padded mask
-    if rank == 0:
-        mask = torch.empty((Hp, Wp), dtype=torch.uint8, device=dev)
-        if band_mask is not None:
-            mask[b["zy0"]:b["zy1"]].copy_(band_mask)
-        for r in range(1, world):
-            br = bands[r]
-            if br["tiles"]:
-                td.recv(mask[br["zy0"]:br["zy1"]], src=r)
-        mask = mask[:H, :W]
-        if out_host is not None:
-            out_host.copy_(mask, non_blocking=True)
-        return mask
-    if band_mask is not None:
-        td.send(band_mask, dst=0)
-    return None
+        _run_tiles(x, H, b["tiles"], unet_model, mask, Wp, tile_batch, row0=y0)
+    if world > 1:
+        td.all_reduce(mask, op=td.ReduceOp.SUM)                   # disjoint zones, zeros elsewhere
+    mask = mask[:H, :W]
+    if out_host is not None and rank == 0:
+        out_host.copy_(mask, non_blocking=True)
+    return mask
 
 
 def zscore_device(img_chw_raw, unet_model):

@@ -679,7 +679,7 @@ def _with_fold(fn, value="0"):
 
 
 def case_banded_inference():
-    """segment_banded (row bands, split z-score) on one rank == zscore_device + segment_device, incl. reflect padding"""
+    """segment_sharded (tile runs, split z-score) on one rank == zscore_device + segment_device, incl. reflect padding"""
     import unetb200.inference as I
     from unetb200.model import UNet
     rng = np.random.default_rng(8)
@@ -700,7 +700,7 @@ def case_banded_inference():
 
     class D:
         rank, world_size = 0, 1
-    got = I.segment_banded(raw, m, D, 1024, radius=96)
+    got = I.segment_sharded(raw, m, D, 1024, radius=96)
     agree = float((got == ref).float().mean())
     return dict(agree=agree, reader_agree=reader_agree, fg=float((ref == 1).float().mean()), ok=bool(agree == 1.0 and reader_agree == 1.0))
 
@@ -744,8 +744,8 @@ CASES = {
     "trained_bf16": case_trained,
     # the reference's data/ fixture -> build_lmdb -> 60 training steps, loss curve vs the oracle's
     "config1_refdata": case_config1_refdata,
-    # row-band sharded inference == tile-sharded inference on one rank
-    "banded_inference": case_banded_inference,
+    # sharded inference (rows uploaded per rank, split z-score, in-place tile reader) == whole-image path on one rank
+    "sharded_inference": case_banded_inference,
     # the y-materialising training forward (UB_FOLD_BN=0; the default folds BatchNorm into the consumer convolutions)
     "nofold_live_bf16_c1k2": _with_fold(lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True)),
     "nofold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True)),

@@ -109,7 +109,7 @@ def test_bucketed_allreduce_world2_gloo():
 
 
 def _banded_worker(rank, world, port, q):
-    """segment_banded over gloo with the kernels replaced by markers: the z-score sums carry the rank, the argmax kernel paints
+    """segment_sharded over gloo with the kernels replaced by markers: the z-score sums carry the rank, the argmax kernel paints
     the zones it is handed with rank + 1 -- so the statistics all-reduce, the band geometry and the assembly on rank 0 are checked"""
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import numpy as np
@@ -148,15 +148,14 @@ def _banded_worker(rank, world, port, q):
         C.call = fake_call
         H, W = 2048 + 150, 1024 + 490
         raw = torch.zeros((1, H, W), dtype=torch.int16)
-        out = I.segment_banded(raw, m, dp, 1024, radius=96, tile_batch=4)
+        out = I.segment_sharded(raw, m, dp, 1024, radius=96, tile_batch=4)
         Hp, Wp = H + (16 - H % 16) % 16, W + (16 - W % 16) % 16
-        bands = I.band_plan(Hp, Wp, 1024, 96, world)
-        ok_mask = None
-        if rank == 0:
-            want = np.zeros((Hp, Wp), dtype=np.uint8)
-            for r, b in enumerate(bands):
-                want[b["zy0"]:b["zy1"]] = r + 1
-            ok_mask = bool(np.array_equal(out.numpy(), want[:H, :W]))
+        shards = I.shard_plan(Hp, Wp, 1024, 96, world)
+        want = np.zeros((Hp, Wp), dtype=np.uint8)
+        for r, b in enumerate(shards):
+            for t in b["tiles"]:
+                want[t["dy"]:t["dy"] + t["cy1"] - t["cy0"], t["dx"]:t["dx"] + t["cx1"] - t["cx0"]] = r + 1
+        ok_mask = bool(np.array_equal(out.numpy(), want[:H, :W]))          # the mask all-reduce leaves the assembled result on every rank
         q.put((rank, out is not None, ok_mask, seen["sums"].tolist()))
     finally:
         dp.shutdown()
@@ -176,7 +175,5 @@ def test_banded_inference_world3_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, has_out, ok_mask, sums in res:
-        assert has_out == (rank == 0)
-        if rank == 0:
-            assert ok_mask, "bands assembled on rank 0 do not tile the image by owner"
+        assert has_out and ok_mask, "the all-reduced mask does not tile the image by owner"
         assert sums == [[6.0, 60.0]]             # 1 + 2 + 3 and 10 + 20 + 30: every rank normalises with the GLOBAL statistics

@@ -51,28 +51,30 @@ def test_bad_dimensions_raise_ioerror():
         I._as_hwc(np.zeros((2, 2, 2, 2)))
 
 
-def test_band_plan_partitions_the_tile_rows():
-    """row-band sharding (unetb200.inference.band_plan): every tile belongs to exactly one rank, a rank's zones are a contiguous
-    row range over the full width, the ranges are disjoint and cover the image, and the rows a rank uploads contain its tiles"""
+def test_shard_plan_partitions_the_tiles():
+    """tile-run sharding (unetb200.inference.shard_plan): every tile belongs to exactly one rank, counts are balanced to one tile, the
+    rows a rank uploads contain its tiles, and the statistics row ranges are disjoint, cover the image and lie inside the uploaded rows"""
     from unetb200 import inference as I
-    for (H, W, world) in [(20000, 20000, 8), (2208, 1520, 2), (2208, 1520, 3), (1040, 5000, 4), (4096, 4096, 1)]:
+    for (H, W, world) in [(20000, 20000, 8), (2208, 1520, 2), (2208, 1520, 3), (1040, 5000, 4), (4096, 4096, 1), (1040, 1040, 8)]:
         plan = I.tile_plan(H, W, 1024, 96)
-        bands = I.band_plan(H, W, 1024, 96, world)
-        assert len(bands) == world
-        seen = [(t["dy"], t["dx"]) for b in bands for t in b["tiles"]]
-        assert sorted(seen) == sorted((t["dy"], t["dx"]) for t in plan)
+        shards = I.shard_plan(H, W, 1024, 96, world)
+        assert len(shards) == world
+        seen = [(t["dy"], t["dx"]) for b in shards for t in b["tiles"]]
+        assert seen == [(t["dy"], t["dx"]) for t in plan]                      # contiguous runs in row-major order
+        counts = [len(b["tiles"]) for b in shards]
+        assert max(counts) - min(counts) <= 1
         edge = 0
-        for b in bands:
+        for b in shards:
             if not b["tiles"]:
+                assert b["sy1"] == b["sy0"]
                 continue
-            assert b["zy0"] == edge and b["zy1"] > b["zy0"]
-            edge = b["zy1"]
             assert all(b["y0"] <= t["y0"] and t["y1"] <= b["y1"] for t in b["tiles"])
-            assert b["y0"] == max(b["zy0"] - 96, 0) and b["y1"] == min(b["zy1"] + 96, H)
-            cover = np.zeros((b["zy1"] - b["zy0"], W), dtype=np.int8)
-            for t in b["tiles"]:
-                cover[t["dy"] - b["zy0"]:t["dy"] - b["zy0"] + t["cy1"] - t["cy0"], t["dx"]:t["dx"] + t["cx1"] - t["cx0"]] += 1
-            assert (cover == 1).all()
+            if b["sy1"] > b["sy0"]:
+                assert b["sy0"] == edge and b["y0"] <= b["sy0"] and b["sy1"] <= b["y1"]
+                edge = b["sy1"]
         assert edge == H
-        counts = [len(b["tiles"]) for b in bands]
-        assert max(counts) - min(counts) <= -(-W // 832) if world <= len({t["dy"] for t in plan}) else True      # balanced to one tile row
+    cover = np.zeros((2208, 1520), dtype=np.int8)
+    for b in I.shard_plan(2208, 1520, 1024, 96, 3):
+        for t in b["tiles"]:
+            cover[t["dy"]:t["dy"] + t["cy1"] - t["cy0"], t["dx"]:t["dx"] + t["cx1"] - t["cx0"]] += 1
+    assert (cover == 1).all()

@@ -178,9 +178,9 @@ def test_tiled_inference_schedule():
     assert (cover == 1).all()
 
 
-def test_banded_inference_schedule():
-    """unetb200.inference.segment_banded (row bands per rank) on the dry model: per rank, the rows uploaded, the statistics call
-    over the owned rows only, and zones that tile the rank's band; bands of all ranks tile the padded image"""
+def test_sharded_inference_schedule():
+    """unetb200.inference.segment_sharded (a run of tiles per rank) on the dry model: per rank, the rows uploaded, the statistics call
+    over the owned rows only, tiles read in place from the uploaded rows; the zones of all ranks tile the padded image"""
     import torch.distributed as td
     import unetb200.inference as I
 
@@ -189,11 +189,9 @@ def test_banded_inference_schedule():
     raw = torch.zeros((1, H, W), dtype=torch.int16)
     cover = np.zeros((Hp, Wp), dtype=np.int32)
     owned_rows = 0
-    real_call, real_ar, real_send, real_recv = C.call, td.all_reduce, td.send, td.recv
+    real_call, real_ar = C.call, td.all_reduce
     try:
         td.all_reduce = lambda *a, **k: None
-        td.send = lambda *a, **k: None
-        td.recv = lambda *a, **k: None
         for rank in range(world):
             log = []
 
@@ -208,28 +206,32 @@ def test_banded_inference_schedule():
                 def _call(self, name, *args):
                     if name == "ub_head_argmax":
                         self.zones.extend(args[9][:args[6]].tolist())
+                    if name == "ub_conv_first_fwd_affine_tiles":
+                        self.origins.extend((args[1][:args[11]] + torch.tensor([self.row0, 0], dtype=torch.int32)).tolist())
+                        self.extent = (args[2], args[3])
                     return super()._call(name, *args)
 
             m = Geo(2, 1, 1, precision="bf16", seed=0)
-            m.zones = []
+            m.zones, m.origins = [], []
+            b = I.shard_plan(Hp, Wp, 1024, 96, world)[rank]
+            m.row0 = b["y0"]
 
             class D:
                 world_size = world
             D.rank = rank
-            out = I.segment_banded(raw, m, D, 1024, radius=96, tile_batch=4)
-            assert (out is not None) == (rank == 0)
-            if rank == 0:
-                assert tuple(out.shape) == (H, W)
-            b = I.band_plan(Hp, Wp, 1024, 96, world)[rank]
+            out = I.segment_sharded(raw, m, D, 1024, radius=96, tile_batch=4)
+            assert tuple(out.shape) == (H, W)
             names = [n for n, _ in log]
             assert names == ["ub_zscore_sums", "ub_zscore_apply_sums"]
             _, a = log[0]
-            rows_owned = min(b["zy1"], H) - b["zy0"]
+            rows_owned = min(b["sy1"], H) - b["sy0"]
             assert a[5] == rows_owned * W and a[6] == (min(b["y1"], H) - b["y0"]) * W and a[4] == 1
             owned_rows += rows_owned
             assert log[1][1][4] == float(H) * float(W)                                      # statistics of the whole unpadded image
+            assert sorted(m.origins) == sorted([t["y0"], t["x0"]] for t in b["tiles"])        # tiles read in place, band-relative rows
+            assert m.extent == (H - b["y0"], W)                                               # mirror past the UNPADDED extent
             for cy0, cy1, cx0, cx1, dy, dx in m.zones:
-                cover[b["zy0"] + dy:b["zy0"] + dy + cy1 - cy0, dx:dx + cx1 - cx0] += 1
+                cover[dy:dy + cy1 - cy0, dx:dx + cx1 - cx0] += 1
     finally:
-        C.call, td.all_reduce, td.send, td.recv = real_call, real_ar, real_send, real_recv
+        C.call, td.all_reduce = real_call, real_ar
     assert owned_rows == H and (cover == 1).all()

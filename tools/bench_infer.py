@@ -19,8 +19,9 @@ sys.path.insert(0, ROOT)
 
 
 def measure(size=20000, reps=3, tile_batch=4, classes=2, banded=None, clock_sampler=None):
-    """returns (on rank 0; None elsewhere) a dict with the host-to-host and the device-resident MPix/s.  banded None = row bands
-    whenever there is more than one rank (UB_INFER_BANDED=0 forces the round-robin tile sharding with a full-mask all-reduce)."""
+    """returns (on rank 0; None elsewhere) a dict with the host-to-host and the device-resident MPix/s.  banded None = segment_sharded
+    (tile runs, each rank uploads only its rows) whenever there is more than one rank; UB_INFER_BANDED=0 forces the round-robin tile
+    sharding in which every rank uploads and normalises the whole image."""
     import torch
     import unetb200.inference as I
     from unetb200.dist import DataParallel
@@ -50,7 +51,7 @@ def measure(size=20000, reps=3, tile_batch=4, classes=2, banded=None, clock_samp
 
     def one():
         if banded:
-            I.segment_banded(host, m, dp, I.TILE_SIZE, radius=96, tile_batch=tile_batch, out_host=out_host if rank == 0 else None)
+            I.segment_sharded(host, m, dp, I.TILE_SIZE, radius=96, tile_batch=tile_batch, out_host=out_host if rank == 0 else None)
             torch.cuda.synchronize(dev)
             return
         raw = host.to(dev, non_blocking=True)
@@ -98,7 +99,7 @@ def measure(size=20000, reps=3, tile_batch=4, classes=2, banded=None, clock_samp
         # forward FLOPs actually executed: tiles incl. halo (1.467776 MFLOP/pixel at Cin = 1, K = 2)
         px_exec = sum((tl["y1"] - tl["y0"]) * (tl["x1"] - tl["x0"]) for tl in plan)
         res = {"metric": "unet_tiled_inference_mpix_per_sec", "value": S * S / secs / 1e6, "unit": "MPix/s", "n_gpus": world,
-               "image": [S, S], "tiles": len(plan), "tile_batch": tile_batch, "seconds": secs, "sharding": "row bands" if banded else "round-robin tiles",
+               "image": [S, S], "tiles": len(plan), "tile_batch": tile_batch, "seconds": secs, "sharding": "tile runs, per-rank row upload" if banded else "round-robin tiles, whole image per rank",
                "device_resident_mpix_per_sec": (S * S / secs_dev / 1e6) if secs_dev else None, "seconds_device_resident": secs_dev,
                "exec_tflops": px_exec * 1.467776e6 / secs / 1e12, "exec_tflop": px_exec * 1.467776e6 / 1e12,
                "foreground_fraction": float((out_host.numpy() == 1).mean()), "mask_crc": int(np.bitwise_xor.reduce(out_host.numpy().view(np.uint32).ravel())) if (S * S) % 4 == 0 else None,
