@@ -248,6 +248,14 @@ int ub_conv3x3_fwd_cases(const void* x0, int C0, const void* x1, int C1, const v
                          int H, int W, int Cout, int relu, cudaStream_t stream);
 int ub_border_sums(const void* dz, const float* total, float* sdz, float* scratch, int N, int H, int W, int C, int dtype, cudaStream_t stream);
 int ub_wgrad_fold_fix(float* dw, const float* scale, const float* shift, const float* sdz, int Cout, int Cin, cudaStream_t stream);
+/* The backward sums of the BatchNormalization that FEEDS a convolution (channels [c_begin, c_begin + c_count) of its Cin inputs), without
+ * a pass over that BatchNorm's gradient tensor: with dy = dgrad(dz, w),
+ *   dbeta[c] = sum dy = sum_{co,tap} w * sdz[tap][co];  dgamma[c] = sum dy * xhat = rstd[c] * sum_{co,tap} w * (dw_a - mean[c] * sdz[tap][co])
+ * w [Cout][taps][Cin] = the weights the dgrad used (bf16 shadow, or fp32 for the 1x1 head), dw_a [Cout][taps][Cin] = the weight gradient
+ * computed on the pre-BatchNorm activation (BEFORE ub_wgrad_fold_fix), sdz [taps][Cout] = ub_border_sums (taps == 1: the bias gradient).
+ * Replaces ub_bn_bwd_reduce / the fused dgrad reduction for every BatchNorm whose only consumer is a folded convolution. */
+int ub_bn_bwd_sums_wgrad(const void* w, int w_dtype, const float* dw_a, const float* sdz, int Cout, int taps, int Cin, int c_begin, int c_count,
+                         const float* mean, const float* rstd, float* dbeta, float* dgamma, cudaStream_t stream);
 /* the 1x1 head on a folded input (no padding, one bias): w fp32 [K][64] -> w_out = w s[c], bias_out[k] = b[k] + sum_c w[k][c] t[c];
  * its weight gradient computed with x = a is fixed by dW[k][c] = s[c] dW[k][c] + t[c] db[k] */
 int ub_fold_head_weights(const float* w, const float* bias, const float* mean, const float* rstd, const float* gamma, const float* beta,

@@ -255,3 +255,15 @@ def conv_wgrad_folded(a, dz, s, t):
     """== conv_wgrad(s * a + t, dz, 3)[0] from `a`: dW[dy,dx,ci,co] = s[ci] * dW_a[dy,dx,ci,co] + t[ci] * Sdz[dy,dx,co]"""
     dw_a, _ = conv_wgrad(a, dz, 3)
     return dw_a * s[None, None, :, None] + t[None, None, :, None] * border_sums(dz)[:, :, None, :]
+
+
+def bn_bwd_sums_from_wgrad(w_hwio, dw_a, sdz, mu, rstd):
+    """The backward sums of the BatchNormalization that FEEDS a convolution, without a pass over its gradient tensor:
+    with dy = conv_dgrad(dz, W) (gradient w.r.t. the BatchNorm output) and xhat = (a - mu) * rstd,
+        dbeta[c]  = sum_p dy[p, c]           = sum_{tap, co} W[tap, c, co] * Sdz[tap, co]
+        dgamma[c] = sum_p dy[p, c] xhat[p, c] = rstd[c] * sum_{tap, co} W[tap, c, co] * (dW_a[tap, c, co] - mu[c] * Sdz[tap, co])
+    where dW_a = conv_wgrad(a, dz) is the consumer's weight gradient computed on the pre-BatchNorm activation (what the folded
+    training step computes anyway) and Sdz = border_sums(dz).  Exact identity (exchange the order of the two sums)."""
+    dbeta = np.einsum("yxco,yxo->c", w_hwio, sdz)
+    dgamma = np.einsum("yxco,yxco->c", w_hwio, dw_a - mu[None, None, :, None] * sdz[:, :, None, :]) * rstd
+    return dbeta, dgamma

@@ -165,6 +165,61 @@ __global__ void __launch_bounds__(TPB) wgrad_fold_fix_kernel(float* __restrict__
   }
 }
 
+// Backward sums of the BatchNorm that FEEDS a convolution, from that convolution's weight gradient (oracle/unet_numpy.py
+// bn_bwd_sums_from_wgrad): with dy = dgrad(dz, W) the gradient w.r.t. the BatchNorm output,
+//   dbeta[c]  = sum_p dy[p][c]            = sum_{co, tap} W[co][tap][c] * Sdz[tap][co]
+//   dgamma[c] = sum_p dy[p][c] xhat[p][c] = rstd[c] * sum_{co, tap} W[co][tap][c] * (dW_a[co][tap][c] - mean[c] * Sdz[tap][co])
+// dW_a = the consumer's weight gradient computed on the pre-BatchNorm activation `a` (before ub_wgrad_fold_fix), Sdz = its border
+// sums (taps == 1: Sdz = the bias gradient).  Replaces a read of dy and `a` (two full tensors) by a read of two weight-sized ones.
+// Block = 32 channels x 8 row groups; rows (co, tap) are strided over the groups, fp64 accumulation, fixed combination order.
+template <typename TW>
+__global__ void __launch_bounds__(256) bn_sums_wgrad_kernel(const TW* __restrict__ w, const float* __restrict__ dw, const float* __restrict__ sdz,
+                                                           int Cout, int taps, int Cin, int c_begin, int c_count,
+                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           float* __restrict__ dbeta, float* __restrict__ dgamma) {
+  __shared__ double sh[2][8][32];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double sb = 0.0, sg = 0.0;
+  if (c < c_count) {
+    const float mu = mean[c];
+    const int rows = Cout * taps;
+    for (int r0 = grp; r0 < rows; r0 += 8 * 4) {
+      float wv[4], dv[4], sv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u * 8;
+        if (r < rows) {
+          const size_t i = (size_t)r * Cin + c_begin + c;
+          wv[u] = (float)w[i];
+          dv[u] = __ldg(dw + i);
+          sv[u] = __ldg(sdz + (size_t)(r % taps) * Cout + r / taps);
+        } else {
+          wv[u] = dv[u] = sv[u] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sb += (double)wv[u] * (double)sv[u];
+        sg += (double)wv[u] * ((double)dv[u] - (double)mu * (double)sv[u]);
+      }
+    }
+  }
+  sh[0][grp][lane] = sb;
+  sh[1][grp][lane] = sg;
+  __syncthreads();
+  if (grp == 0 && c < c_count) {
+    double tb = 0.0, tg = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      tb += sh[0][g][lane];
+      tg += sh[1][g][lane];
+    }
+    dbeta[c] = (float)tb;
+    dgamma[c] = (float)(tg * (double)rstd[c]);
+  }
+}
+
 // 1x1 head (no padding: one bias): w' = w * s[c], b' = b + sum_c w * t[c]; one block, K <= UB_MAX_CLASSES
 __global__ void fold_head_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ mean,
                                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -242,6 +297,21 @@ int ub_border_sums(const void* dz, const float* total, float* sdz, float* scratc
   else UB_CHECK_ARG(false, "border_sums: bad dtype %d", dtype);
   UB_LAUNCH_CHECK();
   border_finish_kernel<<<(C + 31) / 32, 256, 0, stream>>>(scratch, total, sdz, C, chunks);
+  UB_LAUNCH_CHECK();
+  return UB_OK;
+}
+
+int ub_bn_bwd_sums_wgrad(const void* w, int w_dtype, const float* dw_a, const float* sdz, int Cout, int taps, int Cin, int c_begin, int c_count,
+                         const float* mean, const float* rstd, float* dbeta, float* dgamma, cudaStream_t stream) {
+  UB_CHECK_ARG(w && dw_a && sdz && mean && rstd && dbeta && dgamma, "bn_bwd_sums_wgrad: null pointer");
+  UB_CHECK_ARG(Cout > 0 && taps > 0 && Cin > 0 && c_begin >= 0 && c_count > 0 && c_begin + c_count <= Cin, "bn_bwd_sums_wgrad: bad channel range");
+  const int grid = (c_count + 31) / 32;
+  if (w_dtype == UB_BF16)
+    bn_sums_wgrad_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)w, dw_a, sdz, Cout, taps, Cin, c_begin, c_count, mean, rstd, dbeta, dgamma);
+  else if (w_dtype == UB_F32)
+    bn_sums_wgrad_kernel<float><<<grid, 256, 0, stream>>>((const float*)w, dw_a, sdz, Cout, taps, Cin, c_begin, c_count, mean, rstd, dbeta, dgamma);
+  else
+    UB_CHECK_ARG(false, "bn_bwd_sums_wgrad: bad weight dtype %d", w_dtype);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -78,6 +78,10 @@ class UNet:
         self._graphs = {}
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
+        # bf16 folded path: dbeta / dgamma of a BatchNorm whose only consumer is a folded convolution come from that convolution's weight
+        # gradient and border sums (ub_bn_bwd_sums_wgrad) instead of a reduction pass over the gradient tensor
+        self.bn_algebra = os.environ.get("UB_BN_ALGEBRA", "1") == "1"
+        self._sums_ready = set()
         self.fuse_finalize = os.environ.get("UB_FUSE_FINALIZE", "1") == "1"   # bf16 path: the forward's last CTA finalises the BatchNorm statistics
         self.fuse_bn_reduce_ew = os.environ.get("UB_FUSE_EW", "0") == "1"   # ... and in the pool-backward / head-backward passes
         # bf16 training forward with the producers' BatchNorm folded into the consumer convolutions (_forward_train_folded):
@@ -786,15 +790,18 @@ class UNet:
                        relu, self.act_code)
             return g
         mean, rstd = self._bn_vectors(L, True)
-        if self._red_ready == L.name:          # the dgrad that produced g already accumulated [sum dy | sum dy*xhat]
-            src = self.partial_red
-        else:
-            self._call("ub_bn_bwd_reduce", g, a, mean, rstd, self.partial, M, C, self.act_code)
-            src = self.partial
-        self._red_ready = None
-        # [sum dy | sum dy*xhat] lands directly in the flat gradient buffer: beta and gamma segments are adjacent
         assert L.off_gamma == L.off_beta + C
-        self._call("ub_reduce_rows", src, _C.UB_STATS_ROWS, 2 * C, 2 * C, self.G[L.off_beta:L.off_beta + 2 * C], 1.0)
+        if L.name in self._sums_ready:         # dbeta / dgamma were derived from the consumer's weight gradient (ub_bn_bwd_sums_wgrad)
+            self._sums_ready.discard(L.name)
+        else:
+            if self._red_ready == L.name:      # the dgrad that produced g already accumulated [sum dy | sum dy*xhat]
+                src = self.partial_red
+            else:
+                self._call("ub_bn_bwd_reduce", g, a, mean, rstd, self.partial, M, C, self.act_code)
+                src = self.partial
+            # [sum dy | sum dy*xhat] lands directly in the flat gradient buffer: beta and gamma segments are adjacent
+            self._call("ub_reduce_rows", src, _C.UB_STATS_ROWS, 2 * C, 2 * C, self.G[L.off_beta:L.off_beta + 2 * C], 1.0)
+        self._red_ready = None
         dbeta, dgamma = self.G[L.off_beta:L.off_beta + C], self.G[L.off_gamma:L.off_gamma + C]
         self._call("ub_bn_bwd_apply", g, a, mean, rstd, self.P[L.off_gamma:L.off_gamma + C], dbeta, dgamma, g, self.partial, M, C,
                    relu, self.act_code)
@@ -812,6 +819,17 @@ class UNet:
             x0 = self._b("a:" + p0.name) if p0 is not None else x0
             x1 = self._b("a:" + p1.name) if p1 is not None else x1
 
+        # BatchNorm layers whose backward sums follow from THIS layer's weight gradient: the folded sources whose only consumer is this
+        # conv (source 0 of a concat is an encoder skip, which also feeds a max-pool: its sums keep their own pass)
+        algebra = []
+        if self.bn_algebra and L.fold is not None and self.precision == "bf16" and not getattr(self, "_bwd_inference", False):
+            p0, p1 = L.fold
+            if p0 is not None and c1 == 0:
+                algebra.append((p0, 0))
+            if p1 is not None:
+                algebra.append((p1, c0))
+        sums_done = [None]
+
         def wgrad():
             self._call("ub_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, ws, ws.numel(), N, h, w)
             if L.fold is not None:
@@ -819,6 +837,14 @@ class UNet:
                 sdz = self._ensure("fold_sdz", 9 * 2048, torch.float32)
                 scr = self._ensure("fold_scr", _C.MACROS["UB_BORDER_CHUNKS"] * 8 * 2048, torch.float32)
                 self._call("ub_border_sums", dz, self.G[L.off_b:L.off_b + L.cout], sdz, scr, N, h, w, L.cout, self.act_code)
+                for p, cb in algebra:
+                    pm, pr = self._bn_vectors(p, True)
+                    self._call("ub_bn_bwd_sums_wgrad", self.S[L.off_w:L.off_w + L.n_w], _C.UB_BF16, dw, sdz, L.cout, 9, L.cin, cb, p.cout, pm, pr,
+                               self.G[p.off_beta:p.off_beta + p.cout], self.G[p.off_gamma:p.off_gamma + p.cout])
+                    self._sums_ready.add(p.name)
+                if algebra and self.device.type == "cuda":   # the BatchNorm backward of those layers (main stream) waits for the sums, not the fix-up
+                    sums_done[0] = torch.cuda.Event()
+                    sums_done[0].record(torch.cuda.current_stream(self.device))
                 self._call("ub_wgrad_fold_fix", dw, self._b("fold_s:" + L.name), self._b("fold_t:" + L.name), sdz, L.cout, L.cin)
 
         if self.precision == "bf16":
@@ -827,7 +853,7 @@ class UNet:
                 wgrad()
             # worth it only where the K loop is long enough to hide the longer epilogue (measured: 64-output-channel layers,
             # whose dgrad has a single 64-channel K block, lose more in the dgrad than the separate reduction pass costs)
-            if dx0 is not None and red is not None and self.fuse_bn_reduce and L.cout >= 128:
+            if dx0 is not None and red is not None and self.fuse_bn_reduce and L.cout >= 128 and not any(p is red for p, _ in algebra):
                 rm, rr = self._bn_vectors(red, True)
                 self._call("ub_conv3x3_dgrad_bnred", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w, self._b("a:" + red.name), rm, rr,
                            self.partial_red)
@@ -837,6 +863,8 @@ class UNet:
             if self.overlap_wgrad:
                 with torch.cuda.stream(self._fork_side()):
                     wgrad()
+                if sums_done[0] is not None:
+                    torch.cuda.current_stream(self.device).wait_event(sums_done[0])
         else:
             self._call("ub_check_conv3x3_wgrad", x0, c0, x1, c1, dz, L.cout, dw, N, h, w)
             if dx0 is not None:
@@ -879,6 +907,13 @@ class UNet:
         ncomp = K * 64 + K
         self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, ncomp, K * 64, self.G[L.off_w:L.off_w + K * 64], 1.0)
         self._call("ub_reduce_rows", self.partial[K * 64:], _C.UB_STATS_ROWS, ncomp, K, self.G[L.off_b:L.off_b + K], 1.0)
+        if L.fold is not None and self.bn_algebra and not infer and not (self.fuse_bn_reduce_ew and K <= 4):
+            # dec1b's BatchNorm-backward sums from the head's weight gradient on `a` and its bias gradient (a 1x1 conv: one tap, no border)
+            Ld = Ls["dec1b"]
+            pm, pr = self._bn_vectors(Ld, True)
+            self._call("ub_bn_bwd_sums_wgrad", self.P[L.off_w:L.off_w + K * 64], _C.UB_F32, self.G[L.off_w:L.off_w + K * 64],
+                       self.G[L.off_b:L.off_b + K], K, 1, 64, 0, 64, pm, pr, self.G[Ld.off_beta:Ld.off_beta + 64], self.G[Ld.off_gamma:Ld.off_gamma + 64])
+            self._sums_ready.add("dec1b")
         if L.fold is not None:          # dW[k][c] = s[c] dW_a[k][c] + t[c] db[k]
             self._call("ub_head_wgrad_fold_fix", self.G[L.off_w:L.off_w + K * 64], self.G[L.off_b:L.off_b + K], self._b("fold_s:head"),
                        self._b("fold_t:head"), K)

@@ -983,6 +983,61 @@ def case_deconv_fwd_bn(Cin=128, Cout=64, N=2, h=12, w=20, seed=51):
     return r
 
 
+def case_bn_sums_wgrad(C0=64, C1=0, Cout=64, N=2, H=24, W=40, seed=60):
+    """ub_bn_bwd_sums_wgrad: dbeta / dgamma of the BatchNorm(s) feeding a convolution from that convolution's weight gradient on `a`
+    (ub_conv3x3_wgrad) and border sums (ub_border_sums) == the sums over the dgrad output itself (oracle conv_dgrad, fp64)"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    Cin = C0 + C1
+    a = bf16_round(np.maximum(rng.normal(0.3, 1.0, size=(N, H, W, Cin)), 0))
+    dz = bf16_round(rng.normal(size=(N, H, W, Cout)))
+    w = bf16_round(rng.normal(size=(3, 3, Cin, Cout)) / np.sqrt(9 * Cout))
+    mu = a.mean((0, 1, 2))
+    rstd = 1.0 / np.sqrt(a.var((0, 1, 2)) + 1e-3)
+    dy = ON.conv_dgrad(dz, w)
+    db_ref = dy.sum((0, 1, 2))
+    dg_ref = (dy * (a - mu) * rstd).sum((0, 1, 2))
+    dzd = dev(dz, torch.bfloat16)
+    dw = torch.empty(Cout * 9 * Cin, device="cuda")
+    nb = C.lib.ub_conv3x3_wgrad_workspace_bytes(C0, C1, Cout, N, H, W)
+    ws = torch.empty(max(nb, 16), device="cuda", dtype=torch.uint8)
+    C.call("ub_conv3x3_wgrad", dev(a[..., :C0], torch.bfloat16), C0, dev(a[..., C0:], torch.bfloat16) if C1 else None, C1, dzd, Cout, dw, ws, nb, N, H, W, stream())
+    total = dev(dz.sum((0, 1, 2)), torch.float32)
+    sdz = torch.empty((9, Cout), device="cuda")
+    scratch = torch.empty(C.MACROS["UB_BORDER_CHUNKS"] * 8 * Cout, device="cuda")
+    C.call("ub_border_sums", dzd, total, sdz, scratch, N, H, W, Cout, C.UB_BF16, stream())
+    wd = dev(pack_conv(w), torch.bfloat16)
+    r = {}
+    for name, cb, cc in ([("src0", 0, C0)] + ([("src1", C0, C1)] if C1 else [])):
+        dbeta = torch.full((cc,), float("nan"), device="cuda")
+        dgamma = torch.full((cc,), float("nan"), device="cuda")
+        C.call("ub_bn_bwd_sums_wgrad", wd, C.UB_BF16, dw, sdz, Cout, 9, Cin, cb, cc, dev(mu[cb:cb + cc], torch.float32), dev(rstd[cb:cb + cc], torch.float32),
+               dbeta, dgamma, stream())
+        torch.cuda.synchronize()
+        r["e_dbeta_" + name] = rel_err(dbeta.cpu().numpy(), db_ref[cb:cb + cc])
+        r["e_dgamma_" + name] = rel_err(dgamma.cpu().numpy(), dg_ref[cb:cb + cc])
+    r["ok"] = bool(all(v < 2e-4 for v in r.values()))
+    return r
+
+
+def case_bn_sums_head(K=2, P=4099, seed=61):
+    """the same for the 1x1 head (one tap, no border): sums of dx = W^T dz against the direct sums"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    a = np.maximum(rng.normal(0.3, 1.0, size=(P, 64)), 0)
+    dzk = rng.normal(size=(P, K))
+    w = rng.normal(size=(K, 64)) / 8
+    mu, rstd = a.mean(0), 1.0 / np.sqrt(a.var(0) + 1e-3)
+    dx = dzk @ w
+    dbeta, dgamma = torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+    C.call("ub_bn_bwd_sums_wgrad", dev(w, torch.float32), C.UB_F32, dev(dzk.T @ a, torch.float32), dev(dzk.sum(0), torch.float32), K, 1, 64, 0, 64,
+           dev(mu, torch.float32), dev(rstd, torch.float32), dbeta, dgamma, stream())
+    torch.cuda.synchronize()
+    r = dict(e_dbeta=rel_err(dbeta.cpu().numpy(), dx.sum(0)), e_dgamma=rel_err(dgamma.cpu().numpy(), (dx * (a - mu) * rstd).sum(0)))
+    r["ok"] = bool(r["e_dbeta"] < 1e-4 and r["e_dgamma"] < 1e-4)
+    return r
+
+
 def case_conv_first_tiles(Cin=1, H=1000, W=1190, seed=44):
     """ub_conv_first_fwd_affine_tiles (tiles read in place, mirrored past the image edge) == ub_conv_first_fwd_affine on tiles cut
     from the explicitly reflect-padded image (np.pad(mode='reflect'), UNet/inference.py:46): bit-exact"""
@@ -1097,4 +1152,11 @@ CASES = {
     "deconv_fwd_bn_128_64": case_deconv_fwd_bn,
     "deconv_fwd_bn_1024_512": lambda: case_deconv_fwd_bn(1024, 512, N=1, h=8, w=12, seed=56),
     "deconv_fwd_bn_256_128": lambda: case_deconv_fwd_bn(256, 128, N=3, h=32, w=32, seed=57),
+    # BatchNorm-backward sums from the consumer's weight gradient
+    "bn_sums_wgrad_64_64": case_bn_sums_wgrad,
+    "bn_sums_wgrad_cat_64+64_128": lambda: case_bn_sums_wgrad(64, 64, 128, H=18, W=20, seed=62),
+    "bn_sums_wgrad_256_512": lambda: case_bn_sums_wgrad(256, 0, 512, N=1, H=8, W=16, seed=63),
+    "bn_sums_wgrad_64_64_2x2": lambda: case_bn_sums_wgrad(64, 0, 64, N=3, H=2, W=2, seed=64),
+    "bn_sums_head_k2": case_bn_sums_head,
+    "bn_sums_head_k8": lambda: case_bn_sums_head(8, seed=65),
 }

@@ -252,3 +252,20 @@ def test_batchnorm_fold_identities():
     Tt = rng.normal(size=(3, 3, 2))
     bias = ON.border_case_bias(Tt, np.zeros(2))
     assert np.allclose(bias[1, 1], Tt.sum((0, 1))) and np.allclose(bias[0, 0], Tt[1:, 1:].sum((0, 1))) and np.allclose(bias[2, 1], Tt[:2].sum((0, 1)))
+
+
+def test_bn_backward_sums_from_the_consumer_weight_gradient():
+    """the identity behind ub_bn_bwd_sums_wgrad: dbeta / dgamma of the producer's BatchNorm from the consumer's weight gradient on
+    `a` and its border sums == the sums over the gradient tensor itself (fp64), incl. 2-pixel images and a concat consumer"""
+    from oracle import unet_numpy as ON
+    rng = np.random.default_rng(5)
+    for (N, H, W, Cin, Cout) in [(2, 7, 9, 5, 4), (1, 2, 2, 3, 6), (3, 16, 4, 8, 2)]:
+        a = np.maximum(rng.normal(0.3, 1, size=(N, H, W, Cin)), 0)
+        dz = rng.normal(size=(N, H, W, Cout))
+        w = rng.normal(size=(3, 3, Cin, Cout))
+        mu, rstd = a.mean((0, 1, 2)), 1 / np.sqrt(a.var((0, 1, 2)) + 1e-3)
+        dy = ON.conv_dgrad(dz, w)
+        dw_a, _ = ON.conv_wgrad(a, dz, 3)
+        dbeta, dgamma = ON.bn_bwd_sums_from_wgrad(w, dw_a, ON.border_sums(dz), mu, rstd)
+        assert np.allclose(dbeta, dy.sum((0, 1, 2)), rtol=1e-10, atol=1e-10)
+        assert np.allclose(dgamma, (dy * (a - mu) * rstd).sum((0, 1, 2)), rtol=1e-10, atol=1e-10)

@@ -112,6 +112,18 @@ def test_optional_schedules():
     assert c["ub_bn_apply"] == 4 and c["ub_bn_apply_pool"] == 1 and c["ub_bn_pool"] == 3          # botb, dec2b-4b | enc4b | enc1b-3b
     assert c["ub_border_sums"] == 13 and c["ub_wgrad_fold_fix"] == 13 and c["ub_conv3x3_wgrad"] == 17
     assert c["ub_fold_head_weights"] == 1 and c["ub_head_wgrad_fold_fix"] == 1 and c["ub_head_fwd"] == 1
+    # 14 BatchNorm layers get dbeta / dgamma from their consumer's weight gradient: enc<l>a, bota, dec<l>a, up<l> and dec1b (head);
+    # the 8 others (encoder skips, layers in front of dropout or of a transposed convolution) keep a reduction over the gradient
+    assert c["ub_bn_bwd_sums_wgrad"] == 14
+    assert c.get("ub_bn_bwd_reduce", 0) + c.get("ub_conv3x3_dgrad_bnred", 0) == 8 and c["ub_bn_bwd_apply"] == 22
+    before = [n for n, _ in m.calls]
+    for i, n in enumerate(before):           # the sums are taken from dW_a, i.e. before the fold fix-up rewrites the weight gradient
+        if n == "ub_bn_bwd_sums_wgrad" and m.args[i][5] == 9:
+            assert "ub_wgrad_fold_fix" in before[i + 1:i + 3] and before[i - 1] in ("ub_border_sums", "ub_bn_bwd_sums_wgrad")
+    m2 = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    m2.bn_algebra = False                    # UB_BN_ALGEBRA=0
+    c2 = _count(_step(m2))
+    assert "ub_bn_bwd_sums_wgrad" not in c2 and c2.get("ub_bn_bwd_reduce", 0) + c2.get("ub_conv3x3_dgrad_bnred", 0) == 22
     folded = {l for (n, l), a in zip(m.calls, m.args) if n == "ub_conv3x3_fwd_bn" and a[6] == 1}
     assert folded == {"enc1b", "enc2b", "enc3b", "enc4b", "botb", "dec4a", "dec4b", "dec3a", "dec3b", "dec2a", "dec2b", "dec1a", "dec1b"}
     # back to the default schedule on the same object
