@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) bn_sums_wgrad_kernel(const TW* __restrict
   }
 }
 
-// 1x1 head (no padding: one bias): w' = w * s[c], b' = b + sum_c w * t[c]; one block, K <= UB_MAX_CLASSES
+// 1x1 head (no padding: one bias): w' = w * s[c], b' = b + sum_c w * t[c]; one block, K <= UB_MAX_CLASSES_ANY
 __global__ void fold_head_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ mean,
                                  const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                                  float* __restrict__ w_out, float* __restrict__ bias_out, float* __restrict__ scale_out,
@@ -258,7 +258,7 @@ extern "C" {
 
 int ub_fold_head_weights(const float* w, const float* bias, const float* mean, const float* rstd, const float* gamma, const float* beta,
                          float* w_out, float* bias_out, float* scale_out, float* shift_out, int K, cudaStream_t stream) {
-  UB_CHECK_ARG(w && mean && rstd && gamma && beta && w_out && bias_out && scale_out && shift_out && K >= 1 && K <= UB_MAX_CLASSES,
+  UB_CHECK_ARG(w && mean && rstd && gamma && beta && w_out && bias_out && scale_out && shift_out && K >= 1 && K <= UB_MAX_CLASSES_ANY,
                "fold_head_weights: bad args");
   fold_head_kernel<<<1, 64, 0, stream>>>(w, bias, mean, rstd, gamma, beta, w_out, bias_out, scale_out, shift_out, K);
   UB_LAUNCH_CHECK();
@@ -266,7 +266,7 @@ int ub_fold_head_weights(const float* w, const float* bias, const float* mean, c
 }
 
 int ub_head_wgrad_fold_fix(float* dw, const float* db, const float* scale, const float* shift, int K, cudaStream_t stream) {
-  UB_CHECK_ARG(dw && db && scale && shift && K >= 1 && K <= UB_MAX_CLASSES, "head_wgrad_fold_fix: bad args");
+  UB_CHECK_ARG(dw && db && scale && shift && K >= 1 && K <= UB_MAX_CLASSES_ANY, "head_wgrad_fold_fix: bad args");
   head_wgrad_fold_fix_kernel<<<(K * 64 + 127) / 128, 128, 0, stream>>>(dw, db, scale, shift, K);
   UB_LAUNCH_CHECK();
   return UB_OK;

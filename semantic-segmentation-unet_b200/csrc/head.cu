@@ -837,6 +837,18 @@ inline int grid_for(long long work_items, int per_block, int cap) {
 
 }  // namespace
 
+// class-per-lane kernels for UB_MAX_CLASSES < K <= UB_MAX_CLASSES_ANY (csrc/head_generic.cu)
+int ubg_head_fwd(const void* x, const float* w, const float* b, float* a_out, float* partial, long long P, int K, int dtype, cudaStream_t stream);
+int ubg_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int ntiles, int h, int wd,
+                    const int* geo, unsigned char* mask, long long mask_ld, float* softmax_out, int dtype, cudaStream_t stream);
+int ubg_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const unsigned char* labels,
+                  const float* class_w, float inv_denom, float acc_scale, float* softmax_out, float* dlogits, float* partial, long long P, int K,
+                  cudaStream_t stream);
+int ubg_head_bwd_reduce(const float* dy, const float* a, const float* mean, const float* rstd, float* partial, long long P, int K,
+                        cudaStream_t stream);
+int ubg_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd, const float* gamma,
+                       const float* dbeta, const float* dgamma, void* dx, float* partial, long long P, int K, int dtype, cudaStream_t stream);
+
 #define UB_DISPATCH_T(dtype, ...)                                   \
   do {                                                              \
     if ((dtype) == UB_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
@@ -947,7 +959,9 @@ int ub_conv_first_dgrad(const void* dz, const float* w, float* dx_nchw, int N, i
 int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, float* partial, long long P, int K, int dtype,
                 cudaStream_t stream) {
   UB_CHECK_ARG(x && w && b && a_out && P > 0, "head_fwd: bad args");
-  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_fwd: number_classes=%d exceeds UB_MAX_CLASSES=%d", K, KMAX);
+  UB_CHECK_SHAPE(K >= 1 && K <= UB_MAX_CLASSES_ANY, "head_fwd: number_classes=%d must be in [1, %d]", K, UB_MAX_CLASSES_ANY);
+  UB_CHECK_ARG(dtype == UB_BF16 || dtype == UB_F32, "head_fwd: bad dtype %d", dtype);
+  if (K > KMAX) return ubg_head_fwd(x, w, b, a_out, partial, P, K, dtype, stream);
   const int grid = grid_for(P, 64 * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * K, stream));
   UB_DISPATCH_T(dtype, UB_DISPATCH_K(K, (head_fwd_kernel<T, KK><<<grid, TPB, 0, stream>>>((const T*)x, w, b, a_out, partial, P))));
@@ -959,7 +973,8 @@ int ub_head_loss(const float* a, const float* mean, const float* rstd, const flo
                  const float* class_w, float inv_denom, float acc_scale, float* softmax_out, float* dlogits, float* partial, long long P,
                  int K, cudaStream_t stream) {
   UB_CHECK_ARG(a && mean && rstd && gamma && beta && P > 0, "head_loss: bad args");
-  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_loss: number_classes=%d exceeds UB_MAX_CLASSES=%d", K, KMAX);
+  UB_CHECK_SHAPE(K >= 1 && K <= UB_MAX_CLASSES_ANY, "head_loss: number_classes=%d must be in [1, %d]", K, UB_MAX_CLASSES_ANY);
+  if (K > KMAX) return ubg_head_loss(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, softmax_out, dlogits, partial, P, K, stream);
   const int grid = grid_for(P, TPB * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2, stream));
   head_loss_kernel<<<grid, TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, softmax_out, dlogits, partial, P, K);
@@ -977,7 +992,8 @@ int ub_onehot_to_index(const int* onehot, unsigned char* idx, long long P, int K
 int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const float* rstd, float* partial, long long P, int K,
                        cudaStream_t stream) {
   UB_CHECK_ARG(dy && a && mean && rstd && partial && P > 0, "head_bwd_reduce: bad args");
-  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_bwd_reduce: K");
+  UB_CHECK_SHAPE(K >= 1 && K <= UB_MAX_CLASSES_ANY, "head_bwd_reduce: K");
+  if (K > KMAX) return ubg_head_bwd_reduce(dy, a, mean, rstd, partial, P, K, stream);
   const int grid = grid_for(P, TPB * 4, UB_STATS_ROWS);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * K, stream));
   head_bwd_reduce_kernel<<<grid, TPB, 0, stream>>>(dy, a, mean, rstd, partial, P, K);
@@ -991,7 +1007,12 @@ static int head_bwd_apply_launch(const float* dy, const float* a, const void* x,
                                  int dtype, const void* red_a, const float* red_mean, const float* red_rstd, float* red_out,
                                  cudaStream_t stream) {
   UB_CHECK_ARG(dy && a && x && w && mean && rstd && gamma && dbeta && dgamma && partial && P > 0, "head_bwd_apply: bad args");
-  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_bwd_apply: K");
+  UB_CHECK_SHAPE(K >= 1 && K <= UB_MAX_CLASSES_ANY, "head_bwd_apply: K");
+  UB_CHECK_ARG(dtype == UB_BF16 || dtype == UB_F32, "head_bwd_apply: bad dtype %d", dtype);
+  if (K > KMAX) {
+    UB_CHECK_SHAPE(!red_out, "head_bwd_apply_bnred: the fused reduction exists for K <= %d only", KMAX);
+    return ubg_head_bwd_apply(dy, a, x, w, mean, rstd, gamma, dbeta, dgamma, dx, partial, P, K, dtype, stream);
+  }
   const int grid = grid_for(P, 64 * 4, UB_STATS_ROWS);
   UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * (K * 64 + K), stream));
   if (red_out) {
@@ -1038,7 +1059,9 @@ int ub_head_argmax(const void* x, const float* w, const float* b, const float* s
                    const int* geo, unsigned char* mask, long long mask_ld, float* softmax_out, int dtype, cudaStream_t stream) {
   UB_CHECK_ARG(x && w && b && scale && shift && (mask || softmax_out) && ntiles > 0 && h > 0 && wd > 0, "head_argmax: bad args");
   UB_CHECK_ARG(!mask || geo, "head_argmax: a mask needs the tile geometry");
-  UB_CHECK_SHAPE(K >= 1 && K <= KMAX, "head_argmax: K");
+  UB_CHECK_SHAPE(K >= 1 && K <= UB_MAX_CLASSES_ANY, "head_argmax: K");
+  UB_CHECK_ARG(dtype == UB_BF16 || dtype == UB_F32, "head_argmax: bad dtype %d", dtype);
+  if (K > KMAX) return ubg_head_argmax(x, w, b, scale, shift, K, ntiles, h, wd, geo, mask, mask_ld, softmax_out, dtype, stream);
   const long long P = (long long)h * wd;
   int gx = grid_for(P, 32 * 4, ub_num_sms() * 8 / (ntiles < 8 ? ntiles : 8));
   if (gx < 1) gx = 1;

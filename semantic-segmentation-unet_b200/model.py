@@ -50,8 +50,9 @@ class UNet:
             raise RuntimeError("unetb200 requires a CUDA device (sm_100a); there is no CPU fallback")
         if label_smoothing != 0:
             raise NotImplementedError("label_smoothing != 0 is not used by the reference (UNet/model.py:65) and not built")
-        if number_classes < 1 or number_classes > _C.UB_MAX_CLASSES:
-            raise ValueError(f"number_classes must be in [1, {_C.UB_MAX_CLASSES}]")
+        if number_classes < 1 or number_classes > _C.MACROS["UB_MAX_CLASSES_ANY"]:
+            # labels and masks are uint8 on this path, as in the reference's databases (UNet/build_lmdb.py:151 forces uint8 masks)
+            raise ValueError(f"number_classes must be in [1, {_C.MACROS['UB_MAX_CLASSES_ANY']}]")
         if number_channels < 1 or number_channels > 4:
             raise ValueError("number_channels must be in [1, 4]")
         if precision not in ("bf16", "fp32"):
@@ -200,7 +201,8 @@ class UNet:
         wt_dtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
         self.WT = {n: torch.zeros(L.n_w, dtype=wt_dtype, device=dev) for n, L in self.layers.items() if L.kind in ("conv", "deconv")}
         self.metrics = torch.zeros(2, dtype=torch.float32, device=dev)    # [loss, accuracy] of the last step
-        self.partial = torch.zeros(_C.UB_STATS_ROWS * 2 * 2048, dtype=torch.float32, device=dev)
+        # partial rows of every reduction: [UB_STATS_ROWS][<= 2 * 2048 channels], or the head's {dW[K][64], db[K]} rows
+        self.partial = torch.zeros(_C.UB_STATS_ROWS * max(2 * 2048, K * 64 + K), dtype=torch.float32, device=dev)
         self.partial_red = torch.zeros(_C.UB_STATS_ROWS * 2 * 1024, dtype=torch.float32, device=dev)   # BN-backward sums produced by a fused dgrad
         self._red_ready = None                                                                          # layer whose sums partial_red holds
         self.red = torch.zeros(4096, dtype=torch.float32, device=dev)

@@ -731,6 +731,9 @@ CASES = {
     "live_fp32_c3k8": lambda: case_live("fp32", N=1, C=3, H=80, W=112, K=8, seed=22, gb=4),
     "live_bf16_c1k2": lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True),
     "live_bf16_c3k8": lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True),
+    # number_classes > 8: the class-per-lane head kernels inside the whole graph (fp32 check mode <= 1e-4, bf16 at the storage floor)
+    "live_fp32_c3k20": lambda: case_live("fp32", N=1, C=3, H=64, W=80, K=20, seed=26, gb=2),
+    "live_bf16_c1k40": lambda: case_live("bf16", N=1, C=1, H=96, W=96, K=40, seed=27, gb=2, floor=True),
     "golden_c1_k2_fp32": lambda: case_golden("graph_c1_k2", "fp32"),
     "golden_c3_k8_fp32": lambda: case_golden("graph_c3_k8", "fp32"),
     "golden_c1_k2_bf16": lambda: case_golden("graph_c1_k2", "bf16"),

@@ -410,6 +410,16 @@ def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
     gw = torch.empty(K * 64 + K, device="cuda")
     C.call("ub_head_bwd_apply", dl, a_d, xd, wd, mean, rstd, gd, red[:K], red[K:], dx, partial, P, K, C.UB_F32, stream())
     C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, K * 64 + K, K * 64 + K, gw, 1.0, stream())
+    if K > C.UB_MAX_CLASSES:          # class-per-lane kernels (csrc/head_generic.cu): no fused-reduction variant
+        torch.cuda.synchronize()
+        la = la.cpu().numpy()
+        r = dict(e_a=rel_err(a_d.cpu().numpy(), a), e_sm=rel_err(sm.cpu().numpy(), p), e_loss=abs(la[0] - loss_ref) / abs(loss_ref),
+                 e_acc=abs(la[1] - acc_ref), e_dl=rel_err(dl.cpu().numpy(), dy_ref), e_dbeta=rel_err(red[:K].cpu().numpy(), dbeta),
+                 e_dgamma=rel_err(red[K:].cpu().numpy(), dgamma), e_dx=rel_err(dx.cpu().numpy(), dx_ref),
+                 e_dW=rel_err(gw[:K * 64].cpu().numpy().reshape(K, 64), dW_ref), e_db=rel_err(gw[K * 64:].cpu().numpy(), db_ref))
+        r = {k: float(v) for k, v in r.items()}
+        r["ok"] = bool(all(v < 2e-4 for v in r.values()))
+        return r
     # fused variant: same dx / partials, plus the BatchNorm-backward sums of the 64-channel tensor below the head
     ra = np.maximum(rng.normal(0.2, 1.0, size=(P, 64)), 0).astype(np.float32)
     rmean = rng.normal(0.4, 0.1, size=64).astype(np.float32)
@@ -1038,6 +1048,43 @@ def case_bn_sums_head(K=2, P=4099, seed=61):
     return r
 
 
+def case_head_argmax(K=2, ntiles=3, h=24, w=40, seed=70, dtype="f32"):
+    """ub_head_argmax: relu(x . w + b) * scale + shift -> per-pixel argmax of each tile's crop box written into the mask at its
+    destination, and the softmax of the model-call contract (UNet/inference.py:105-107), against numpy (first maximum on ties)"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    tdt, code = (torch.bfloat16, C.UB_BF16) if dtype == "bf16" else (torch.float32, C.UB_F32)
+    x = rng.normal(size=(ntiles, h, w, 64)).astype(np.float32)
+    if dtype == "bf16":
+        x = bf16_round(x).astype(np.float32)
+    wt = (rng.normal(size=(K, 64)) / 8).astype(np.float32)
+    b = (rng.normal(size=K) * 0.1).astype(np.float32)
+    sc, sh = rng.uniform(0.5, 1.5, K).astype(np.float32), rng.normal(size=K).astype(np.float32)
+    y = np.maximum(x.astype(np.float64) @ wt.T.astype(np.float64) + b, 0) * sc + sh
+    e = np.exp(y - y.max(-1, keepdims=True))
+    p = e / e.sum(-1, keepdims=True)
+    geo = np.array([[2 + t, h - 3, 1, w - 2 - t, t * h, 5 * t] for t in range(ntiles)], dtype=np.int32)
+    ld = w + 5 * ntiles
+    mask = torch.full((ntiles * h, ld), 255, dtype=torch.uint8, device="cuda")
+    want = np.full((ntiles * h, ld), 255, dtype=np.uint8)
+    am = y.argmax(-1)
+    top2 = np.sort(y, -1)
+    margin = top2[..., -1] - top2[..., -2] if K > 1 else np.ones(y.shape[:-1])
+    sure = np.zeros((ntiles * h, ld), dtype=bool)
+    for t, (cy0, cy1, cx0, cx1, dy, dx) in enumerate(geo):
+        want[dy:dy + cy1 - cy0, dx:dx + cx1 - cx0] = am[t, cy0:cy1, cx0:cx1]
+        sure[dy:dy + cy1 - cy0, dx:dx + cx1 - cx0] = margin[t, cy0:cy1, cx0:cx1] > 1e-4
+    sm = torch.empty((ntiles, h, w, K), dtype=torch.float32, device="cuda")
+    C.call("ub_head_argmax", dev(x, tdt), dev(wt, torch.float32), dev(b, torch.float32), dev(sc, torch.float32), dev(sh, torch.float32), K, ntiles, h, w,
+           dev(geo, torch.int32), mask, ld, sm, code, stream())
+    torch.cuda.synchronize()
+    got = mask.cpu().numpy()
+    r = dict(mask_untouched_ok=bool(np.array_equal(got == 255, want == 255)), mask_agree=float((got == want)[sure].mean()),
+             e_softmax=float(np.abs(sm.cpu().numpy() - p).max()))
+    r["ok"] = bool(r["mask_untouched_ok"] and r["mask_agree"] == 1.0 and r["e_softmax"] < 1e-5)
+    return r
+
+
 def case_conv_first_tiles(Cin=1, H=1000, W=1190, seed=44):
     """ub_conv_first_fwd_affine_tiles (tiles read in place, mirrored past the image edge) == ub_conv_first_fwd_affine on tiles cut
     from the explicitly reflect-padded image (np.pad(mode='reflect'), UNet/inference.py:46): bit-exact"""
@@ -1159,4 +1206,13 @@ CASES = {
     "bn_sums_wgrad_64_64_2x2": lambda: case_bn_sums_wgrad(64, 0, 64, N=3, H=2, W=2, seed=64),
     "bn_sums_head_k2": case_bn_sums_head,
     "bn_sums_head_k8": lambda: case_bn_sums_head(8, seed=65),
+    # number_classes beyond the register-resident kernels (class-per-lane kernels, csrc/head_generic.cu) and the argmax epilogue
+    "head_k9": lambda: case_head(9, seed=71),
+    "head_k20_weighted": lambda: case_head(20, weighted=True, seed=72),
+    "head_k33": lambda: case_head(33, N=1, H=17, W=19, seed=73),
+    "head_k255": lambda: case_head(255, N=1, H=16, W=16, seed=74),
+    "head_argmax_k2": case_head_argmax,
+    "head_argmax_k8_bf16": lambda: case_head_argmax(8, dtype="bf16", seed=75),
+    "head_argmax_k20": lambda: case_head_argmax(20, seed=76),
+    "head_argmax_k255_bf16": lambda: case_head_argmax(255, ntiles=2, h=16, w=24, dtype="bf16", seed=77),
 }

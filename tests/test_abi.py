@@ -52,8 +52,9 @@ def test_argument_errors_are_reported_not_thrown(C):
     rc = C.lib.ub_conv3x3_fwd(ctypes.c_void_p(256), 48, None, 0, ctypes.c_void_p(256), None, ctypes.c_void_p(256), None, 1, 16, 16, 64, 1, None)
     assert rc == C.MACROS["UB_ERR_UNSUPPORTED_SHAPE"]
     assert "multiples of 64" in C.last_error()
-    rc = C.lib.ub_head_fwd(ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), None, 10, 9, 0, None)
-    assert rc == C.MACROS["UB_ERR_UNSUPPORTED_SHAPE"]
+    rc = C.lib.ub_head_fwd(ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), ctypes.c_void_p(256), None, 10, 256, 0, None)
+    assert rc == C.MACROS["UB_ERR_UNSUPPORTED_SHAPE"]          # number_classes > UB_MAX_CLASSES_ANY (labels and masks are uint8)
+    assert "255" in C.last_error()
     with pytest.raises(C.UBError):
         C.call("ub_adam", None, None, None, None, None, 0, 0.0, 0.0, 0.0, 0.0, 1.0, None)
 
