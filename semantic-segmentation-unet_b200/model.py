@@ -49,7 +49,8 @@ class UNet:
         if not torch.cuda.is_available():
             raise RuntimeError("unetb200 requires a CUDA device (sm_100a); there is no CPU fallback")
         if label_smoothing != 0:
-            raise NotImplementedError("label_smoothing != 0 is not used by the reference (UNet/model.py:65) and not built")
+            raise NotImplementedError("label_smoothing != 0 is not built: the reference's train.py and inference.py never pass it "
+                                      "(UNet/model.py:65 default 0, UNet/train.py:94)")
         if number_classes < 1 or number_classes > _C.MACROS["UB_MAX_CLASSES_ANY"]:
             # labels and masks are uint8 on this path, as in the reference's databases (UNet/build_lmdb.py:151 forces uint8 masks)
             raise ValueError(f"number_classes must be in [1, {_C.MACROS['UB_MAX_CLASSES_ANY']}]")
@@ -79,9 +80,11 @@ class UNet:
         self._graphs = {}
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
-        # bf16 folded path: dbeta / dgamma of a BatchNorm whose only consumer is a folded convolution come from that convolution's weight
-        # gradient and border sums (ub_bn_bwd_sums_wgrad) instead of a reduction pass over the gradient tensor
-        self.bn_algebra = os.environ.get("UB_BN_ALGEBRA", "1") == "1"
+        # bf16 folded path, optional (UB_BN_ALGEBRA=1): dbeta / dgamma of a BatchNorm whose only consumer is a folded convolution come from that
+        # convolution's weight gradient and border sums (ub_bn_bwd_sums_wgrad) instead of a reduction pass over the gradient tensor.  Parity
+        # green and 4.3 GB less HBM traffic per step, but the BatchNorm backward of layer L then has to wait for the weight gradient of layer
+        # L + 1, which takes the weight gradients off the side stream: measured 24.22 ms against 22.89 ms per step (profiles/r02_ab_runs.md).
+        self.bn_algebra = os.environ.get("UB_BN_ALGEBRA", "0") == "1"
         self._sums_ready = set()
         self.fuse_finalize = os.environ.get("UB_FUSE_FINALIZE", "1") == "1"   # bf16 path: the forward's last CTA finalises the BatchNorm statistics
         self.fuse_bn_reduce_ew = os.environ.get("UB_FUSE_EW", "0") == "1"   # ... and in the pool-backward / head-backward passes

@@ -678,6 +678,22 @@ def _with_fold(fn, value="0"):
     return run
 
 
+def _with_env(fn, **env):
+    """run a graph case with environment switches of unetb200.model.UNet set (e.g. UB_BN_ALGEBRA="1")"""
+    def run():
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            return fn()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return run
+
+
 def case_banded_inference():
     """segment_sharded (tile runs, split z-score) on one rank == zscore_device + segment_device, incl. reflect padding"""
     import unetb200.inference as I
@@ -754,5 +770,9 @@ CASES = {
     "nofold_live_bf16_c3k8": _with_fold(lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True)),
     "nofold_wellcond_bf16_n2_256": _with_fold(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256)),
     "nofold_golden_c1_k2_bf16": _with_fold(lambda: case_golden("graph_c1_k2", "bf16")),
+    # optional schedule: BatchNorm-backward sums from the consumer's weight gradient (UB_BN_ALGEBRA=1)
+    "algebra_live_bf16_c1k2": _with_env(lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True), UB_BN_ALGEBRA="1"),
+    "algebra_wellcond_bf16_n2_256": _with_env(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256), UB_BN_ALGEBRA="1"),
+    "algebra_curve_bf16": _with_env(lambda: case_curve("bf16", steps=100), UB_BN_ALGEBRA="1"),
     "nofold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=100)),
 }

@@ -443,7 +443,8 @@ def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
              e_dW=rel_err(gw[:K * 64].cpu().numpy().reshape(K, 64), dW_ref), e_db=rel_err(gw[K * 64:].cpu().numpy(), db_ref))
     r.update(fused)
     r = {k: float(v) for k, v in r.items()}
-    r["ok"] = bool(all(v < 2e-4 for k, v in r.items() if k.startswith("e_")) and r["e_fused_dx"] == 0.0 and r["e_fused_gw"] == 0.0)
+    # dx is bit-identical; the weight-gradient partials are summed in a different order (4 vs 2 pixels per thread per iteration)
+    r["ok"] = bool(all(v < 2e-4 for k, v in r.items() if k.startswith("e_")) and r["e_fused_dx"] == 0.0 and r["e_fused_gw"] < 1e-6)
     return r
 
 

@@ -103,7 +103,8 @@ def test_optional_schedules():
     c = _count(_step(m))
     assert c["ub_maxpool2x2_bwd_add_bnred"] == 4 and c["ub_head_bwd_apply_bnred"] == 1 and "ub_maxpool2x2_bwd_add" not in c
     m = DryUNet(2, 1, 1, precision="bf16", seed=0)
-    assert m.fold_bn                      # the default schedule folds BatchNorm into the consumer convolutions
+    assert m.fold_bn and not m.bn_algebra # the default schedule folds BatchNorm into the consumer convolutions
+    m.bn_algebra = True                   # UB_BN_ALGEBRA=1 (optional: BatchNorm-backward sums from the consumer's weight gradient)
     names = _step(m)
     c = _count(names)
     # 17 producers lose their BatchNorm-apply pass (13 conv/deconv layers, enc1b-3b behind a y-less pool, dec1b behind the folded
@@ -120,8 +121,7 @@ def test_optional_schedules():
     for i, n in enumerate(before):           # the sums are taken from dW_a, i.e. before the fold fix-up rewrites the weight gradient
         if n == "ub_bn_bwd_sums_wgrad" and m.args[i][5] == 9:
             assert "ub_wgrad_fold_fix" in before[i + 1:i + 3] and before[i - 1] in ("ub_border_sums", "ub_bn_bwd_sums_wgrad")
-    m2 = DryUNet(2, 1, 1, precision="bf16", seed=0)
-    m2.bn_algebra = False                    # UB_BN_ALGEBRA=0
+    m2 = DryUNet(2, 1, 1, precision="bf16", seed=0)          # the default
     c2 = _count(_step(m2))
     assert "ub_bn_bwd_sums_wgrad" not in c2 and c2.get("ub_bn_bwd_reduce", 0) + c2.get("ub_conv3x3_dgrad_bnred", 0) == 22
     folded = {l for (n, l), a in zip(m.calls, m.args) if n == "ub_conv3x3_fwd_bn" and a[6] == 1}
