@@ -103,11 +103,12 @@ int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, flo
                 cudaStream_t stream);
 /* BatchNorm -> Softmax -> CategoricalCrossentropy + CategoricalAccuracy -- UNet/model.py:136-142, :211-215, :225-226.
  * labels: uint8 class index per pixel (nullable: inference); class_w nullable (all ones = reference behaviour);
- * dlogits = (softmax - onehot) * class_w[label] * inv_denom;
+ * label_smoothing eps (UNet/model.py:65, :77; the reference passes 0): target = onehot * (1 - eps) + eps / K;
+ * dlogits = (softmax - target) * class_w[label] * inv_denom;
  * partial[UB_STATS_ROWS][2] = {inv_denom * sum CE, acc_scale * #correct} (sum the rows with ub_reduce_rows). */
 int ub_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta,
-                 const unsigned char* labels, const float* class_w, float inv_denom, float acc_scale, float* softmax_out,
-                 float* dlogits, float* partial, long long P, int K, cudaStream_t stream);
+                 const unsigned char* labels, const float* class_w, float inv_denom, float acc_scale, float label_smoothing,
+                 float* softmax_out, float* dlogits, float* partial, long long P, int K, cudaStream_t stream);
 /* one-hot int32 [P][K] (the reference's label tensor, UNet/imagereader.py:302-312) -> uint8 index */
 int ub_onehot_to_index(const int* onehot, unsigned char* idx, long long P, int K, cudaStream_t stream);
 int ub_head_bwd_reduce(const float* dy, const float* a, const float* mean, const float* rstd, float* partial, long long P, int K,

@@ -265,17 +265,22 @@ def forward(params, x, training, dropout_masks=None, new_stats=None, taps=None, 
     return torch.softmax(logits, dim=-1), logits
 
 
-def loss_and_accuracy(logits_nhwc, labels_onehot, global_batch_size):
-    """UNet/model.py:211-215 + App. A.7/A.8.  labels_onehot [N,H,W,K] (any numeric dtype)."""
+def loss_and_accuracy(logits_nhwc, labels_onehot, global_batch_size, label_smoothing=0.0):
+    """UNet/model.py:211-215 + App. A.7/A.8.  labels_onehot [N,H,W,K] (any numeric dtype).
+    label_smoothing (UNet/model.py:65, :77; Keras CategoricalCrossentropy): y_true * (1 - eps) + eps / K."""
     t = labels_onehot.to(logits_nhwc.dtype)
-    ce = -(t * torch.log_softmax(logits_nhwc, dim=-1)).sum(-1)           # [N,H,W]
+    if label_smoothing:
+        t_s = t * (1.0 - label_smoothing) + label_smoothing / t.shape[-1]
+    else:
+        t_s = t
+    ce = -(t_s * torch.log_softmax(logits_nhwc, dim=-1)).sum(-1)         # [N,H,W]
     loss = (ce.sum(0) / global_batch_size).mean()
     acc = (logits_nhwc.argmax(-1) == t.argmax(-1)).to(torch.float64).mean()
     return loss, acc
 
 
 def train_step_grads(params, x, labels_onehot, global_batch_size, dropout_masks=None, taps=None, relu_masks=None,
-                     pool_idx=None, storage=None):
+                     pool_idx=None, storage=None, label_smoothing=0.0):
     """fwd(training=True) + loss + grads of every trainable tensor (UNet/model.py:204-221).
 
     Returns dict(loss, acc, softmax, logits, grads{name: tensor}, new_stats{...}).
@@ -286,7 +291,7 @@ def train_step_grads(params, x, labels_onehot, global_batch_size, dropout_masks=
         leaves[k] = v.detach().clone().requires_grad_(k in names)
     new_stats = {}
     sm, logits = forward(leaves, x, True, dropout_masks, new_stats, taps, relu_masks, pool_idx, storage)
-    loss, acc = loss_and_accuracy(logits, labels_onehot, global_batch_size)
+    loss, acc = loss_and_accuracy(logits, labels_onehot, global_batch_size, label_smoothing)
     tap_keys = list(taps.keys()) if taps is not None else []
     grads = torch.autograd.grad(loss, [leaves[k] for k in names] + [taps[k] for k in tap_keys])
     out = dict(loss=loss.detach(), acc=acc, softmax=sm.detach(), logits=logits.detach(),

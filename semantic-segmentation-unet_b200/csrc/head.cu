@@ -509,8 +509,8 @@ __global__ void __launch_bounds__(TPB) head_fwd_kernel(const T* __restrict__ x, 
 __global__ void __launch_bounds__(TPB) head_loss_kernel(const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         const uint8_t* __restrict__ labels, const float* __restrict__ class_w, float inv_denom,
-                                                        float acc_scale, float* __restrict__ softmax_out, float* __restrict__ dlogits, float* __restrict__ partial,
-                                                        long long P, int K) {
+                                                        float acc_scale, float smooth, float* __restrict__ softmax_out, float* __restrict__ dlogits,
+                                                        float* __restrict__ partial, long long P, int K) {
   __shared__ float sh[TPB / 32];
   float sc[KMAX], sf[KMAX];
 #pragma unroll
@@ -533,16 +533,20 @@ __global__ void __launch_bounds__(TPB) head_loss_kernel(const float* __restrict_
         }
       }
     }
-    float se = 0.f;
+    // label smoothing (Keras CategoricalCrossentropy, UNet/model.py:77): target t'_k = (1 - eps) [k == label] + eps / K, so the loss also
+    // needs sum_k log p_k = sum_k (y_k - max) - K log(sum exp)
+    float se = 0.f, sy = 0.f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) {
+        sy += y[k] - mx;
         y[k] = __expf(y[k] - mx);
         se += y[k];
       }
     const float inv = 1.f / se;
     const int lab = labels ? (int)labels[px] : 0;
     const float cw = class_w ? class_w[lab] : 1.f;
+    const float t_on = 1.f - smooth + smooth / (float)K, t_off = smooth / (float)K;
     float pl = 1.f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
@@ -550,10 +554,12 @@ __global__ void __launch_bounds__(TPB) head_loss_kernel(const float* __restrict_
         const float p = y[k] * inv;
         if (k == lab) pl = p;
         if (softmax_out) softmax_out[px * K + k] = p;
-        if (dlogits) dlogits[px * K + k] = (p - (k == lab ? 1.f : 0.f)) * cw * inv_denom;
+        if (dlogits) dlogits[px * K + k] = (p - (k == lab ? t_on : t_off)) * cw * inv_denom;
       }
     if (labels) {
-      loss += -__logf(fmaxf(pl, 1e-37f)) * cw;
+      float l = -__logf(fmaxf(pl, 1e-37f)) * (1.f - smooth);
+      if (smooth != 0.f) l -= t_off * (sy - (float)K * __logf(se));
+      loss += l * cw;
       correct += (am == lab) ? 1.f : 0.f;
     }
   }
@@ -842,8 +848,8 @@ int ubg_head_fwd(const void* x, const float* w, const float* b, float* a_out, fl
 int ubg_head_argmax(const void* x, const float* w, const float* b, const float* scale, const float* shift, int K, int ntiles, int h, int wd,
                     const int* geo, unsigned char* mask, long long mask_ld, float* softmax_out, int dtype, cudaStream_t stream);
 int ubg_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const unsigned char* labels,
-                  const float* class_w, float inv_denom, float acc_scale, float* softmax_out, float* dlogits, float* partial, long long P, int K,
-                  cudaStream_t stream);
+                  const float* class_w, float inv_denom, float acc_scale, float smooth, float* softmax_out, float* dlogits, float* partial, long long P,
+                  int K, cudaStream_t stream);
 int ubg_head_bwd_reduce(const float* dy, const float* a, const float* mean, const float* rstd, float* partial, long long P, int K,
                         cudaStream_t stream);
 int ubg_head_bwd_apply(const float* dy, const float* a, const void* x, const float* w, const float* mean, const float* rstd, const float* gamma,
@@ -970,14 +976,17 @@ int ub_head_fwd(const void* x, const float* w, const float* b, float* a_out, flo
 }
 
 int ub_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const unsigned char* labels,
-                 const float* class_w, float inv_denom, float acc_scale, float* softmax_out, float* dlogits, float* partial, long long P,
-                 int K, cudaStream_t stream) {
+                 const float* class_w, float inv_denom, float acc_scale, float label_smoothing, float* softmax_out, float* dlogits, float* partial,
+                 long long P, int K, cudaStream_t stream) {
   UB_CHECK_ARG(a && mean && rstd && gamma && beta && P > 0, "head_loss: bad args");
+  UB_CHECK_ARG(label_smoothing >= 0.f && label_smoothing <= 1.f, "head_loss: label_smoothing must be in [0, 1]");
   UB_CHECK_SHAPE(K >= 1 && K <= UB_MAX_CLASSES_ANY, "head_loss: number_classes=%d must be in [1, %d]", K, UB_MAX_CLASSES_ANY);
-  if (K > KMAX) return ubg_head_loss(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, softmax_out, dlogits, partial, P, K, stream);
+  if (K > KMAX)
+    return ubg_head_loss(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, label_smoothing, softmax_out, dlogits, partial, P, K, stream);
   const int grid = grid_for(P, TPB * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2, stream));
-  head_loss_kernel<<<grid, TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, softmax_out, dlogits, partial, P, K);
+  head_loss_kernel<<<grid, TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, label_smoothing, softmax_out, dlogits,
+                                             partial, P, K);
   UB_LAUNCH_CHECK();
   return UB_OK;
 }

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(TPB) head_fwd_g_kernel(const T* __restrict__ x
 __global__ void __launch_bounds__(TPB) head_loss_g_kernel(const float* __restrict__ a, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           const uint8_t* __restrict__ labels, const float* __restrict__ class_w, float inv_denom,
-                                                          float acc_scale, float* __restrict__ softmax_out, float* __restrict__ dlogits,
+                                                          float acc_scale, float smooth, float* __restrict__ softmax_out, float* __restrict__ dlogits,
                                                           float* __restrict__ partial, long long P, int K) {
   __shared__ float shl[WARPS], shc[WARPS];
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -225,11 +225,12 @@ __global__ void __launch_bounds__(TPB) head_loss_g_kernel(const float* __restric
         am = oa;
       }
     }
-    float se = 0.f;
+    float se = 0.f, sy = 0.f;
 #pragma unroll
     for (int j = 0; j < JMAX; ++j) {
       const int k = lane + 32 * j;
       if (j < J && k < K) {
+        sy += y[j] - mx;
         y[j] = __expf(y[j] - mx);
         se += y[j];
       }
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(TPB) head_loss_g_kernel(const float* __restric
     const float inv = 1.f / se;
     const int lab = labels ? (int)labels[px] : 0;
     const float cw = class_w ? class_w[lab] : 1.f;
+    const float t_on = 1.f - smooth + smooth / (float)K, t_off = smooth / (float)K;      // label smoothing, see head.cu
     float pl = 0.f;
 #pragma unroll
     for (int j = 0; j < JMAX; ++j) {
@@ -246,13 +248,16 @@ __global__ void __launch_bounds__(TPB) head_loss_g_kernel(const float* __restric
         const float p = y[j] * inv;
         if (k == lab) pl = p;
         if (softmax_out) softmax_out[px * K + k] = p;
-        if (dlogits) dlogits[px * K + k] = (p - (k == lab ? 1.f : 0.f)) * cw * inv_denom;
+        if (dlogits) dlogits[px * K + k] = (p - (k == lab ? t_on : t_off)) * cw * inv_denom;
       }
     }
     if (labels) {
       pl = warp_sum(pl);                                     // exactly one lane holds the label's probability
+      if (smooth != 0.f) sy = warp_sum(sy);
       if (lane == 0) {
-        loss += -__logf(fmaxf(pl, 1e-37f)) * cw;
+        float l = -__logf(fmaxf(pl, 1e-37f)) * (1.f - smooth);
+        if (smooth != 0.f) l -= t_off * (sy - (float)K * __logf(se));
+        loss += l * cw;
         correct += (am == lab) ? 1.f : 0.f;
       }
     }
@@ -493,10 +498,10 @@ int ubg_head_argmax(const void* x, const float* w, const float* b, const float* 
 }
 
 int ubg_head_loss(const float* a, const float* mean, const float* rstd, const float* gamma, const float* beta, const unsigned char* labels,
-                  const float* class_w, float inv_denom, float acc_scale, float* softmax_out, float* dlogits, float* partial, long long P, int K,
-                  cudaStream_t stream) {
+                  const float* class_w, float inv_denom, float acc_scale, float smooth, float* softmax_out, float* dlogits, float* partial, long long P,
+                  int K, cudaStream_t stream) {
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2, stream));
-  head_loss_g_kernel<<<grid_rows(P, WARPS * 16), TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, softmax_out,
+  head_loss_g_kernel<<<grid_rows(P, WARPS * 16), TPB, 0, stream>>>(a, mean, rstd, gamma, beta, labels, class_w, inv_denom, acc_scale, smooth, softmax_out,
                                                                   dlogits, partial, P, K);
   UB_LAUNCH_CHECK();
   return UB_OK;

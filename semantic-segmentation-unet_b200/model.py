@@ -48,9 +48,9 @@ class UNet:
                  *, precision="bf16", device=None, seed=None, class_weights=None, dist=None):
         if not torch.cuda.is_available():
             raise RuntimeError("unetb200 requires a CUDA device (sm_100a); there is no CPU fallback")
-        if label_smoothing != 0:
-            raise NotImplementedError("label_smoothing != 0 is not built: the reference's train.py and inference.py never pass it "
-                                      "(UNet/model.py:65 default 0, UNet/train.py:94)")
+        if not 0.0 <= float(label_smoothing) <= 1.0:
+            raise ValueError("label_smoothing must be in [0, 1]")
+        self.label_smoothing = float(label_smoothing)          # UNet/model.py:65, :77 (the reference's train.py leaves it at 0)
         if number_classes < 1 or number_classes > _C.MACROS["UB_MAX_CLASSES_ANY"]:
             # labels and masks are uint8 on this path, as in the reference's databases (UNet/build_lmdb.py:151 forces uint8 masks)
             raise ValueError(f"number_classes must be in [1, {_C.MACROS['UB_MAX_CLASSES_ANY']}]")
@@ -365,7 +365,7 @@ class UNet:
         gradient w.r.t. the softmax INPUT (the head's BatchNorm output) is dlogits_fn(softmax [N,H,W,K] numpy) -> numpy.
         Runs on a private fp32 (check-mode) copy of this model: the reference differentiates in fp32 and thresholds the
         result at 1e-8 (UNet/model.py:165-202)."""
-        m = UNet(self.number_classes, 1, self.number_channels, self.learning_rate, precision="fp32", device=self.device, seed=0)
+        m = UNet(self.number_classes, 1, self.number_channels, self.learning_rate, self.label_smoothing, precision="fp32", device=self.device, seed=0)
         m.P.copy_(self.P)
         m.MM.copy_(self.MM)
         m.MV.copy_(self.MV)
@@ -774,7 +774,7 @@ class UNet:
         gamma, beta = self._affine(L)
         sm = self._ensure("softmax", P * K, torch.float32) if want_softmax else None
         inv_denom = 1.0 / (self.global_batch_size * H * W)            # UNet/model.py:213-215
-        self._call("ub_head_loss", self._b("a:head"), mean, rstd, gamma, beta, labels_u8, self.class_weights, inv_denom, 1.0 / P,
+        self._call("ub_head_loss", self._b("a:head"), mean, rstd, gamma, beta, labels_u8, self.class_weights, inv_denom, 1.0 / P, self.label_smoothing,
                    sm, self._b("dlogits") if want_grad else None, self.partial if labels_u8 is not None else None, P, K)
         if labels_u8 is not None:
             self._call("ub_reduce_rows", self.partial, _C.UB_STATS_ROWS, 2, 2, self.metrics, 1.0)

@@ -107,7 +107,7 @@ def cuda_logits(m, N, H, W):
     return ((a - mean) * rstd * gamma + beta).cpu().numpy()
 
 
-def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=False, absolute=None, floor=False):
+def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=False, absolute=None, floor=False, smooth=0.0):
     """one training step: softmax / loss / accuracy / BN moving statistics vs the oracle; all 92 gradients vs the
     oracle conditioned on the CUDA path's activation pattern.  learn: image and labels are correlated (the oracle's
     synthetic_batch, the shape of bench.py's workload) instead of independent noise"""
@@ -119,7 +119,7 @@ def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=Fals
     if learn:
         x, lab = O.synthetic_batch(N, C, H, W, K, seed=seed)
     oh = np.eye(K, dtype=np.int32)[lab]
-    m = UNet(K, gb, C, learning_rate=1e-3, precision=precision, seed=0)
+    m = UNet(K, gb, C, learning_rate=1e-3, label_smoothing=smooth, precision=precision, seed=0)
     m.load_oracle_params({k: v.numpy() for k, v in p.items()})
     m.train_step(torch.tensor(x), torch.tensor(oh), dropout_masks=dm, apply_update=False, keep_softmax=True)   # one-hot label contract
     torch.cuda.synchronize()
@@ -131,8 +131,8 @@ def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=Fals
 
     xt, oht = torch.tensor(x, dtype=torch.float64), torch.tensor(oh)
     dmt = {k: torch.tensor(v) for k, v in dm.items()}
-    ref = O.train_step_grads(p, xt, oht, gb, dmt)
-    refc = O.train_step_grads(p, xt, oht, gb, dmt, relu_masks=relu, pool_idx=pool)
+    ref = O.train_step_grads(p, xt, oht, gb, dmt, label_smoothing=smooth)
+    refc = O.train_step_grads(p, xt, oht, gb, dmt, relu_masks=relu, pool_idx=pool, label_smoothing=smooth)
 
     r = {}
     r["e_softmax"] = rel(sm, ref["softmax"].numpy())
@@ -192,9 +192,9 @@ def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=Fals
             return r
     # ---- noise-floor criterion against the bf16-storage emulation of the oracle (module docstring)
     taps = {}
-    emu = O.train_step_grads(p, xt, oht, gb, dmt, taps=taps, storage="bf16_fold" if m.fold_bn else "bf16")      # same storage points as the path under test
+    emu = O.train_step_grads(p, xt, oht, gb, dmt, taps=taps, storage="bf16_fold" if m.fold_bn else "bf16", label_smoothing=smooth)      # same storage points as the path under test
     relu_e, pool_e = oracle_pattern(taps, dmt)
-    refe = O.train_step_grads(p, xt, oht, gb, dmt, relu_masks=relu_e, pool_idx=pool_e)
+    refe = O.train_step_grads(p, xt, oht, gb, dmt, relu_masks=relu_e, pool_idx=pool_e, label_smoothing=smooth)
     sme = emu["softmax"].numpy()
     r["sm_rms_floor"] = rms(sme, sm64)
     r["sm_max_floor"] = rel(sme, sm64)
@@ -678,6 +678,32 @@ def _with_fold(fn, value="0"):
     return run
 
 
+def case_graph_two_shapes():
+    """CUDA-graph replay across a buffer reallocation (UNet._ensure): steps at shape A capture a graph, steps at a LARGER shape B grow the
+    persistent buffers (the A graph holds the old pointers and must be dropped), then shape A again -- the parameters must equal, bit
+    for bit, those of an identical model that launches every step eagerly"""
+    from unetb200.model import UNet
+    rng = np.random.default_rng(19)
+    shapes = [(2, 32, 48)] * 3 + [(2, 64, 64)] * 3 + [(2, 32, 48)] * 3 + [(4, 64, 64)] * 2 + [(2, 32, 48)] * 2
+    data = [(rng.normal(size=(n, 1, h, w)).astype(np.float32), rng.integers(0, 2, size=(n, h, w)).astype(np.uint8)) for n, h, w in shapes]
+    out = {}
+    for mode in ("graph", "eager"):
+        m = UNet(2, 2, 1, 1e-3, seed=7)
+        m.use_graph = mode == "graph"
+        m.dropout_seed = 11
+        losses = []
+        for x, lab in data:
+            losses.append(float(m.train_step(torch.tensor(x), torch.tensor(lab)).item()))
+        torch.cuda.synchronize()
+        out[mode] = (m.P.clone(), m.MV.clone(), losses, len(m._graphs))
+    same_p = bool(torch.equal(out["graph"][0], out["eager"][0]))
+    same_mv = bool(torch.equal(out["graph"][1], out["eager"][1]))
+    r = dict(params_bit_identical=same_p, moving_var_bit_identical=same_mv, losses_equal=out["graph"][2] == out["eager"][2],
+             finite=bool(np.isfinite(out["graph"][2]).all()), graphs_alive=out["graph"][3])
+    r["ok"] = bool(same_p and same_mv and r["losses_equal"] and r["finite"])
+    return r
+
+
 def _with_env(fn, **env):
     """run a graph case with environment switches of unetb200.model.UNet set (e.g. UB_BN_ALGEBRA="1")"""
     def run():
@@ -748,6 +774,8 @@ CASES = {
     "live_bf16_c1k2": lambda: case_live("bf16", N=2, C=1, H=96, W=64, K=2, seed=23, floor=True),
     "live_bf16_c3k8": lambda: case_live("bf16", N=1, C=3, H=112, W=144, K=8, seed=24, gb=8, floor=True),
     # number_classes > 8: the class-per-lane head kernels inside the whole graph (fp32 check mode <= 1e-4, bf16 at the storage floor)
+    # label_smoothing (UNet/model.py:65, :77)
+    "live_fp32_c1k2_smooth": lambda: case_live("fp32", N=2, C=1, H=64, W=48, K=2, seed=28, smooth=0.1),
     "live_fp32_c3k20": lambda: case_live("fp32", N=1, C=3, H=64, W=80, K=20, seed=26, gb=2),
     "live_bf16_c1k40": lambda: case_live("bf16", N=1, C=1, H=96, W=96, K=40, seed=27, gb=2, floor=True),
     "golden_c1_k2_fp32": lambda: case_golden("graph_c1_k2", "fp32"),
@@ -761,6 +789,8 @@ CASES = {
     "wellcond_bf16_n2_256": lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256),
     # ... and at trained weights: north_star's 1e-2 / 99.9 %
     "trained_bf16": case_trained,
+    # graph replay across buffer reallocation (two alternating input shapes) == eager launches, bit for bit
+    "graph_two_shapes": case_graph_two_shapes,
     # the reference's data/ fixture -> build_lmdb -> 60 training steps, loss curve vs the oracle's
     "config1_refdata": case_config1_refdata,
     # sharded inference (rows uploaded per rank, split z-score, in-place tile reader) == whole-image path on one rank

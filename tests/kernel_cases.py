@@ -360,7 +360,7 @@ def case_conv_first(Cin=1, N=2, H=16, W=24, seed=8):
     return dict(err=e, err_sum=es, err_dw=ew, ok=bool(e < 1e-5 and es < 1e-4 and ew < 1e-4))
 
 
-def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
+def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False, smooth=0.0):
     C = _C()
     rng = np.random.default_rng(seed)
     P = N * H * W
@@ -380,7 +380,7 @@ def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
     y = (a - mu) * rs * gamma + beta
     e_ = np.exp(y - y.max(-1, keepdims=True))
     p = e_ / e_.sum(-1, keepdims=True)
-    oh = np.eye(K)[lab]
+    oh = np.eye(K)[lab] * (1.0 - smooth) + smooth / K          # Keras label_smoothing (UNet/model.py:77)
     cwl = cw[lab].astype(np.float64) if weighted else np.ones(P)
     loss_ref = float((-(np.log(p) * oh).sum(-1) * cwl).sum() * inv_denom)
     acc_ref = float((p.argmax(-1) == lab).mean())
@@ -400,7 +400,7 @@ def case_head(K=2, N=2, H=16, W=24, seed=9, weighted=False):
     dl = torch.empty((P, K), dtype=torch.float32, device="cuda")
     gd, btd = dev(gamma, torch.float32), dev(beta, torch.float32)
     cwd = dev(cw, torch.float32) if weighted else None
-    C.call("ub_head_loss", a_d, mean, rstd, gd, btd, dev(lab, torch.uint8), cwd, inv_denom, 1.0 / P, sm, dl, partial, P, K, stream())
+    C.call("ub_head_loss", a_d, mean, rstd, gd, btd, dev(lab, torch.uint8), cwd, inv_denom, 1.0 / P, smooth, sm, dl, partial, P, K, stream())
     la = torch.empty(2, device="cuda")
     C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2, 2, la, 1.0, stream())
     red = torch.empty(2 * K, device="cuda")
@@ -790,7 +790,7 @@ def case_published_known_answers():
     sm = torch.empty((P, K), device="cuda")
     dl = torch.empty((P, K), device="cuda")
     partial = torch.zeros(C.UB_STATS_ROWS * 2, device="cuda")
-    C.call("ub_head_loss", a, zeros, ones, ones, zeros, lab, None, 1.0, 1.0 / P, sm, dl, partial, P, K, stream())
+    C.call("ub_head_loss", a, zeros, ones, ones, zeros, lab, None, 1.0, 1.0 / P, 0.0, sm, dl, partial, P, K, stream())
     la = torch.empty(2, device="cuda")
     C.call("ub_reduce_rows", partial, C.UB_STATS_ROWS, 2, 2, la, 1.0, stream())
     torch.cuda.synchronize()
@@ -1216,4 +1216,7 @@ CASES = {
     "head_argmax_k8_bf16": lambda: case_head_argmax(8, dtype="bf16", seed=75),
     "head_argmax_k20": lambda: case_head_argmax(20, seed=76),
     "head_argmax_k255_bf16": lambda: case_head_argmax(255, ntiles=2, h=16, w=24, dtype="bf16", seed=77),
+    "head_k2_smooth": lambda: case_head(2, smooth=0.1, seed=78),
+    "head_k8_weighted_smooth": lambda: case_head(8, weighted=True, smooth=0.2, seed=79),
+    "head_k20_smooth": lambda: case_head(20, smooth=0.1, seed=80),
 }
