@@ -283,6 +283,76 @@ __device__ __forceinline__ void tc_mma_steps_bf16_e(uint32_t d_tmem, uint64_t ad
         : "memory");
   }
 }
+// ---- CTA pair (cta_group::2): two SMs of one TPC issue ONE tcgen05.mma of M = 256; each CTA holds its own 128 rows of A and HALF of
+// the B tile, so the shared-memory port of an SM serves 6 KB instead of 8 KB per 128x128x16 MMA step.  Only the leader (cluster rank 0)
+// issues MMAs; both CTAs issue TMA loads that signal the LEADER's mbarrier (peer bit 24 of the shared::cluster address cleared), and
+// tcgen05.commit multicasts its arrive to the same barrier in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t UB_PEER_MASK = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the even (leader) CTA of the pair
+__device__ __forceinline__ void tma_load_4d_2sm_e(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & UB_PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_e(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & UB_PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_e(uint64_t* bar) {          // arrive on `bar` in BOTH CTAs once the MMAs issued so far are done
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t.reg .b16 m;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma4_bf16_2sm_e(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred p, q, t;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, 0, 0;\n\t"
+      "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\t"
+      "add.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\t"
+      "add.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], a3, b3, %3, t;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at the same offset in cluster CTA `cta` (the leader's accumulator-empty barrier, from the peer's epilogue warps)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+
 // value known to be identical in all lanes -> tell the compiler (lets it keep descriptors / addresses in uniform registers)
 __device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 

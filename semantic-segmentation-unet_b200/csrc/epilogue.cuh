@@ -116,6 +116,7 @@ struct Epilogue {
   int red_cur = 0;           // buffer holding the current part's `a` tile
   bool red_primed = false;
   bool red_mine = false;     // this thread's column pair belongs to the BatchNorm'd tensor
+  int pair_rank = -1;        // >= 0: this CTA is rank `pair_rank` of a cta_group::2 pair (igemm_conv3_2cta.cu)
 
   // epi_thread: 0 .. EPI_THREADS-1; hw_warp: warp index within the CTA (a warp may only touch TMEM lanes 32 * (hw_warp % 4) .. +31)
   __device__ __forceinline__ Epilogue(uint8_t* smem_region, const EpiParams& e, uint32_t tmem, uint64_t* tf, uint64_t* te, int epi_thread,
@@ -249,7 +250,10 @@ struct Epilogue {
     // accumulator stage drained -> the MMA warp may reuse it
     tc_fence_before();
     __syncwarp();
-    if (last && lane == 0) mbar_arrive(&tempty[as]);
+    if (last && lane == 0) {
+      if (pair_rank < 0) mbar_arrive(&tempty[as]);
+      else mbar_arrive_cluster(&tempty[as], 0);         // CTA pair: the MMA issuer (leader) waits for the epilogues of BOTH CTAs
+    }
     fence_proxy_async_smem();
     named_bar_sync(1, EPI_THREADS);
     if (et == 0) {

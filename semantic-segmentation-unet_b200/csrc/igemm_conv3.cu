@@ -255,6 +255,282 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_kernel(const __grid
   }
 }
 
+// conv3x3 forward / dgrad on CTA PAIRS (tcgen05 cta_group::2): the halo-patch implicit GEMM of igemm_conv3.cu with M = 256 per MMA.
+// Two CTAs of a cluster (two SMs of one TPC) take two horizontally independent pixel super-tiles and the SAME 128 output columns;
+// each loads its own activation patch and HALF of every weight tile, the leader issues tcgen05.mma.cta_group::2 for both, and each CTA
+// drains its own 128 TMEM lanes through the unchanged epilogue.  Per SM and per 64-channel block the shared-memory port then serves
+// 72 x 6 KB of operand reads + 115 KB of TMA writes instead of 72 x 8 KB + 188 KB: ~119 B/clk against the 128 B/clk port, where the
+// single-CTA kernel asks for ~166 B/clk and is port-bound.  Selected for the 128-column tiles by UB_CONV3_2CTA=1.
+//
+// Protocol (every barrier exists at the same shared-memory offset in both CTAs):
+//   afull / bfull   used in the LEADER only: its producer arms them with the bytes of BOTH CTAs; the peer's TMA loads complete_tx on
+//                   the leader's barrier (cp.async.bulk.tensor ... cta_group::2 with the peer bit of the barrier address cleared)
+//   aempty / bempty one arrive in EACH CTA from the leader's tcgen05.commit ... multicast::cluster (mask 0b11): each producer refills
+//                   its own shared memory
+//   tfull           multicast commit as well: each CTA's epilogue waits on its own copy
+//   tempty          LEADER only, 2 x EPI_WARPS arrivals: the peer's epilogue warps arrive remotely (mapa + mbarrier.arrive ... cluster)
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED, int CASEB = 0>
+struct C3PSmem {
+  using E = EpiSmem<BLOCK_N, OUT_BUFS, RED, CASEB>;
+  using P = Patch<MT>;
+  static constexpr int B_BYTES = (BLOCK_N / 2) * 128;      // this CTA's half of a weight tile
+  static constexpr int OFF_B = A_STAGES * P::STRIDE;
+  static constexpr int OFF_EPI = OFF_B + B_SLOTS * B_BYTES;
+  static constexpr int OFF_BAR = OFF_EPI + E::TOTAL;
+  static constexpr int NBAR = 2 * A_STAGES + 2 * B_SLOTS + 4;
+  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+  static constexpr int TOTAL = OFF_TMEM + 16 + 1024;
+  static constexpr int STAGE_COLS = MT * BLOCK_N;              // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = 2 * STAGE_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+};
+
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED, int CASEB = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EPI_THREADS, 1) conv3_pair_kernel(const __grid_constant__ Conv3Params p) {
+  using L = C3PSmem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED, CASEB>;
+  using PT = Patch<MT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* aempty = afull + A_STAGES;
+  uint64_t* bfull = aempty + A_STAGES;
+  uint64_t* bempty = bfull + B_SLOTS;
+  uint64_t* tfull = bempty + B_SLOTS;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&p.a_map[i]);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.o_map[0]);
+    if (RED) tma_prefetch_desc(&p.red_map);
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&aempty[s], 1);
+    }
+    for (int s = 0; s < B_SLOTS; ++s) {
+      mbar_init(&bfull[s], 1);
+      mbar_init(&bempty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 2 * EPI_WARPS);        // epilogue warps of both CTAs (used in the leader)
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_slot, L::TMEM_COLS);      // warp 1 of BOTH CTAs, same shared-memory slot
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int rank = (int)cluster_ctarank();          // 0 = leader (issues the MMAs of the pair)
+  const int cid = blockIdx.x >> 1, NC = gridDim.x >> 1;
+  const int n_tile = cid % p.n_tiles;               // host guarantees NC % n_tiles == 0: fixed per cluster
+  const bool leader = rank == 0;
+  const bool resident = p.b_resident != 0;
+
+  if (warp == 0) {
+    // ================= TMA producer (all lanes run the loop, one elected lane issues) =================
+    int a_stage = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    bool first = true;
+    for (int tile = cid; tile < p.total_tiles; tile += NC) {
+      const int m_tile = 2 * (tile / p.n_tiles) + rank;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * TH;
+      const int w0 = (rem % p.tiles_w) * PT::TWS;
+      int cbg = 0;
+      for (int src = 0; src < p.nsrc; ++src) {
+        for (int cb = 0; cb < p.cblk[src]; ++cb, ++cbg) {
+          mbar_wait(&aempty[a_stage], a_phase ^ 1);
+          if (leader) mbar_expect_tx_e(&afull[a_stage], 2 * PT::BYTES);          // this CTA's patch and the peer's
+          tma_load_4d_2sm_e(smem + a_stage * PT::STRIDE, &p.a_map[src], &afull[a_stage], cb * 64, w0 - 1, h0 - 1, img);
+          if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
+          if (resident && !first) continue;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int slot = resident ? cbg * 9 + tap : b_slot;
+            if (!resident) mbar_wait(&bempty[slot], b_phase ^ 1);
+            if (leader) mbar_expect_tx_e(&bfull[slot], 2 * L::B_BYTES);
+            tma_load_2d_2sm_e(smem + L::OFF_B + slot * L::B_BYTES, &p.b_map, &bfull[slot], (tap * p.cblk_total + cbg) * 64,
+                              n_tile * BLOCK_N + rank * (BLOCK_N / 2));
+            if (!resident && ++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
+          }
+        }
+      }
+      first = false;
+    }
+    __syncwarp();
+  } else if (warp == 1 && leader) {
+    // ================= MMA issuer (all lanes run the loop, one elected lane issues) =================
+    // Kept lean on purpose: with 64-column tiles an MMA retires every 48 clocks and this warp's own instruction stream
+    // was the bottleneck (profiles/r01g): descriptors are base + compile-time offsets, one elect per four MMAs, and
+    // resident weights are waited for once (first tile) instead of once per tap.
+    constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);      // M = 256: 128 rows in each CTA
+    const uint32_t tmem_u = warp_uniform(tmem_base);
+    const uint32_t smem_base_u = warp_uniform(smem_u32(smem));
+    const uint64_t bdesc0 = make_smem_desc(smem_base_u + L::OFF_B, 16, 1024);
+    int a_stage = 0, b_slot = 0;
+    uint32_t a_phase = 0, b_phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    bool first = true;
+    for (int tile = cid; tile < p.total_tiles; tile += NC) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_u + as * L::STAGE_COLS;
+      for (int cbg = 0; cbg < p.cblk_total; ++cbg) {
+        mbar_wait(&afull[a_stage], a_phase);
+        if (resident && first)
+          for (int tap = 0; tap < 9; ++tap) mbar_wait(&bfull[cbg * 9 + tap], 0u);
+        tc_fence_after();
+        const uint64_t adesc0 = make_smem_desc(smem_base_u + a_stage * PT::STRIDE, 16, PT::PW * 128);
+        const uint64_t bdesc_cb = bdesc0 + (uint64_t)((cbg * 9 * L::B_BYTES) >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dh = tap / 3, dw = tap % 3;           // already offset by +1 (patch origin is pixel (-1, -1))
+          uint64_t bdesc;
+          if (resident) {
+            bdesc = bdesc_cb + (uint64_t)((tap * L::B_BYTES) >> 4);
+          } else {
+            mbar_wait(&bfull[b_slot], b_phase);
+            tc_fence_after();
+            bdesc = bdesc0 + (uint64_t)((b_slot * L::B_BYTES) >> 4);
+          }
+#pragma unroll
+          for (int j = 0; j < MT; ++j)                    // the MT 16x8 pixel tiles of the super-tile share this weight tile
+            tc_mma4_bf16_2sm_e(d_tmem + j * BLOCK_N, adesc0 + (uint64_t)(((dh * PT::PW + dw + j * TW) * 128) >> 4), bdesc, idesc,
+                           (cbg | tap) != 0);
+          if (!resident) {
+            tc_commit_2sm_e(&bempty[b_slot]);
+            if (++b_slot == B_SLOTS) { b_slot = 0; b_phase ^= 1; }
+          }
+        }
+        tc_commit_2sm_e(&aempty[a_stage]);
+        if (++a_stage == A_STAGES) { a_stage = 0; a_phase ^= 1; }
+      }
+      tc_commit_2sm_e(&tfull[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+      first = false;
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    // ================= epilogue (8 warps in each CTA, epilogue.cuh) =================
+    Epilogue<BLOCK_N, OUT_BUFS, TW, RED, CASEB> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    epi.red_map = &p.red_map;
+    epi.pair_rank = rank;
+    epi.load_vectors(n_tile);
+    for (int tile = cid; tile < p.total_tiles; tile += NC) {
+      const int m_tile = 2 * (tile / p.n_tiles) + rank;
+      const int img = m_tile / tiles_per_img;
+      const int rem = m_tile - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * TH;
+      const int w0 = (rem % p.tiles_w) * PT::TWS;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        const int wj = w0 + j * TW;
+        // RED == 2: the part after this one (its `a` tile is prefetched now)
+        bool has_next = false;
+        int nh0 = h0, nw0 = wj + TW, nimg = img;
+        if (RED == 2) {
+          if (j + 1 < MT) {
+            has_next = true;
+          } else if (tile + NC < p.total_tiles) {
+            const int nm = 2 * ((tile + NC) / p.n_tiles) + rank;
+            nimg = nm / tiles_per_img;
+            const int nrem = nm - nimg * tiles_per_img;
+            nh0 = (nrem / p.tiles_w) * TH;
+            nw0 = (nrem % p.tiles_w) * PT::TWS;
+            has_next = true;
+          }
+        }
+        epi.tile(h0, wj, [&](const uint8_t* blk, int b) {
+          const int jb = n_tile * (BLOCK_N / 64) + b;
+          const int map = jb / p.blocks_per_omap;
+          tma_store_4d(&p.o_map[map], blk, (jb - map * p.blocks_per_omap) * 64, wj, h0, img);
+        }, j * BLOCK_N, j == 0, j == MT - 1, L::STAGE_COLS, img, has_next, nh0, nw0, nimg);
+      }
+    }
+    epi.finish(n_tile, 2 * (cid / p.n_tiles) + rank);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // neither CTA leaves (or frees TMEM) while the other may still signal its barriers or run pair MMAs
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, L::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED = 0, int CASEB = 0>
+int launch_c3_pair(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream, bool* taken) {
+  using L = C3PSmem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED, CASEB>;
+  using PT = Patch<MT>;
+  static_assert(L::TOTAL <= 232448, "smem budget");
+  *taken = false;
+  const int n_tiles = p.ncols / BLOCK_N;
+  const int tiles_w = (p.W + PT::TWS - 1) / PT::TWS, tiles_h = (p.H + TH - 1) / TH;
+  const long long m_tiles = (long long)n_img * tiles_w * tiles_h;
+  const int pairs_avail = ub_num_sms() / 2;
+  if (m_tiles % 2 != 0 || n_tiles > pairs_avail) return UB_OK;          // an odd pixel-tile count or too many column tiles: single-CTA kernel
+  *taken = true;
+  auto kern = conv3_pair_kernel<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED, CASEB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_done = true;
+  }
+  int rc;
+  for (int i = 0; i < p.nsrc; ++i)
+    if ((rc = ub_tmap_act4d(&p.a_map[i], a_base[i], a_ch[i], p.W, p.H, n_img, (long long)a_ch[i] * 2, (long long)p.W * a_ch[i] * 2,
+                            (long long)p.H * p.W * a_ch[i] * 2, PT::PW, PH)))
+      return rc;
+  if ((rc = ub_tmap_mat2d(&p.b_map, p.w_base, p.ncols, 9ll * p.cblk_total * 64, BLOCK_N / 2))) return rc;      // each CTA loads half a tile
+  p.n_tiles = n_tiles;
+  p.tiles_w = tiles_w;
+  p.tiles_h = tiles_h;
+  const long long total = (m_tiles / 2) * n_tiles;                       // pair tiles: two pixel super-tiles x one column tile
+  UB_CHECK_SHAPE(total > 0 && total < (1ll << 30), "conv3 (pair): tile count out of range");
+  p.total_tiles = (int)total;
+  p.b_resident = 0;
+  long long clusters = (long long)(pairs_avail / n_tiles) * n_tiles;
+  if (clusters > total) clusters = total;                                // total is a multiple of n_tiles
+  const long long grid = 2 * clusters;
+  UB_CHECK_SHAPE(grid / n_tiles <= UB_STATS_ROWS, "conv3 (pair): stats rows");
+  const BnFin* fin = p.fin;
+  p.fin = nullptr;
+  const bool fused = fin && p.ep.stats && epi_fin_bytes(p.ncols) <= OUT_BUFS * L::E::OUT_BYTES;
+  if (fused) epi_set_fin(p.ep, *fin, (int)(grid / n_tiles));
+  else if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  if (RED) UB_CUDA(cudaMemsetAsync(p.ep.red_out, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ep.red_ncols, stream));
+  kern<<<(int)grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);           // __cluster_dims__(2, 1, 1)
+  UB_LAUNCH_CHECK();
+  if (fin && !fused)
+    return ub_bn_finalize(p.ep.stats, p.ncols, fin->groups, (long long)fin->count, fin->mean, fin->rstd, fin->moving_mean, fin->moving_var,
+                          fin->momentum, fin->eps, stream);
+  return UB_OK;
+}
+
+static bool use_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UB_CONV3_2CTA");       // CTA-pair (cta_group::2) kernel for the 128-column tiles
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED = 0, int CASEB = 0>
 int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream) {
   using L = C3Smem<BLOCK_N, MT, A_STAGES, B_SLOTS, OUT_BUFS, RED, CASEB>;
@@ -305,6 +581,14 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
+  if (use_pairs() && p.ncols % 128 == 0) {
+    bool taken = false;
+    int rc;
+    if (bias_cases) rc = launch_c3_pair<128, 2, 2, 8, 2, 0, 1>(p, a_base, a_ch, n_img, stream, &taken);
+    else if (p.ep.red_out) rc = launch_c3_pair<128, 2, 2, 8, 1, 1>(p, a_base, a_ch, n_img, stream, &taken);
+    else rc = launch_c3_pair<128, 2, 2, 8, 2>(p, a_base, a_ch, n_img, stream, &taken);
+    if (taken || rc) return rc;
+  }
   if (bias_cases) {            // forward of a BatchNorm-folded input: 9-case border bias (H, W >= 2 checked by the caller)
     if (p.ncols % 128 == 0) return launch_c3<128, 2, 2, 4, 2, 0, 1>(p, a_base, a_ch, n_img, stream);
     if (p.cblk_total == 1) return launch_c3<64, 2, 2, 9, 2, 0, 1>(p, a_base, a_ch, n_img, stream);
