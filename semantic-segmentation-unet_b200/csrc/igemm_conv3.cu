@@ -503,7 +503,7 @@ int launch_c3_pair(Conv3Params& p, const void* const* a_base, const int* a_ch, i
   const long long total = (m_tiles / 2) * n_tiles;                       // pair tiles: two pixel super-tiles x one column tile
   UB_CHECK_SHAPE(total > 0 && total < (1ll << 30), "conv3 (pair): tile count out of range");
   p.total_tiles = (int)total;
-  p.b_resident = 0;
+  p.b_resident = (9 * p.cblk_total <= B_SLOTS) ? 1 : 0;                 // 64-channel layers: the whole (half) weight slice stays in shared memory
   long long clusters = (long long)(pairs_avail / n_tiles) * n_tiles;
   if (clusters > total) clusters = total;                                // total is a multiple of n_tiles
   const long long grid = 2 * clusters;
@@ -525,8 +525,18 @@ int launch_c3_pair(Conv3Params& p, const void* const* a_base, const int* a_ch, i
 static bool use_pairs() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("UB_CONV3_2CTA");       // CTA-pair (cta_group::2) kernel for the 128-column tiles
-    v = (e && e[0] == '1') ? 1 : 0;
+    // CTA-pair (cta_group::2) kernel: parity green and 5-10 % faster sustained on the 128-column tiles (profiles/r02_ab_runs.md);
+    // UB_CONV3_2CTA=0 selects the single-CTA kernels for A/B runs
+    const char* e = getenv("UB_CONV3_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+static bool use_pairs64() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UB_CONV3_2CTA_64");    // ... also for the 64-output-channel layers
+    v = (e && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
 }
@@ -587,6 +597,16 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
     if (bias_cases) rc = launch_c3_pair<128, 2, 2, 8, 2, 0, 1>(p, a_base, a_ch, n_img, stream, &taken);
     else if (p.ep.red_out) rc = launch_c3_pair<128, 2, 2, 8, 1, 1>(p, a_base, a_ch, n_img, stream, &taken);
     else rc = launch_c3_pair<128, 2, 2, 8, 2>(p, a_base, a_ch, n_img, stream, &taken);
+    if (taken || rc) return rc;
+  } else if (use_pairs() && use_pairs64() && !p.ep.red_out && p.cblk_total <= 2) {
+    // 64 output channels (level 1): M = 256 x N = 64 per MMA, each CTA holds 32 columns of the resident weights (5 KB instead of 6 KB of
+    // operand reads per MMA: the layer is bound by the shared-memory port)
+    bool taken = false;
+    int rc;
+    if (bias_cases) rc = p.cblk_total == 1 ? launch_c3_pair<64, 2, 2, 9, 2, 0, 1>(p, a_base, a_ch, n_img, stream, &taken)
+                                           : launch_c3_pair<64, 1, 2, 18, 2, 0, 1>(p, a_base, a_ch, n_img, stream, &taken);
+    else rc = p.cblk_total == 1 ? launch_c3_pair<64, 2, 2, 9, 2>(p, a_base, a_ch, n_img, stream, &taken)
+                                : launch_c3_pair<64, 1, 2, 18, 2>(p, a_base, a_ch, n_img, stream, &taken);
     if (taken || rc) return rc;
   }
   if (bias_cases) {            // forward of a BatchNorm-folded input: 9-case border bias (H, W >= 2 checked by the caller)

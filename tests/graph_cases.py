@@ -40,7 +40,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 # tolerances (north_star): bf16 storage <= 1e-2, fp32 check mode <= 1e-4
 TOL = {"bf16": dict(softmax=1e-2, loss=1e-2, grad=1e-2, stat=1e-2, uncond=0.25, agree=0.99),
-       "fp32": dict(softmax=1e-4, loss=1e-4, grad=1e-4, stat=1e-4, uncond=0.25, agree=0.9995)}
+       "fp32": dict(softmax=1e-4, loss=1e-4, grad=1e-4, stat=1e-4, uncond=0.5, agree=0.9995)}
 
 
 # bf16 product path, one training step at Keras-initial weights, shapes with >= 512 BatchNorm samples per channel everywhere

@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "semantic-segmentation-unet_b200", "libunetb200.so")
-PAT = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCATOMSWS", "UTCBAR", "SYNCS", "HMMA", "LDG", "STG", "LDS", "STS", "REDG", "ATOM"]
+PAT = ["UTCHMMA", "2CTA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCATOMSWS", "UTCBAR", "SYNCS", "HMMA", "LDG", "STG", "LDS", "STS", "REDG", "ATOM"]
 
 
 def main():
@@ -35,9 +35,11 @@ def main():
             for p in PAT:
                 if op == p or op.startswith(p + "."):
                     cur[p] += 1
+            if ".2CTA" in op:
+                cur["2CTA"] += 1
     print("# SASS census of libunetb200.so (sm_100a), `cuobjdump -sass` opcode counts per kernel\n")
     print("`UTCHMMA` = tcgen05.mma (kind::f16), `UTMALDG`/`UTMASTG` = TMA tensor load/store, `LDTM` = tcgen05.ld (TMEM -> registers), "
-          "`UTCATOMSWS` = tcgen05.alloc/dealloc, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops.  `HMMA` (mma.sync) must be 0 everywhere.\n")
+          "`UTCATOMSWS` = tcgen05.alloc/dealloc, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops, `2CTA` = instructions of the cta_group::2 forms (`UTCHMMA.2CTA`, `UTMALDG.*.2CTA`, `UTCBAR.2CTA.MULTICAST`: the CTA-pair conv kernel).  `HMMA` (mma.sync) must be 0 everywhere.\n")
     print("| kernel | instr | " + " | ".join(PAT) + " |")
     print("|---|---:|" + "---:|" * len(PAT))
     tot = collections.Counter()
