@@ -395,10 +395,13 @@ def run_cuda(args):
         if args.layers:
             write_layer_table(args.layers, layer_ms)
     dp_check = None
-    if dp:
+    if dp and os.environ.get("UB_DP_NOREDUCE", "0") == "1":
+        dp_check = {"skipped": "UB_DP_NOREDUCE=1: attribution run without the gradient all-reduce (replicas diverge by design)"}
+    elif dp:
         dp.barrier()
         # data-parallel numerics on the live ranks: all-reduced G == sum of per-rank gradients, parameters identical after Adam
         dp_check = dp.verify_step(model, dx[0], dl[0])
+        dp_check["buckets"] = len(dp._buckets)
         dp.barrier()
 
     def finish():

@@ -532,11 +532,21 @@ static bool use_pairs() {
   }
   return v == 1;
 }
+static bool use_pairs256() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UB_CONV3_PAIR256");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 static bool use_pairs64() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("UB_CONV3_2CTA_64");    // ... also for the 64-output-channel layers
-    v = (e && e[0] == '0') ? 0 : 1;
+    // ... also for the 64-output-channel layers: parity green, but SLOWER (enc1b forward 718 -> 660 TFLOP/s sustained, dgrad 805 -> 738:
+    // an M = 256 x N = 64 pair MMA does not retire faster than two M = 128 x N = 64 ones, and the pair protocol adds latency): off
+    const char* e = getenv("UB_CONV3_2CTA_64");
+    v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
 }
@@ -591,6 +601,14 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
+  if (use_pairs() && use_pairs256() && p.ncols % 256 == 0 && !p.ep.red_out) {
+    // experiment (UB_CONV3_PAIR256=1): 128 pixels x 256 columns per CTA, N = 256 per pair MMA (each CTA holds 128 columns of the weight tile):
+    // 8 KB of operand reads per 128-clock MMA instead of 6 KB per 64-clock one, at the price of a weight tile per 128 instead of 256 pixels
+    bool taken = false;
+    int rc = bias_cases ? launch_c3_pair<256, 1, 2, 4, 1, 0, 1>(p, a_base, a_ch, n_img, stream, &taken)
+                        : launch_c3_pair<256, 1, 2, 4, 1>(p, a_base, a_ch, n_img, stream, &taken);
+    if (taken || rc) return rc;
+  }
   if (use_pairs() && p.ncols % 128 == 0) {
     bool taken = false;
     int rc;

@@ -17,7 +17,9 @@ import os
 import torch
 import torch.distributed as dist
 
-BUCKET_MIN_PARAMS = 2_000_000
+BUCKET_MIN_PARAMS = int(os.environ.get("UB_BUCKET_MIN_PARAMS", "2000000"))
+# measurement only (bench.py attribution runs): launch no gradient all-reduce at all, to time the step's compute at N ranks without its communication
+_NO_REDUCE = os.environ.get("UB_DP_NOREDUCE", "0") == "1"
 
 
 def plan_buckets(layers, min_params=BUCKET_MIN_PARAMS):
@@ -90,6 +92,8 @@ class DataParallel:
 
     def _reduce_slice(self, t, side_stream=None):
         self.allreduce_calls += 1
+        if _NO_REDUCE:
+            return
         if t.is_cuda:
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(t.device))

@@ -23,22 +23,34 @@ def short(name):
 
 
 def launches():
+    """per-kernel launch count, total duration and DRAM bytes of the captured launches (one CSV row per launch and metric)"""
     fp = os.path.join(OUT, f"launches_{tag}.csv")
     if not os.path.exists(fp):
         return None
     rows = [r for r in csv.reader(l for l in open(fp) if l.startswith('"'))]
     hdr = rows[0]
-    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-    agg = defaultdict(lambda: [0, 0.0])
+    ki, mi, vi, ii = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    agg = defaultdict(lambda: [set(), 0.0, 0.0, 0.0])
     for r in rows[1:]:
         k = short(r[ki])
-        agg[k][0] += 1
-        agg[k][1] += float(r[vi].replace(",", "")) / 1e6
+        v = float(r[vi].replace(",", ""))
+        agg[k][0].add(r[ii])
+        if r[mi] == "gpu__time_duration.sum":
+            agg[k][1] += v / 1e6
+        elif r[mi] == "dram__bytes_read.sum":
+            agg[k][2] += v / 1e9
+        elif r[mi] == "dram__bytes_write.sum":
+            agg[k][3] += v / 1e9
     tot = sum(v[1] for v in agg.values())
-    lines = [f"# ncu launch list `{tag}`: {len(rows) - 1} launches, {tot:.2f} ms total (cold-cache, serialised: compare SHARES)", "",
-             "| kernel | launches | ms | share |", "|---|---:|---:|---:|"]
-    for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        lines.append(f"| `{k}` | {n} | {ms:.3f} | {100 * ms / tot:.1f} % |")
+    n = sum(len(v[0]) for v in agg.values())
+    have_dram = any(v[2] or v[3] for v in agg.values())
+    lines = [f"# ncu launch list `{tag}`: {n} launches, {tot:.2f} ms total (cold-cache, serialised: compare SHARES)", "",
+             "| kernel | launches | ms | share |" + (" DRAM read GB | DRAM written GB |" if have_dram else ""),
+             "|---|---:|---:|---:|" + ("---:|---:|" if have_dram else "")]
+    for k, (ids, ms, rd, wr) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| `{k}` | {len(ids)} | {ms:.3f} | {100 * ms / tot:.1f} % |" + (f" {rd:.2f} | {wr:.2f} |" if have_dram else ""))
+    if have_dram:
+        lines.append(f"| **total** | {n} | {tot:.3f} | | {sum(v[2] for v in agg.values()):.2f} | {sum(v[3] for v in agg.values()):.2f} |")
     return "\n".join(lines)
 
 
