@@ -532,13 +532,13 @@ static bool use_pairs() {
   }
   return v == 1;
 }
-static bool use_pairs256() {
-  static int v = -1;
-  if (v < 0) {
+static int use_pairs256() {          // 1 = forced on, 0 = forced off, -1 = by shape
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("UB_CONV3_PAIR256");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = !e ? -1 : (e[0] == '1' ? 1 : 0);
   }
-  return v == 1;
+  return v;
 }
 static bool use_pairs64() {
   static int v = -1;
@@ -601,9 +601,11 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
-  if (use_pairs() && use_pairs256() && p.ncols % 256 == 0 && !p.ep.red_out) {
-    // experiment (UB_CONV3_PAIR256=1): 128 pixels x 256 columns per CTA, N = 256 per pair MMA (each CTA holds 128 columns of the weight tile):
-    // 8 KB of operand reads per 128-clock MMA instead of 6 KB per 64-clock one, at the price of a weight tile per 128 instead of 256 pixels
+  if (use_pairs() && !p.ep.red_out && p.ncols % 256 == 0 && (use_pairs256() == 1 || (use_pairs256() < 0 && p.ncols == 512))) {
+    // 128 pixels x 256 columns per CTA, N = 256 per pair MMA (each CTA holds 128 columns of the weight tile): 8 KB of operand reads per
+    // 128-clock MMA instead of 6 KB per 64-clock one, at the price of a weight tile per 128 instead of 256 pixels.  Measured sustained
+    // (profiles/r02_ab_runs.md, block I): 512-column layers +6 % (enc4b forward 1262 -> 1347, dgrad 1300 -> 1375 TFLOP/s), 256- and
+    // 1024-column layers +-1 %: default for 512 columns; UB_CONV3_PAIR256=1 / 0 forces it on for every multiple of 256 / off.
     bool taken = false;
     int rc = bias_cases ? launch_c3_pair<256, 1, 2, 4, 1, 0, 1>(p, a_base, a_ch, n_img, stream, &taken)
                         : launch_c3_pair<256, 1, 2, 4, 1>(p, a_base, a_ch, n_img, stream, &taken);
