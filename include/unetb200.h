@@ -280,12 +280,6 @@ int ub_check_deconv2x2_dgrad(const float* dz, const float* w, float* dx, int N, 
 int ub_check_deconv2x2_wgrad(const float* x, const float* dz, float* dw, int N, int h, int w_in, int Cin, int Cout,
                              cudaStream_t stream);
 
-/* ---- hardware probe (used by tests/tools only; documents the swizzled-operand addressing the conv kernels rely on) */
-int ub_debug_mma_rate(int N, int iters, int mn_major, int a_shift_rows, int a_sbo_bytes, int nblocks, long long* clocks,
-                      cudaStream_t stream);
-int ub_debug_desc_probe(const void* x, int R, const void* ident, float* out, int shift, int sbo_bytes, int base_offset, int mode,
-                        cudaStream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,7 @@ class UNet:
         self.step_count = 0
         self.launches = 0
         self.profile = None
+        self.nvtx = os.environ.get("UB_NVTX", "0") == "1"
         self._cur = ""                    # layer the current launches belong to (profiling tag)
         self._buf = {}
         self._inference_stale = True
@@ -101,6 +102,12 @@ class UNet:
     # ------------------------------------------------------------------------------------------------ plumbing
     def _call(self, name, *args):
         self.launches += 1
+        if self.nvtx:                      # UB_NVTX=1: one NVTX range per entry point, named <layer>:<entry> (nsys / ncu --nvtx)
+            torch.cuda.nvtx.range_push(f"{self._cur}:{name}")
+            try:
+                return _raw_call(name, *args, self._stream())
+            finally:
+                torch.cuda.nvtx.range_pop()
         if self.profile is not None:       # bench.py: CUDA events around every entry point
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()

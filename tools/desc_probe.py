@@ -9,7 +9,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import unetb200._C as C  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import _probe as C  # noqa: E402  (libunetb200_probe.so)
 
 dev = torch.device("cuda")
 R = 256

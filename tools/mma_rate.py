@@ -5,7 +5,8 @@ import json, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import unetb200._C as C  # noqa: E402
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import _probe as C  # noqa: E402  (libunetb200_probe.so)
 dev = torch.device("cuda")
 nblocks = 148
 for mn in (0, 1):
