@@ -115,7 +115,7 @@ class DataParallel:
             lo, hi, _ = self._buckets[self._next]
             self._next += 1
             self._reduce_slice(model.G[lo:hi], getattr(model, "_wstream", None))
-        if model.G.is_cuda:
+        if model.G.is_cuda and not _NO_REDUCE:
             torch.cuda.current_stream(model.G.device).wait_stream(self._comm_stream)
         for w in self._pending:
             w.wait()
