@@ -247,3 +247,17 @@ def test_sharded_inference_schedule():
     finally:
         C.call, td.all_reduce = real_call, real_ar
     assert owned_rows == H and (cover == 1).all()
+
+
+def test_bench_family_map_covers_the_default_schedule():
+    """bench.py's roofline object divides algorithmic FLOPs by the CUDA-event time of the entry points it knows by NAME: every
+    tensor-core entry point of the default step must be in its FAMILY map (a renamed entry point once left `roofline.achieved` empty)"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    m = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    names = set(_step(m))
+    tensor = {n for n in names if any(k in n for k in ("conv3x3_fwd", "conv3x3_dgrad", "conv3x3_wgrad", "deconv2x2_fwd", "deconv2x2_dgrad", "deconv2x2_wgrad"))}
+    assert tensor and tensor <= set(bench.FAMILY), tensor - set(bench.FAMILY)
