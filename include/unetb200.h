@@ -38,6 +38,7 @@ extern "C" {
 #define UB_MAX_CLASSES 8    /* number_classes of the register-resident head kernels (weights of every class in registers) */
 #define UB_MAX_CLASSES_ANY 255  /* number_classes of the head entry points: above UB_MAX_CLASSES the class-per-lane kernels of
                                    csrc/head_generic.cu run; 255 because labels and masks are uint8 (UNet/build_lmdb.py:151) */
+#define UB_MAX_CHANNELS 16  /* number_channels of the first-layer kernels (1..4 templated, 5..16 with run-time channel loops) */
 #define UB_ZSCORE_BLOCKS 256
 #define UB_BORDER_CHUNKS 64  /* ub_border_sums: scratch = UB_BORDER_CHUNKS * 8 * C floats */
 

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(TPB) aug_chanmix_kernel(float* __restrict__ x,
   float* p = x + (long long)n * C * plane;
   const double* m = mix + (long long)n * C * C;
   for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < plane; i += (long long)gridDim.x * TPB) {
-    double v[4], o[4];
+    double v[UB_MAX_CHANNELS], o[UB_MAX_CHANNELS];
     for (int c = 0; c < C; ++c) v[c] = (double)p[(long long)c * plane + i];
     for (int c = 0; c < C; ++c) {
       o[c] = 0.0;
@@ -277,7 +277,7 @@ int ub_aug_blur_axis(const float* src, float* dst, const double* weights, const 
 }
 
 int ub_aug_chanmix(float* x, const double* mix, int N, int C, long long plane, cudaStream_t stream) {
-  UB_CHECK_ARG(x && mix && N > 0 && C >= 1 && C <= 4 && plane > 0, "aug_chanmix: bad args");
+  UB_CHECK_ARG(x && mix && N > 0 && C >= 1 && C <= UB_MAX_CHANNELS && plane > 0, "aug_chanmix: bad args");
   UB_CHECK_SHAPE(N <= 65535, "aug_chanmix: N");
   aug_chanmix_kernel<<<dim3(blocks_for(plane, ub_num_sms() * 8), N), TPB, 0, stream>>>(x, mix, C, plane);
   UB_LAUNCH_CHECK();

@@ -1,4 +1,4 @@
-// First layer (Cin <= 4, not a tensor-core problem) and the class head of the U-Net (sm_100a, HBM-bound).
+// First layer (Cin <= UB_MAX_CHANNELS: templated for 1..4 channels, run-time channel loops above; not a tensor-core problem) and the class head of the U-Net (sm_100a, HBM-bound).
 //
 //   conv_first : relu(conv3x3_same(x_nchw_fp32, W) + b) -> NHWC 64 channels (+BN stat partials)   UNet/model.py:88
 //   head_fwd   : relu(conv1x1(x, W) + b), 64 -> K classes, fp32 [P][K] (+BN stat partials)          UNet/model.py:136
@@ -68,11 +68,14 @@ __device__ __forceinline__ float block_sum(float v, float* sh /*[TPB/32]*/) {
 
 // ------------------------------------------------------------------ first conv
 // x: fp32 NCHW [N][CIN][H][W]; w: fp32 [64][9][CIN]; out: NHWC [P][64]; partial: [rows][2][64]
-template <typename T, int CIN>
+template <typename T, int CIN_T>
 __global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                              const float* __restrict__ post_scale, const float* __restrict__ post_shift,
-                                                             T* __restrict__ out, float* __restrict__ partial, int N, int H, int W) {
-  __shared__ float ws[9 * CIN][64];
+                                                             T* __restrict__ out, float* __restrict__ partial, int N, int H, int W,
+                                                             int cin_rt) {
+  constexpr int CMAX = CIN_T ? CIN_T : UB_MAX_CHANNELS;      // CIN_T == 0: channel count at run time (5 .. UB_MAX_CHANNELS)
+  const int CIN = CIN_T ? CIN_T : cin_rt;
+  __shared__ float ws[9 * CMAX][64];
   __shared__ float red[TPB * 8];
   for (int i = threadIdx.x; i < 64 * 9 * CIN; i += TPB) {
     const int co = i / (9 * CIN), k = i % (9 * CIN);
@@ -139,12 +142,14 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_kernel(const float* __rest
 // window is loaded once per strip (one 128-bit + two scalar loads per row) and the weights are read from shared memory
 // once per strip instead of once per pixel: ~2.5x fewer issued instructions per output than the per-pixel kernels,
 // which were issue-bound at 1/8 of the HBM roofline (profiles/r01a).
-template <typename T, int CIN>
+template <typename T, int CIN_T>
 __global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, const float* __restrict__ post_scale,
                                                                    const float* __restrict__ post_shift, T* __restrict__ out,
-                                                                   float* __restrict__ partial, int N, int H, int W) {
-  __shared__ float ws[9 * CIN][64];
+                                                                   float* __restrict__ partial, int N, int H, int W, int cin_rt) {
+  constexpr int CMAX = CIN_T ? CIN_T : UB_MAX_CHANNELS;
+  const int CIN = CIN_T ? CIN_T : cin_rt;
+  __shared__ float ws[9 * CMAX][64];
   __shared__ float red[TPB * 8];
   for (int i = threadIdx.x; i < 64 * 9 * CIN; i += TPB) {
     const int co = i / (9 * CIN), k = i % (9 * CIN);     // w is [co][tap][ci]; k = tap * CIN + ci
@@ -236,13 +241,15 @@ __global__ void __launch_bounds__(TPB) conv_first_fwd_strip_kernel(const float* 
 // positions outside the TILE are zero (the tile is convolved as an image of its own, 'same' padding).  Same strip mining as above.
 __device__ __forceinline__ int reflect_index(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }
 
-template <typename T, int CIN>
+template <typename T, int CIN_T>
 __global__ void __launch_bounds__(TPB) conv_first_fwd_tiles_kernel(const float* __restrict__ img, const int* __restrict__ origin, int img_h,
                                                                    int img_w, long long pitch, long long plane_stride,
                                                                    const float* __restrict__ w, const float* __restrict__ bias,
                                                                    const float* __restrict__ post_scale, const float* __restrict__ post_shift,
-                                                                   T* __restrict__ out, int N, int H, int W) {
-  __shared__ float ws[9 * CIN][64];
+                                                                   T* __restrict__ out, int N, int H, int W, int cin_rt) {
+  constexpr int CMAX = CIN_T ? CIN_T : UB_MAX_CHANNELS;
+  const int CIN = CIN_T ? CIN_T : cin_rt;
+  __shared__ float ws[9 * CMAX][64];
   for (int i = threadIdx.x; i < 64 * 9 * CIN; i += TPB) {
     const int co = i / (9 * CIN), k = i % (9 * CIN);
     ws[k][co] = w[i];
@@ -881,7 +888,8 @@ int ubg_head_bwd_apply(const float* dy, const float* a, const void* x, const flo
     if ((cin) == 1) { constexpr int CIN = 1; __VA_ARGS__; }         \
     else if ((cin) == 2) { constexpr int CIN = 2; __VA_ARGS__; }    \
     else if ((cin) == 3) { constexpr int CIN = 3; __VA_ARGS__; }    \
-    else { constexpr int CIN = 4; __VA_ARGS__; }                    \
+    else if ((cin) == 4) { constexpr int CIN = 4; __VA_ARGS__; }    \
+    else { constexpr int CIN = 0; __VA_ARGS__; }  /* 5 .. UB_MAX_CHANNELS: channel loops at run time */ \
   } while (0)
 
 extern "C" {
@@ -904,7 +912,7 @@ int ub_conv_first_fwd_affine_tiles(const float* img, const int* origin_yx, int i
                                    const float* w, const float* bias, const float* scale, const float* shift, void* out, int N, int H, int W,
                                    int Cin, int dtype, cudaStream_t stream) {
   UB_CHECK_ARG(img && origin_yx && w && bias && scale && shift && out, "conv_first_fwd_affine_tiles: null pointer");
-  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_fwd_affine_tiles: Cin=%d must be in [1,4]", Cin);
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= UB_MAX_CHANNELS, "conv_first_fwd_affine_tiles: Cin=%d must be in [1, %d]", Cin, UB_MAX_CHANNELS);
   UB_CHECK_SHAPE(N > 0 && H > 0 && W > 0 && W % 4 == 0, "conv_first_fwd_affine_tiles: tile width must be a multiple of 4 (got %d x %d)", H, W);
   UB_CHECK_SHAPE(img_h >= 2 && img_w >= 2 && row_pitch >= img_w, "conv_first_fwd_affine_tiles: bad image extent %d x %d, pitch %lld", img_h, img_w,
                  row_pitch);
@@ -913,7 +921,7 @@ int ub_conv_first_fwd_affine_tiles(const float* img, const int* origin_yx, int i
   const long long P = (long long)N * H * W;
   const int grid = grid_for(P / 4, 32 * 4, UB_STATS_ROWS);
   UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_tiles_kernel<T, CIN><<<grid, TPB, 0, stream>>>(img, origin_yx, img_h, img_w, row_pitch, plane_stride,
-                                                                                                        w, bias, scale, shift, (T*)out, N, H, W))));
+                                                                                                        w, bias, scale, shift, (T*)out, N, H, W, Cin))));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
@@ -921,15 +929,15 @@ int ub_conv_first_fwd_affine_tiles(const float* img, const int* origin_yx, int i
 static int conv_first_impl(const float* x_nchw, const float* w, const float* bias, const float* post_scale, const float* post_shift, void* out,
                            float* partial, int N, int H, int W, int Cin, int dtype, cudaStream_t stream) {
   UB_CHECK_ARG(x_nchw && w && bias && out, "conv_first_fwd: null pointer");
-  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_fwd: Cin=%d must be in [1,4]", Cin);
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= UB_MAX_CHANNELS, "conv_first_fwd: Cin=%d must be in [1, %d]", Cin, UB_MAX_CHANNELS);
   const long long P = (long long)N * H * W;
   const bool strip = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
   const int grid = grid_for(strip ? P / 4 : P, 32 * 4, UB_STATS_ROWS);
   if (partial) UB_CUDA(cudaMemsetAsync(partial, 0, sizeof(float) * UB_STATS_ROWS * 2 * 64, stream));
   if (strip)
-    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_strip_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, post_scale, post_shift, (T*)out, partial, N, H, W))));
+    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_strip_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, post_scale, post_shift, (T*)out, partial, N, H, W, Cin))));
   else
-    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, post_scale, post_shift, (T*)out, partial, N, H, W))));
+    UB_DISPATCH_T(dtype, UB_DISPATCH_CIN(Cin, (conv_first_fwd_kernel<T, CIN><<<grid, TPB, 0, stream>>>(x_nchw, w, bias, post_scale, post_shift, (T*)out, partial, N, H, W, Cin))));
   UB_LAUNCH_CHECK();
   return UB_OK;
 }
@@ -938,7 +946,7 @@ static int conv_first_impl(const float* x_nchw, const float* w, const float* bia
 int ub_conv_first_wgrad(const float* x_nchw, const void* dz, float* dw, float* partial, int N, int H, int W, int Cin, int dtype,
                         cudaStream_t stream) {
   UB_CHECK_ARG(x_nchw && dz && dw && partial, "conv_first_wgrad: null pointer");
-  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4, "conv_first_wgrad: Cin=%d must be in [1,4]", Cin);
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= UB_MAX_CHANNELS, "conv_first_wgrad: Cin=%d must be in [1, %d]", Cin, UB_MAX_CHANNELS);
   const long long P = (long long)N * H * W;
   const bool strip = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
   const int rows = grid_for(strip ? P / 4 : P, 32 * 4, UB_STATS_ROWS);
@@ -955,7 +963,7 @@ int ub_conv_first_wgrad(const float* x_nchw, const void* dz, float* dw, float* p
 
 int ub_conv_first_dgrad(const void* dz, const float* w, float* dx_nchw, int N, int H, int W, int Cin, int dtype, cudaStream_t stream) {
   UB_CHECK_ARG(dz && w && dx_nchw, "conv_first_dgrad: null pointer");
-  UB_CHECK_SHAPE(Cin >= 1 && Cin <= 4 && N > 0 && H > 0 && W > 0, "conv_first_dgrad: bad shape");
+  UB_CHECK_SHAPE(Cin >= 1 && Cin <= UB_MAX_CHANNELS && N > 0 && H > 0 && W > 0, "conv_first_dgrad: bad shape");
   const long long total = (long long)N * Cin * H * W;
   UB_DISPATCH_T(dtype, (conv_first_dgrad_kernel<T><<<grid_for(total, TPB, ub_num_sms() * 8), TPB, 0, stream>>>((const T*)dz, w, dx_nchw, N, H, W, Cin)));
   UB_LAUNCH_CHECK();

@@ -54,8 +54,8 @@ class UNet:
         if number_classes < 1 or number_classes > _C.MACROS["UB_MAX_CLASSES_ANY"]:
             # labels and masks are uint8 on this path, as in the reference's databases (UNet/build_lmdb.py:151 forces uint8 masks)
             raise ValueError(f"number_classes must be in [1, {_C.MACROS['UB_MAX_CLASSES_ANY']}]")
-        if number_channels < 1 or number_channels > 4:
-            raise ValueError("number_channels must be in [1, 4]")
+        if number_channels < 1 or number_channels > _C.MACROS["UB_MAX_CHANNELS"]:
+            raise ValueError(f"number_channels must be in [1, {_C.MACROS['UB_MAX_CHANNELS']}]")
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.number_channels = int(number_channels)

@@ -776,6 +776,7 @@ CASES = {
     # number_classes > 8: the class-per-lane head kernels inside the whole graph (fp32 check mode <= 1e-4, bf16 at the storage floor)
     # label_smoothing (UNet/model.py:65, :77)
     "live_fp32_c1k2_smooth": lambda: case_live("fp32", N=2, C=1, H=64, W=48, K=2, seed=28, smooth=0.1),
+    "live_fp32_c6k3": lambda: case_live("fp32", N=1, C=6, H=48, W=64, K=3, seed=29, gb=2),
     "live_fp32_c3k20": lambda: case_live("fp32", N=1, C=3, H=64, W=80, K=20, seed=26, gb=2),
     "live_bf16_c1k40": lambda: case_live("bf16", N=1, C=1, H=96, W=96, K=40, seed=27, gb=2, floor=True),
     "golden_c1_k2_fp32": lambda: case_golden("graph_c1_k2", "fp32"),
