@@ -1222,6 +1222,6 @@ CASES = {
     # more than 4 input channels: run-time channel loops in the first-layer kernels (UB_MAX_CHANNELS = 16)
     "conv_first_c6": lambda: case_conv_first(6, seed=81),
     "conv_first_c16_oddw": lambda: case_conv_first(16, N=1, H=12, W=18, seed=82),
-    "conv_first_tiles_c5": lambda: case_conv_first_tiles(5, H=330, W=518, seed=83),
+    "conv_first_tiles_c5": lambda: case_conv_first_tiles(5, H=330, W=1030, seed=83),
     "augment_c6_f32": lambda: case_augment(6, "f32", N=2, H=32, W=48, seed=84),
 }
