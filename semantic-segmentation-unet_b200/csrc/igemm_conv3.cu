@@ -56,6 +56,9 @@ struct Conv3Params {
   int b_resident;
   const void* w_base;        // host-side only: weight matrix [ncols][9 * Cin] for the tensor map
   const BnFin* fin;          // host-side only: BatchNorm to finalise in the last CTA (forward with statistics), or null
+  const void* o_base[2];     // host-side only: output tensors behind o_map (the row-streaming kernel rebuilds the maps with its own box)
+  int o_ch[2];
+  int rows_total, strips_w;  // conv3_rows.cuh: row units (image, 128-pixel strip, row) of the launch; strips per image row
 };
 
 template <int BLOCK_N, int MT, int A_STAGES, int B_SLOTS, int OUT_BUFS, int RED, int CASEB = 0>
@@ -595,12 +598,21 @@ int launch_c3(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_
   return UB_OK;
 }
 
+#include "conv3_rows.cuh"
+
 int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream, bool bias_cases = false) {
   p.cblk_total = 0;
   for (int i = 0; i < p.nsrc; ++i) p.cblk_total += p.cblk[i];
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
+  if (use_rows() >= 1 && p.ncols == 64 && !p.ep.red_out && p.W % RW == 0 && p.o_ch[0] == 64) {
+    // 64 output channels and rows of whole 128-pixel strips (level 1 at the benchmark shapes): the row-streaming kernel (conv3_rows.cuh)
+    if (p.cblk_total == 1)
+      return bias_cases ? launch_c3_rows<1, 6, 2, 1>(p, a_base, a_ch, n_img, stream) : launch_c3_rows<1, 6, 2, 0>(p, a_base, a_ch, n_img, stream);
+    if (p.cblk_total == 2 && use_rows() >= 2)
+      return bias_cases ? launch_c3_rows<2, 3, 1, 1>(p, a_base, a_ch, n_img, stream) : launch_c3_rows<2, 3, 1, 0>(p, a_base, a_ch, n_img, stream);
+  }
   if (use_pairs() && !p.ep.red_out && p.ncols % 256 == 0 && (use_pairs256() == 1 || (use_pairs256() < 0 && p.ncols == 512))) {
     // 128 pixels x 256 columns per CTA, N = 256 per pair MMA (each CTA holds 128 columns of the weight tile): 8 KB of operand reads per
     // 128-clock MMA instead of 6 KB per 64-clock one, at the price of a weight tile per 128 instead of 256 pixels.  Measured sustained
@@ -692,6 +704,8 @@ int ub_conv3_halo_fwd(const void* x0, int C0, const void* x1, int C1, const void
   p.cblk[1] = C1 / 64;
   p.w_base = w;
   if ((rc = out_map(&p.o_map[0], out, Cout, W, H, N))) return rc;
+  p.o_base[0] = out;
+  p.o_ch[0] = Cout;
   p.H = p.ep.H = H;
   p.W = p.ep.W = W;
   p.blocks_per_omap = Cout / 64;
@@ -717,6 +731,10 @@ int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, in
   p.w_base = w_t;
   if ((rc = out_map(&p.o_map[0], dx0, C0, W, H, N))) return rc;
   if (C1 > 0 && (rc = out_map(&p.o_map[1], dx1, C1, W, H, N))) return rc;
+  p.o_base[0] = dx0;
+  p.o_ch[0] = C0;
+  p.o_base[1] = dx1;
+  p.o_ch[1] = C1;
   p.H = p.ep.H = H;
   p.W = p.ep.W = W;
   p.blocks_per_omap = C0 / 64;

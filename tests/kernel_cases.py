@@ -1224,4 +1224,16 @@ CASES = {
     "conv_first_c16_oddw": lambda: case_conv_first(16, N=1, H=12, W=18, seed=82),
     "conv_first_tiles_c5": lambda: case_conv_first_tiles(5, H=330, W=1030, seed=83),
     "augment_c6_f32": lambda: case_augment(6, "f32", N=2, H=32, W=48, seed=84),
+    # 64 output channels at widths that are multiples of 128: the row-streaming kernel (csrc/conv3_rows.cuh); segments that start and end
+    # inside a strip, strips and images changing inside a CTA's range, ring wrap (H > 8), a single row, 128 -> 64 (two channel blocks)
+    "rows_fwd_64_64": lambda: case_conv3x3_fwd(64, 0, 64, N=2, H=11, W=256, seed=90),
+    "rows_fwd_64_64_h1": lambda: case_conv3x3_fwd(64, 0, 64, N=3, H=1, W=128, seed=91),
+    "rows_fwd_64_64_tall": lambda: case_conv3x3_fwd(64, 0, 64, N=1, H=333, W=128, relu=0, seed=92),
+    "rows_fwd_cat_64+64_64": lambda: case_conv3x3_fwd(64, 64, 64, N=2, H=19, W=128, seed=93),
+    "rows_fwd_bn_cases": lambda: case_conv_fwd_bn(64, 0, 64, N=2, H=37, W=256, cases=True, seed=94),
+    "rows_fwd_bn_cat_cases": lambda: case_conv_fwd_bn(64, 64, 64, N=1, H=21, W=128, cases=True, seed=95),
+    "rows_fwd_folded": lambda: case_conv_fwd_folded(64, 0, 64, N=2, H=24, W=128, seed=96),
+    "rows_fwd_folded_cat": lambda: case_conv_fwd_folded(64, 64, 64, N=1, H=9, W=256, seed=97, identity0=True),
+    "rows_dgrad_64_64": lambda: case_conv3x3_dgrad(64, 64, 0, N=2, H=13, W=256, seed=98),
+    "rows_dgrad_128_64": lambda: case_conv3x3_dgrad(128, 64, 0, N=2, H=10, W=128, seed=99),
 }

@@ -119,7 +119,7 @@ def main():
         x = torch.empty(1 << 30, device=dev, dtype=torch.bfloat16)
         y = torch.empty_like(x)
         sustained("copy_2GiB", lambda i: y.copy_(x), 2.0 * x.numel() * 2, "GB/s", secs)
-    layers = {"enc1b": (512, 64, 0, 64), "dec2a": (256, 128, 128, 128), "enc3b": (128, 256, 0, 256), "enc4b": (64, 512, 0, 512), "botb": (32, 1024, 0, 1024)}
+    layers = {"enc1b": (512, 64, 0, 64), "dec1a": (512, 64, 64, 64), "enc2a": (256, 64, 0, 128), "dec2a": (256, 128, 128, 128), "enc3b": (128, 256, 0, 256), "enc4b": (64, 512, 0, 512), "botb": (32, 1024, 0, 1024)}
     for name, (H, C0, C1, Cout) in layers.items():
         for mode in ("fwd", "dgrad", "wgrad"):
             if want(f"{name}_{mode}"):
