@@ -243,7 +243,7 @@ int launch_c3_rows(Conv3Params& p, const void* const* a_base, const int* a_ch, i
   if ((rc = ub_tmap_act4d(&p.o_map[0], p.o_base[0], p.o_ch[0], p.W, p.H, n_img, (long long)p.o_ch[0] * 2, (long long)p.W * p.o_ch[0] * 2,
                           (long long)p.H * p.W * p.o_ch[0] * 2, RW, 1)))
     return rc;
-  p.strips_w = p.W / RW;
+  p.strips_w = (p.W + RW - 1) / RW;         // a ragged last strip: loads zero-fill, stores clip, statistics mask (epilogue.cuh)
   const long long total = (long long)n_img * p.strips_w * p.H;
   UB_CHECK_SHAPE(total > 0 && total < (1ll << 30), "conv3 (rows): row count out of range");
   p.rows_total = (int)total;
@@ -264,11 +264,17 @@ int launch_c3_rows(Conv3Params& p, const void* const* a_base, const int* a_ch, i
   return UB_OK;
 }
 
-static int use_rows() {            // UB_CONV3_ROWS: 0 = off, 1 = 64 -> 64 layers, 2 = also 128 -> 64 (dec1a forward)
+// the last strip of a row may be ragged; worth it while the padding stays under 1/8 of the row
+static bool rows_width_ok(int W) { return W >= RW && ((W + RW - 1) / RW * RW - W) * 8 <= W; }
+
+// UB_CONV3_ROWS: 0 = off (the halo-patch kernels of igemm_conv3.cu), 1 = 64 -> 64 layers only, 2 (default) = also 128 -> 64 (dec1a forward,
+// enc2a dgrad).  Measured on B200 (profiles/r02_ab_runs.md, block N): enc1b dgrad 796 -> 1042 TFLOP/s sustained, dec1a forward 908 -> 1054,
+// enc2a dgrad 905 -> 1136; the step 22.69 -> 22.36 ms.
+static int use_rows() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("UB_CONV3_ROWS");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 2;
   }
   return v;
 }

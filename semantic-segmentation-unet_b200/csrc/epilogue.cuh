@@ -79,14 +79,14 @@ __host__ __device__ constexpr int epi_fin_bytes(int ncols) { return 256 * 8 * 8 
 template <int BLOCK_N, int OUT_BUFS, int RED = 0, int CASEB = 0>
 struct EpiSmem {
   static constexpr int OUT_BYTES = (BLOCK_N / 64) * EPI_OUT_BLK;
-  static constexpr int OFF_STAT = 0;                                  // float[row groups <= 8][2][BLOCK_N]: aliases staging buffer 0,
+  static constexpr int OFF_STAT = 0;                                  // float[row groups][2][BLOCK_N] (16 KB): aliases staging buffer 0,
                                                                       // only touched in finish() after every TMA store has drained
   static constexpr int OFF_ABUF = OUT_BUFS * OUT_BYTES;               // RED: the `a` tile, same swizzled layout as the staging tile
   static constexpr int OFF_VEC = OFF_ABUF + RED * OUT_BYTES;          // scale, shift, bias: float[2 + NBIAS][BLOCK_N]
   static constexpr int NBIAS = CASEB ? 9 : 1;
   static constexpr int OFF_ABAR = OFF_VEC + (2 + NBIAS) * BLOCK_N * 4;   // RED: mbarrier of the `a` tile load
   static constexpr int TOTAL = OFF_ABAR + 16;
-  static_assert(8 * 2 * BLOCK_N * 4 <= OUT_BYTES, "statistics scratch must fit the staging buffer");
+  static_assert((256 / (BLOCK_N / 8)) * 2 * BLOCK_N * 4 <= OUT_BYTES, "statistics scratch must fit the staging buffer");
 };
 
 // TILE_W_: pixels per tile row (tile row r of accumulator row m: m / TILE_W_, column m % TILE_W_)
@@ -98,6 +98,11 @@ struct Epilogue {
   static constexpr int PAIRS = BLOCK_N / 2;                    // column pairs
   static constexpr int ROW_GROUPS = EPI_THREADS / PAIRS;       // 8 / 4 / 2 for BLOCK_N 64 / 128 / 256
   static constexpr int ROWS_PER_GROUP = 128 / ROW_GROUPS;
+  // forward statistics: thread = (16-byte chunk of 8 columns, row group); rows are interleaved over the groups so that the four rows a
+  // warp reads at once differ in (row & 7) -- with the 128-byte swizzle every ld.shared.v4 wavefront then covers all 32 banks
+  static constexpr int ST_CHUNKS = BLOCK_N / 8;                // 8 / 16 / 32
+  static constexpr int ST_GROUPS = EPI_THREADS / ST_CHUNKS;    // 32 / 16 / 8
+  static constexpr int ST_ROWS = 128 / ST_GROUPS;              // rows per thread and part: 4 / 8 / 16
 
   uint8_t* base;             // epilogue smem region (1024-aligned)
   const EpiParams& ep;
@@ -107,7 +112,8 @@ struct Epilogue {
   int as = 0, buf = 0;
   uint32_t aphase = 0;
   bool post;
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;      // RED: sums of this thread's column pair
+  float ss[8] = {}, qq[8] = {};                       // forward statistics: sum / sum of squares of this thread's 8 columns
   // RED state
   const CUtensorMap* red_map = nullptr;
   int red_nt = 0;            // this CTA's n_tile
@@ -230,10 +236,20 @@ struct Epilogue {
       tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + as * stage_cols + col_off + chunk * 32, r);
       tmem_ld_wait();
       float f[32];
+      const float4* vb4 = reinterpret_cast<const float4*>(vb + chunk * 32);     // 16-byte aligned: OFF_VEC and every vector start are
+      if (RED != 0) {               // a dgrad: no bias, no activation (ub_conv3_halo_dgrad leaves both unset)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float x = __uint_as_float(r[j]) + vb[chunk * 32 + j];
-        f[j] = ep.relu ? fmaxf(x, 0.f) : x;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+      } else
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = vb4[j];
+        const float x0 = __uint_as_float(r[4 * j + 0]) + b4.x, x1 = __uint_as_float(r[4 * j + 1]) + b4.y;
+        const float x2 = __uint_as_float(r[4 * j + 2]) + b4.z, x3 = __uint_as_float(r[4 * j + 3]) + b4.w;
+        f[4 * j + 0] = ep.relu ? fmaxf(x0, 0.f) : x0;
+        f[4 * j + 1] = ep.relu ? fmaxf(x1, 0.f) : x1;
+        f[4 * j + 2] = ep.relu ? fmaxf(x2, 0.f) : x2;
+        f[4 * j + 3] = ep.relu ? fmaxf(x3, 0.f) : x3;
       }
       if (post) {
 #pragma unroll
@@ -261,24 +277,34 @@ struct Epilogue {
       for (int b = 0; b < BLOCK_N / 64; ++b) store_fn(out_stage + b * EPI_OUT_BLK, b);
       tma_store_commit();
     }
-    if (ep.stats) {
-      // column sums of the staged (rounded) tile: thread = (column pair, row group)
-      const int pair = et % PAIRS, grp = et / PAIRS;
-      const int c = 2 * pair;
-      const uint32_t colbase = smem_u32(out_stage) + (c >> 6) * EPI_OUT_BLK + ((c & 7) << 1);
-      const int c16 = (c & 63) >> 3;
-      const int r_begin = grp * ROWS_PER_GROUP;
-#pragma unroll 8
-      for (int rr = 0; rr < ROWS_PER_GROUP; ++rr) {
-        const int r_ = r_begin + rr;
-        if ((h0 + r_ / TILE_W_ < ep.H) && (w0 + r_ % TILE_W_ < ep.W)) {   // warp-uniform
-          uint32_t u;
-          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(colbase + r_ * 128 + ((c16 ^ (r_ & 7)) << 4)));
-          const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
-          s0 += a;
-          s1 += b;
-          q0 = fmaf(a, a, q0);
-          q1 = fmaf(b, b, q1);
+    if (RED == 0 && ep.stats) {   // (a dgrad with a fused reduction never has forward statistics)
+      // column sums of the staged (rounded) tile: thread = (16-byte chunk, row group); four independent 16-byte loads in flight
+      const int ck = et % ST_CHUNKS, grp = et / ST_CHUNKS;
+      const uint32_t cbase = smem_u32(out_stage) + (ck >> 3) * EPI_OUT_BLK;
+      const int c16 = ck & 7;
+#pragma unroll
+      for (int rb = 0; rb < ST_ROWS; rb += 4) {
+        uint32_t u[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r_ = (rb + i) * ST_GROUPS + grp;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(u[i][0]), "=r"(u[i][1]), "=r"(u[i][2]), "=r"(u[i][3])
+                       : "r"(cbase + r_ * 128 + ((c16 ^ (r_ & 7)) << 4)));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r_ = (rb + i) * ST_GROUPS + grp;
+          if ((h0 + r_ / TILE_W_ < ep.H) && (w0 + r_ % TILE_W_ < ep.W)) {      // ragged tiles: rows outside the image do not count
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float a = __uint_as_float(u[i][k] << 16), b = __uint_as_float(u[i][k] & 0xffff0000u);
+              ss[2 * k] += a;
+              ss[2 * k + 1] += b;
+              qq[2 * k] = fmaf(a, a, qq[2 * k]);
+              qq[2 * k + 1] = fmaf(b, b, qq[2 * k + 1]);
+            }
+          }
         }
       }
     }
@@ -351,19 +377,20 @@ struct Epilogue {
       return;
     }
     if (ep.stats) {
-      float* st = reinterpret_cast<float*>(base + S::OFF_STAT);     // [ROW_GROUPS][2][BLOCK_N]
-      const int pair = et % PAIRS, grp = et / PAIRS;
+      float* st = reinterpret_cast<float*>(base + S::OFF_STAT);     // [ST_GROUPS][2][BLOCK_N]
+      const int ck = et % ST_CHUNKS, grp = et / ST_CHUNKS;
       named_bar_sync(1, EPI_THREADS);
-      st[(grp * 2 + 0) * BLOCK_N + 2 * pair] = s0;
-      st[(grp * 2 + 0) * BLOCK_N + 2 * pair + 1] = s1;
-      st[(grp * 2 + 1) * BLOCK_N + 2 * pair] = q0;
-      st[(grp * 2 + 1) * BLOCK_N + 2 * pair + 1] = q1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        st[(grp * 2 + 0) * BLOCK_N + ck * 8 + k] = ss[k];
+        st[(grp * 2 + 1) * BLOCK_N + ck * 8 + k] = qq[k];
+      }
       named_bar_sync(1, EPI_THREADS);
       for (int i = et; i < 2 * BLOCK_N; i += EPI_THREADS) {
         const int which = i / BLOCK_N, c = i % BLOCK_N;
         float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < ROW_GROUPS; ++g) t += st[(g * 2 + which) * BLOCK_N + c];
+        for (int g = 0; g < ST_GROUPS; ++g) t += st[(g * 2 + which) * BLOCK_N + c];
         ep.stats[((size_t)stats_row * 2 + which) * ep.ncols + n_tile * BLOCK_N + c] = t;
       }
       if (ep.fin_mean) finalize_last_cta(st);

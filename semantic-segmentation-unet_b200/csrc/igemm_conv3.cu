@@ -606,8 +606,9 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
-  if (use_rows() >= 1 && p.ncols == 64 && !p.ep.red_out && p.W % RW == 0 && p.o_ch[0] == 64) {
-    // 64 output channels and rows of whole 128-pixel strips (level 1 at the benchmark shapes): the row-streaming kernel (conv3_rows.cuh)
+  if (use_rows() >= 1 && p.ncols == 64 && !p.ep.red_out && p.o_ch[0] == 64 && rows_width_ok(p.W)) {
+    // 64 output channels and rows that fill their 128-pixel strips (level 1 at the benchmark shapes, the 1216-pixel inference tiles): the
+    // row-streaming kernel (conv3_rows.cuh)
     if (p.cblk_total == 1)
       return bias_cases ? launch_c3_rows<1, 6, 2, 1>(p, a_base, a_ch, n_img, stream) : launch_c3_rows<1, 6, 2, 0>(p, a_base, a_ch, n_img, stream);
     if (p.cblk_total == 2 && use_rows() >= 2)
