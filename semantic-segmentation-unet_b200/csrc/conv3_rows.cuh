@@ -26,9 +26,9 @@ constexpr int ROW_STRIDE = 17 * 1024;        // ring pitch (1024-aligned)
 constexpr int RING = 8;                      // TMEM slots of 64 columns
 constexpr int WT_BYTES = 64 * 128;           // one (tap, channel block) weight tile: 64 output channels x 64 input channels
 
-template <int CBLK, int A_STAGES, int OUT_BUFS, int CASEB>
+template <int CBLK, int A_STAGES, int OUT_BUFS, int CASEB, int RED = 0>
 struct C3RSmem {
-  using E = EpiSmem<64, OUT_BUFS, 0, CASEB>;
+  using E = EpiSmem<64, OUT_BUFS, RED, CASEB>;
   static constexpr int OFF_W = 0;                                   // [(cbg, dw)][group g = 2 - dh][64 co][64 ci], resident
   static constexpr int OFF_A = 9 * CBLK * WT_BYTES;
   static constexpr int OFF_EPI = OFF_A + A_STAGES * ROW_STRIDE;
@@ -70,9 +70,9 @@ struct RowWalk {
   }
 };
 
-template <int CBLK, int A_STAGES, int OUT_BUFS, int CASEB>
+template <int CBLK, int A_STAGES, int OUT_BUFS, int CASEB, int RED = 0>
 __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_rows_kernel(const __grid_constant__ Conv3Params p) {
-  using L = C3RSmem<CBLK, A_STAGES, OUT_BUFS, CASEB>;
+  using L = C3RSmem<CBLK, A_STAGES, OUT_BUFS, CASEB, RED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* afull = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_rows_kernel(const _
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
     tma_prefetch_desc(&p.o_map[0]);
+    if (RED) tma_prefetch_desc(&p.red_map);
     for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(&afull[s], 1);
       mbar_init(&aempty[s], 1);
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_rows_kernel(const _
     __syncwarp();
   } else {
     // ================= epilogue =================
-    Epilogue<64, OUT_BUFS, RW, 0, CASEB> epi(smem + L::OFF_EPI, p.ep, tmem_base, nullptr, nullptr, threadIdx.x - 64, warp);
+    Epilogue<64, OUT_BUFS, RW, RED, CASEB> epi(smem + L::OFF_EPI, p.ep, tmem_base, nullptr, nullptr, threadIdx.x - 64, warp);
+    epi.red_map = &p.red_map;
     epi.load_vectors(0);
     // all 512 accumulator columns start at zero: this warp's 32 lanes x its half of the columns
     const uint32_t lane_addr = tmem_base + ((uint32_t)(epi.quad * 32) << 16);
@@ -196,13 +198,19 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_rows_kernel(const _
     int rc = 0;
     RowWalk walk(p);
     int img, w0, hb, S;
-    while (walk.next(img, w0, hb, S)) {
+    bool more = walk.next(img, w0, hb, S);
+    while (more) {
+      RowWalk peek = walk;                                // the segment after this one (RED == 2 prefetches the next row's `a` tile)
+      int nimg = 0, nw0 = 0, nhb = 0, nS = 0;
+      const bool more_next = peek.next(nimg, nw0, nhb, nS);
       for (int j = 0; j < S; ++j) {
         const int r = rc + j;
         const int slot = r & (RING - 1);
         mbar_wait(&rfull[slot], (uint32_t)(r >> 3) & 1u);
         const int h = hb + j;
-        epi.tile(h, w0, [&](const uint8_t* blk, int) { tma_store_4d(&p.o_map[0], blk, 0, w0, h, img); }, slot * 64, false, false, 0, img);
+        const bool in_seg = j + 1 < S;
+        epi.tile(h, w0, [&](const uint8_t* blk, int) { tma_store_4d(&p.o_map[0], blk, 0, w0, h, img); }, slot * 64, false, false, 0, img,
+                 in_seg || more_next, in_seg ? h + 1 : nhb, in_seg ? w0 : nw0, in_seg ? img : nimg);
         // the accumulator has been read (tcgen05.wait::ld inside tile): zero it and hand the slot to output row r + 8
         tmem_st_zero_32x32(lane_addr + slot * 64 + epi.half * 32);
         tmem_st_wait();
@@ -211,6 +219,9 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_rows_kernel(const _
         if (lane == 0) mbar_arrive(&rempty[slot]);
       }
       rc += S;
+      walk = peek;
+      img = nimg; w0 = nw0; hb = nhb; S = nS;
+      more = more_next;
     }
     epi.finish(0, blockIdx.x);
   }
@@ -224,11 +235,11 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) conv3_rows_kernel(const _
 }
 
 // host side: p.o_base / p.o_ch, p.H, p.W, p.ep and p.fin are set by the entry points below
-template <int CBLK, int A_STAGES, int OUT_BUFS, int CASEB>
+template <int CBLK, int A_STAGES, int OUT_BUFS, int CASEB, int RED = 0>
 int launch_c3_rows(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img, cudaStream_t stream) {
-  using L = C3RSmem<CBLK, A_STAGES, OUT_BUFS, CASEB>;
+  using L = C3RSmem<CBLK, A_STAGES, OUT_BUFS, CASEB, RED>;
   static_assert(L::TOTAL <= 232448, "smem budget");
-  auto kern = conv3_rows_kernel<CBLK, A_STAGES, OUT_BUFS, CASEB>;
+  auto kern = conv3_rows_kernel<CBLK, A_STAGES, OUT_BUFS, CASEB, RED>;
   static bool attr_done = false;
   if (!attr_done) {
     UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -243,6 +254,9 @@ int launch_c3_rows(Conv3Params& p, const void* const* a_base, const int* a_ch, i
   if ((rc = ub_tmap_act4d(&p.o_map[0], p.o_base[0], p.o_ch[0], p.W, p.H, n_img, (long long)p.o_ch[0] * 2, (long long)p.W * p.o_ch[0] * 2,
                           (long long)p.H * p.W * p.o_ch[0] * 2, RW, 1)))
     return rc;
+  if (RED && (rc = ub_tmap_act4d(&p.red_map, p.red_base, p.ep.red_ncols, p.W, p.H, n_img, (long long)p.ep.red_ncols * 2,
+                                 (long long)p.W * p.ep.red_ncols * 2, (long long)p.H * p.W * p.ep.red_ncols * 2, RW, 1)))
+    return rc;
   p.strips_w = (p.W + RW - 1) / RW;         // a ragged last strip: loads zero-fill, stores clip, statistics mask (epilogue.cuh)
   const long long total = (long long)n_img * p.strips_w * p.H;
   UB_CHECK_SHAPE(total > 0 && total < (1ll << 30), "conv3 (rows): row count out of range");
@@ -256,6 +270,7 @@ int launch_c3_rows(Conv3Params& p, const void* const* a_base, const int* a_ch, i
   const bool fused = fin && p.ep.stats && epi_fin_bytes(p.ncols) <= OUT_BUFS * L::E::OUT_BYTES;
   if (fused) epi_set_fin(p.ep, *fin, (int)grid);
   else if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  if (RED) UB_CUDA(cudaMemsetAsync(p.ep.red_out, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ep.red_ncols, stream));
   kern<<<(int)grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);
   UB_LAUNCH_CHECK();
   if (fin && !fused)

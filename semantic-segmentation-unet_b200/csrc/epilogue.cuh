@@ -112,16 +112,15 @@ struct Epilogue {
   int as = 0, buf = 0;
   uint32_t aphase = 0;
   bool post;
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;      // RED: sums of this thread's column pair
-  float ss[8] = {}, qq[8] = {};                       // forward statistics: sum / sum of squares of this thread's 8 columns
+  // forward statistics: sum / sum of squares of this thread's 8 columns; RED: sum dy / sum dy * (a - mean) of the same 8 columns
+  float ss[8] = {}, qq[8] = {};
   // RED state
   const CUtensorMap* red_map = nullptr;
   int red_nt = 0;            // this CTA's n_tile
-  float m0 = 0.f, m1 = 0.f;  // mean of this thread's column pair
   uint32_t red_phase0 = 0, red_phase1 = 0;
   int red_cur = 0;           // buffer holding the current part's `a` tile
   bool red_primed = false;
-  bool red_mine = false;     // this thread's column pair belongs to the BatchNorm'd tensor
+  bool red_mine = false;     // this thread's 8 columns belong to the BatchNorm'd tensor
   int pair_rank = -1;        // >= 0: this CTA is rank `pair_rank` of a cta_group::2 pair (igemm_conv3_2cta.cu)
 
   // epi_thread: 0 .. EPI_THREADS-1; hw_warp: warp index within the CTA (a warp may only touch TMEM lanes 32 * (hw_warp % 4) .. +31)
@@ -153,12 +152,13 @@ struct Epilogue {
     }
     if (RED) {
       red_nt = n_tile;
-      const int c = 2 * (et % PAIRS);
+      const int c = 8 * (et % ST_CHUNKS);
       const int gcol = n_tile * BLOCK_N + c - ep.red_blk_begin * 64;
-      red_mine = gcol >= 0 && gcol < ep.red_ncols;
-      if (red_mine) {
-        m0 = ep.red_mean[gcol];
-        m1 = ep.red_mean[gcol + 1];
+      red_mine = gcol >= 0 && gcol < ep.red_ncols;          // whole 64-column blocks belong to the tensor or do not
+      // the column means sit in the (otherwise unused: a dgrad has no bias) bias slots of the vector area
+      for (int cc = et; cc < BLOCK_N; cc += EPI_THREADS) {
+        const int g = n_tile * BLOCK_N + cc - ep.red_blk_begin * 64;
+        v[cc] = (g >= 0 && g < ep.red_ncols) ? ep.red_mean[g] : 0.f;
       }
       if (et == 0) {
         mbar_init(abar(0), 1);
@@ -318,27 +318,38 @@ struct Epilogue {
           red_phase1 ^= 1;
         }
         if (red_mine) {
-          const int pair = et % PAIRS, grp = et / PAIRS;
-          const int c = 2 * pair;
-          const uint32_t off0 = (c >> 6) * EPI_OUT_BLK + ((c & 7) << 1);
+          // thread = (16-byte chunk, row group) as for the forward statistics; dy from the staging tile, `a` from its TMA'd tile
+          const int ck = et % ST_CHUNKS, grp = et / ST_CHUNKS;
+          const uint32_t off0 = (ck >> 3) * EPI_OUT_BLK;
           const uint32_t dybase = smem_u32(out_stage) + off0;
           const uint32_t abase = smem_u32(base + S::OFF_ABUF + red_cur * S::OUT_BYTES) + off0;
-          const int c16 = (c & 63) >> 3;
-          const int r_begin = grp * ROWS_PER_GROUP;
-#pragma unroll 8
-          for (int rr = 0; rr < ROWS_PER_GROUP; ++rr) {
-            const int r_ = r_begin + rr;
-            if ((h0 + r_ / TILE_W_ < ep.H) && (w0 + r_ % TILE_W_ < ep.W)) {   // warp-uniform
+          const int c16 = ck & 7;
+          const float4 mlo = *reinterpret_cast<const float4*>(vec() + ck * 8), mhi = *reinterpret_cast<const float4*>(vec() + ck * 8 + 4);
+          const float rm[8] = {mlo.x, mlo.y, mlo.z, mlo.w, mhi.x, mhi.y, mhi.z, mhi.w};
+#pragma unroll
+          for (int rb = 0; rb < ST_ROWS; rb += 2) {
+            uint32_t u[2][4], v[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int r_ = (rb + i) * ST_GROUPS + grp;
               const uint32_t o = r_ * 128 + ((c16 ^ (r_ & 7)) << 4);
-              uint32_t u, v;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(u) : "r"(dybase + o));
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(abase + o));
-              const float d0 = __uint_as_float(u << 16), d1 = __uint_as_float(u & 0xffff0000u);
-              const float a0 = __uint_as_float(v << 16), a1 = __uint_as_float(v & 0xffff0000u);
-              s0 += d0;
-              s1 += d1;
-              q0 = fmaf(d0, a0 - m0, q0);
-              q1 = fmaf(d1, a1 - m1, q1);
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u[i][0]), "=r"(u[i][1]), "=r"(u[i][2]), "=r"(u[i][3]) : "r"(dybase + o));
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]) : "r"(abase + o));
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int r_ = (rb + i) * ST_GROUPS + grp;
+              if ((h0 + r_ / TILE_W_ < ep.H) && (w0 + r_ % TILE_W_ < ep.W)) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float d0 = __uint_as_float(u[i][k] << 16), d1 = __uint_as_float(u[i][k] & 0xffff0000u);
+                  const float a0 = __uint_as_float(v[i][k] << 16), a1 = __uint_as_float(v[i][k] & 0xffff0000u);
+                  ss[2 * k] += d0;
+                  ss[2 * k + 1] += d1;
+                  qq[2 * k] = fmaf(d0, a0 - rm[2 * k], qq[2 * k]);
+                  qq[2 * k + 1] = fmaf(d1, a1 - rm[2 * k + 1], qq[2 * k + 1]);
+                }
+              }
             }
           }
         }
@@ -356,13 +367,14 @@ struct Epilogue {
   __device__ __forceinline__ void finish(int n_tile, int stats_row) {
     if (et == 0) tma_store_wait_all0();
     if (RED) {
-      float* st = reinterpret_cast<float*>(base + S::OFF_STAT);     // [ROW_GROUPS][2][BLOCK_N]
-      const int pair = et % PAIRS, grp = et / PAIRS;
+      float* st = reinterpret_cast<float*>(base + S::OFF_STAT);     // [ST_GROUPS][2][BLOCK_N]
+      const int ck = et % ST_CHUNKS, grp = et / ST_CHUNKS;
       named_bar_sync(1, EPI_THREADS);
-      st[(grp * 2 + 0) * BLOCK_N + 2 * pair] = s0;
-      st[(grp * 2 + 0) * BLOCK_N + 2 * pair + 1] = s1;
-      st[(grp * 2 + 1) * BLOCK_N + 2 * pair] = q0;
-      st[(grp * 2 + 1) * BLOCK_N + 2 * pair + 1] = q1;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        st[(grp * 2 + 0) * BLOCK_N + ck * 8 + k] = ss[k];
+        st[(grp * 2 + 1) * BLOCK_N + ck * 8 + k] = qq[k];
+      }
       named_bar_sync(1, EPI_THREADS);
       for (int i = et; i < 2 * BLOCK_N; i += EPI_THREADS) {
         const int which = i / BLOCK_N, c = i % BLOCK_N;
@@ -370,7 +382,7 @@ struct Epilogue {
         if (gcol < 0 || gcol >= ep.red_ncols) continue;
         float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < ROW_GROUPS; ++g) t += st[(g * 2 + which) * BLOCK_N + c];
+        for (int g = 0; g < ST_GROUPS; ++g) t += st[(g * 2 + which) * BLOCK_N + c];
         if (which) t *= ep.red_rstd[gcol];
         ep.red_out[((size_t)stats_row * 2 + which) * ep.red_ncols + gcol] = t;
       }

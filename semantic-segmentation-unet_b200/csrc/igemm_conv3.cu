@@ -58,6 +58,7 @@ struct Conv3Params {
   const BnFin* fin;          // host-side only: BatchNorm to finalise in the last CTA (forward with statistics), or null
   const void* o_base[2];     // host-side only: output tensors behind o_map (the row-streaming kernel rebuilds the maps with its own box)
   int o_ch[2];
+  const void* red_base;      // host-side only: tensor behind red_map
   int rows_total, strips_w;  // conv3_rows.cuh: row units (image, 128-pixel strip, row) of the launch; strips per image row
 };
 
@@ -606,6 +607,8 @@ int launch(Conv3Params& p, const void* const* a_base, const int* a_ch, int n_img
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.cblk_total > 0, "conv3: columns must be a multiple of 64");
   p.ep.ncols = p.ncols;
   p.ep.bias_mod = p.ncols;
+  if (use_rows() >= 1 && p.ncols == 64 && p.ep.red_out && p.o_ch[0] == 64 && p.ep.red_ncols == 64 && p.cblk_total == 1 && rows_width_ok(p.W))
+    return launch_c3_rows<1, 4, 2, 0, 2>(p, a_base, a_ch, n_img, stream);      // 64 -> 64 dgrad with the fused BatchNorm-backward reduction
   if (use_rows() >= 1 && p.ncols == 64 && !p.ep.red_out && p.o_ch[0] == 64 && rows_width_ok(p.W)) {
     // 64 output channels and rows that fill their 128-pixel strips (level 1 at the benchmark shapes, the 1216-pixel inference tiles): the
     // row-streaming kernel (conv3_rows.cuh)
@@ -744,6 +747,7 @@ int ub_conv3_halo_dgrad(const void* dz, int Cout, const void* w_t, void* dx0, in
     // the BatchNorm'd tensor is the LAST output (dx1 of a concat dgrad, else dx0)
     const int cred = C1 > 0 ? C1 : C0;
     if ((rc = out_map(&p.red_map, red_a, cred, W, H, N))) return rc;
+    p.red_base = red_a;
     p.ep.red_mean = red_mean;
     p.ep.red_rstd = red_rstd;
     p.ep.red_out = red_partial;

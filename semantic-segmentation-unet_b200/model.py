@@ -81,6 +81,8 @@ class UNet:
         self._graphs = {}
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
+        # ... also for the 64 -> 64 layers (enc1b -> enc1a, dec1b -> dec1a), whose dgrad is the row-streaming kernel (csrc/conv3_rows.cuh)
+        self.fuse_bn_reduce_64 = os.environ.get("UB_FUSE_RED64", "0") == "1"
         # bf16 folded path, optional (UB_BN_ALGEBRA=1): dbeta / dgamma of a BatchNorm whose only consumer is a folded convolution come from that
         # convolution's weight gradient and border sums (ub_bn_bwd_sums_wgrad) instead of a reduction pass over the gradient tensor.  Parity
         # green and 4.3 GB less HBM traffic per step, but the BatchNorm backward of layer L then has to wait for the weight gradient of layer
@@ -863,9 +865,10 @@ class UNet:
             ws = self._b("wgrad_ws")
             if not self.overlap_wgrad:
                 wgrad()
-            # worth it only where the K loop is long enough to hide the longer epilogue (measured: 64-output-channel layers,
-            # whose dgrad has a single 64-channel K block, lose more in the dgrad than the separate reduction pass costs)
-            if dx0 is not None and red is not None and self.fuse_bn_reduce and L.cout >= 128 and not any(p is red for p, _ in algebra):
+            # worth it where the K loop is long enough to hide the longer epilogue: layers with >= 128 output channels, and (optional,
+            # UB_FUSE_RED64) the 64 -> 64 layers through the row-streaming kernel
+            wide = L.cout >= 128 or (self.fuse_bn_reduce_64 and L.cout == 64 and L.cin == 64)
+            if dx0 is not None and red is not None and self.fuse_bn_reduce and wide and not any(p is red for p, _ in algebra):
                 rm, rr = self._bn_vectors(red, True)
                 self._call("ub_conv3x3_dgrad_bnred", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w, self._b("a:" + red.name), rm, rr,
                            self.partial_red)

@@ -1239,4 +1239,7 @@ CASES = {
     "rows_fwd_bn_cases_ragged": lambda: case_conv_fwd_bn(64, 0, 64, N=2, H=10, W=360, cases=True, seed=100),
     "rows_fwd_cat_ragged": lambda: case_conv3x3_fwd(64, 64, 64, N=1, H=5, W=1000, seed=101),
     "rows_dgrad_ragged": lambda: case_conv3x3_dgrad(64, 64, 0, N=1, H=17, W=360, seed=102),
+    "rows_dgrad_bnred_64_64": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=2, H=13, W=256, seed=103),
+    "rows_dgrad_bnred_tall": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=1, H=150, W=128, seed=104),
+    "rows_dgrad_bnred_ragged": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=1, H=9, W=360, seed=105),
 }
