@@ -82,7 +82,8 @@ class UNet:
         self._lr_ring = None
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
         # ... also for the 64 -> 64 layers (enc1b -> enc1a, dec1b -> dec1a), whose dgrad is the row-streaming kernel (csrc/conv3_rows.cuh)
-        self.fuse_bn_reduce_64 = os.environ.get("UB_FUSE_RED64", "0") == "1"
+        # (on by default: 21.81 -> 21.59 ms per step, profiles/r02_ab_runs.md block P; UB_FUSE_RED64=0 restores the separate reduction pass)
+        self.fuse_bn_reduce_64 = os.environ.get("UB_FUSE_RED64", "1") == "1"
         # bf16 folded path, optional (UB_BN_ALGEBRA=1): dbeta / dgamma of a BatchNorm whose only consumer is a folded convolution come from that
         # convolution's weight gradient and border sums (ub_bn_bwd_sums_wgrad) instead of a reduction pass over the gradient tensor.  Parity
         # green and 4.3 GB less HBM traffic per step, but the BatchNorm backward of layer L then has to wait for the weight gradient of layer
