@@ -74,7 +74,7 @@ def step_flops(batch=None, **kw):
     return batch * fwd, batch * train, fam
 
 
-FAMILY = {"ub_conv3x3_fwd": "igemm_fwd", "ub_conv3x3_fwd_cases": "igemm_fwd", "ub_conv3x3_fwd_bn": "igemm_fwd", "ub_deconv2x2_fwd_bn": "igemm_fwd", "ub_conv3x3_dgrad": "igemm_fwd", "ub_conv3x3_dgrad_bnred": "igemm_fwd", "ub_deconv2x2_fwd": "igemm_fwd", "ub_deconv2x2_dgrad": "igemm_fwd",
+FAMILY = {"ub_conv3x3_fwd": "igemm_fwd", "ub_conv3x3_fwd_cases": "igemm_fwd", "ub_conv3x3_fwd_bn": "igemm_fwd", "ub_deconv2x2_fwd_bn": "igemm_fwd", "ub_conv3x3_dgrad": "igemm_fwd", "ub_conv3x3_dgrad_bnred": "igemm_fwd", "ub_deconv2x2_fwd": "igemm_fwd", "ub_deconv2x2_dgrad": "igemm_fwd", "ub_deconv2x2_dgrad_bnred": "igemm_fwd",
           "ub_conv3x3_wgrad": "igemm_wgrad", "ub_deconv2x2_wgrad": "igemm_wgrad"}
 
 
@@ -349,28 +349,45 @@ def run_cuda(args):
     clocks = sampler.stop() if rank == 0 else None
     final_loss = float(model.metrics[0].item())
 
-    # ---- end-to-end arm: pinned host -> device copies and the loss read-back inside the timed region
-    dxe = torch.empty_like(dx[0])
-    dle = torch.empty_like(dl[0])
-    for i in range(2):
-        dxe.copy_(hx[i % nb], non_blocking=True)
-        dle.copy_(hl[i % nb], non_blocking=True)
-        float(model.train_step(dxe, dle).item())
+    # ---- end-to-end arm: pinned host -> device copies and the loss read-back inside the timed region, through the package's public
+    # host pipeline (unetb200.train.StepPipeline: the upload of batch i + 1 overlaps step i, the loss of step i is read while step
+    # i + 1 runs -- every batch is copied and every loss reaches the host inside the timed region)
+    from unetb200.train import StepPipeline
+    pipe = StepPipeline(model)
+    for i in range(3):
+        pipe.feed(hx[i % nb], hl[i % nb])
+    pipe.flush()
     sync_all()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
+    host_losses = []
     for i in range(args.steps):
-        dxe.copy_(hx[i % nb], non_blocking=True)
-        dle.copy_(hl[i % nb], non_blocking=True)
-        loss = model.train_step(dxe, dle)
-        float(loss.item())                      # device -> host read of the step's loss
+        v = pipe.feed(hx[i % nb], hl[i % nb])
+        if v is not None:
+            host_losses.append(v)
+    host_losses += pipe.flush()                  # runs the last uploaded batch and reads the outstanding losses
     t1.record()
     sync_all()
+    assert len(host_losses) == args.steps, (len(host_losses), args.steps)
     ms_e = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if dp:
         ms_e = dp.reduce_max(ms_e)
     ms_e2e = float(ms_e.item())
+
+    # the same without the pipeline (copy, step, blocking loss read in sequence): what the copies and the read-back cost when exposed
+    dxe = torch.empty_like(dx[0])
+    dle = torch.empty_like(dl[0])
+    ns = max(1, min(args.steps, 10))
+    sync_all()
+    t0.record()
+    for i in range(ns):
+        dxe.copy_(hx[i % nb], non_blocking=True)
+        dle.copy_(hl[i % nb], non_blocking=True)
+        float(model.train_step(dxe, dle).item())
+    t1.record()
+    sync_all()
+    ms_serial = t0.elapsed_time(t1) / ns
 
     # ---- per-kernel-family timing (extra steps after the timed region, CUDA events around every launch)
     fam_ms, kern_ms = {}, {}
@@ -451,8 +468,9 @@ def run_cuda(args):
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "image": [CH, HW, HW], "classes": CLASSES,
                    "parallelism": f"dp{world}", "l2": "per-step working set (>10 GB of activations) far exceeds the 126 MB L2; 4 rotating input batches",
                    "lr": "3e-5 (warm-up epoch lr/10, train.py:129)", "dropout": "on (Philox)"},
-        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(hx[0].numel() * 4 + hl[0].numel()), "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(hx[0].numel() * 4 + hl[0].numel()), "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / args.steps, "api": "unetb200.train.StepPipeline (one batch of look-ahead, loss read one step behind)",
+                "serial_ms_per_step": ms_serial},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv3_pair_kernel / conv3_kernel (the 17 conv3x3 forward launches)", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",

@@ -85,6 +85,11 @@ int ub_deconv2x2_fwd_bn(const void* x, int Cin, const void* w, const float* bias
                         unsigned int* counter, cudaStream_t stream);
 int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int w_in,
                        cudaStream_t stream);
+/* ... fused with the backward reduction of the BatchNormalization in front of the up-sampling (the conv block whose output the
+ * transposed convolution reads, UNet/model.py:97-131): partial[UB_STATS_ROWS][2][Cin] = {sum dy, rstd * sum dy * (a - mean)} over the
+ * dx it writes, as ub_conv3x3_dgrad_bnred does -- replaces ub_bn_bwd_reduce for that layer. */
+int ub_deconv2x2_dgrad_bnred(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int w_in, const void* a,
+                             const float* mean, const float* rstd, float* partial, cudaStream_t stream);
 long long ub_deconv2x2_wgrad_workspace_bytes(int Cin, int Cout, int N, int h, int w_in);
 int ub_deconv2x2_wgrad(const void* x, int Cin, const void* dz, int Cout, float* dw, void* workspace,
                        long long workspace_bytes, int N, int h, int w_in, cudaStream_t stream);

@@ -30,6 +30,7 @@ struct IgemmFwdParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
   CUtensorMap o_map[4];
+  CUtensorMap red_map;  // RED: saved activation `a` of the BatchNorm'd tensor whose gradient a dgrad writes (epilogue.cuh)
   int nsrc;
   int cblk[4];       // 64-channel blocks per source
   int ntaps;
@@ -46,9 +47,9 @@ struct IgemmFwdParams {
   const BnFin* fin;   // host-side only: BatchNorm to finalise in the last CTA (forward with statistics), or null
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int RED = 0>
 struct SmemLayout {
-  using E = EpiSmem<BLOCK_N, 1>;
+  using E = EpiSmem<BLOCK_N, 1, RED>;
   static constexpr int B_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
@@ -57,9 +58,9 @@ struct SmemLayout {
   static constexpr int TOTAL = OFF_TMEM + 16 + 1024;            // + alignment slack
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int RED = 0>
 __global__ void __launch_bounds__(64 + EPI_THREADS, 1) igemm_fwd_kernel(const __grid_constant__ IgemmFwdParams p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, RED>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) igemm_fwd_kernel(const __
     for (int i = 0; i < p.nsrc; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
     tma_prefetch_desc(&p.o_map[0]);
+    if (RED) tma_prefetch_desc(&p.red_map);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -155,7 +157,8 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) igemm_fwd_kernel(const __
     // ================= epilogue (8 warps, epilogue.cuh) =================
     // host guarantees gridDim.x % n_tiles == 0, so this CTA's n_tile never changes
     const int n_tile = blockIdx.x % p.n_tiles;
-    Epilogue<BLOCK_N, 1, TILE_W> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    Epilogue<BLOCK_N, 1, TILE_W, RED> epi(smem + L::OFF_EPI, p.ep, tmem_base, tfull, tempty, threadIdx.x - 64, warp);
+    epi.red_map = &p.red_map;
     epi.load_vectors(n_tile);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(64 + EPI_THREADS, 1) igemm_fwd_kernel(const __
         const int j = n_tile * (BLOCK_N / 64) + b;
         const int map = j / p.blocks_per_omap;
         tma_store_4d(&p.o_map[map], blk, (j - map * p.blocks_per_omap) * 64, w0, h0, img);
-      });
+      }, 0, true, true, BLOCK_N, img);
     }
     epi.finish(n_tile, blockIdx.x / p.n_tiles);
   }
@@ -189,11 +192,11 @@ struct IgemmFwdLaunch {
   int ncols;
 };
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int RED = 0>
 int launch_t(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, RED>;
   static_assert(L::TOTAL <= 232448, "smem budget");
-  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES>;
+  auto kern = igemm_fwd_kernel<BLOCK_N, STAGES, RED>;
   static bool attr_done = false;
   if (!attr_done) {
     UB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -216,6 +219,7 @@ int launch_t(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
   const bool fused = fin && p.ep.stats && epi_fin_bytes(p.ncols) <= L::E::OUT_BYTES;
   if (fused) epi_set_fin(p.ep, *fin, grid / p.n_tiles);
   else if (p.ep.stats) UB_CUDA(cudaMemsetAsync(p.ep.stats, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ncols, stream));
+  if (RED) UB_CUDA(cudaMemsetAsync(p.ep.red_out, 0, sizeof(float) * UB_STATS_ROWS * 2 * p.ep.red_ncols, stream));
   kern<<<grid, 64 + EPI_THREADS, L::TOTAL, stream>>>(p);
   UB_LAUNCH_CHECK();
   if (fin && !fused)
@@ -232,6 +236,10 @@ int launch(IgemmFwdParams& p, int n_img, cudaStream_t stream) {
   p.ep.H = p.H;
   p.ep.W = p.W;
   UB_CHECK_SHAPE(p.ncols % 64 == 0 && p.num_kb > 0, "igemm: columns must be a multiple of 64");
+  if (p.ep.red_out) {          // a dgrad that also accumulates the BatchNorm-backward sums of the tensor it writes: room for the `a` tile
+    if (p.ncols % 128 == 0) return launch_t<128, 4, 1>(p, n_img, stream);
+    return launch_t<64, 8, 1>(p, n_img, stream);
+  }
   if (p.ncols % 256 == 0) return launch_t<256, 3>(p, n_img, stream);
   if (p.ncols % 128 == 0) return launch_t<128, 5>(p, n_img, stream);
   return launch_t<64, 8>(p, n_img, stream);
@@ -449,13 +457,21 @@ static int deconv_fwd_impl(const void* x, int Cin, const void* w, const float* b
   return launch(p, N, stream);
 }
 
-int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int wd,
-                       cudaStream_t stream) {
+static int deconv_dgrad_impl(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int wd, const void* red_a,
+                             const float* red_mean, const float* red_rstd, float* red_partial, cudaStream_t stream) {
   UB_CHECK_ARG(dz && w_t && dx, "deconv2x2_dgrad: null pointer");
   UB_CHECK_SHAPE(Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "deconv2x2_dgrad: channels must be multiples of 64");
   IgemmFwdParams p;
   memset(&p, 0, sizeof(p));
   int rc;
+  if (red_partial) {
+    if ((rc = dense_map(&p.red_map, red_a, Cin, wd, h, N))) return rc;
+    p.ep.red_mean = red_mean;
+    p.ep.red_rstd = red_rstd;
+    p.ep.red_out = red_partial;
+    p.ep.red_blk_begin = 0;
+    p.ep.red_ncols = Cin;
+  }
   for (int ab = 0; ab < 4; ++ab) {
     if ((rc = strided_map(&p.a_map[ab], dz, Cout, wd, h, N, ab >> 1, ab & 1))) return rc;
     p.cblk[ab] = Cout / 64;
@@ -473,6 +489,19 @@ int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int 
   p.ep.stats = nullptr;
   p.ncols = Cin;
   return launch(p, N, stream);
+}
+
+int ub_deconv2x2_dgrad(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int wd, cudaStream_t stream) {
+  return deconv_dgrad_impl(dz, Cout, w_t, dx, Cin, N, h, wd, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+/* transposed-convolution dgrad fused with the backward-BatchNorm reduction of the tensor whose gradient it writes (the conv block in front
+ * of the up-sampling, UNet/model.py:97-131): partial[UB_STATS_ROWS][2][Cin] = {sum dy, rstd * sum dy * (a - mean)} -- replaces
+ * ub_bn_bwd_reduce for that layer */
+int ub_deconv2x2_dgrad_bnred(const void* dz, int Cout, const void* w_t, void* dx, int Cin, int N, int h, int wd, const void* a,
+                             const float* mean, const float* rstd, float* partial, cudaStream_t stream) {
+  UB_CHECK_ARG(a && mean && rstd && partial, "deconv2x2_dgrad_bnred: null pointer");
+  return deconv_dgrad_impl(dz, Cout, w_t, dx, Cin, N, h, wd, a, mean, rstd, partial, stream);
 }
 
 }  // extern "C"

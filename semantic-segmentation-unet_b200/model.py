@@ -83,7 +83,10 @@ class UNet:
         self.fuse_bn_reduce = True        # bf16 path: BatchNorm-backward sums in the producing dgrad's epilogue
         # ... also for the 64 -> 64 layers (enc1b -> enc1a, dec1b -> dec1a), whose dgrad is the row-streaming kernel (csrc/conv3_rows.cuh)
         # (on by default: 21.81 -> 21.59 ms per step, profiles/r02_ab_runs.md block P; UB_FUSE_RED64=0 restores the separate reduction pass)
-        self.fuse_bn_reduce_64 = os.environ.get("UB_FUSE_RED64", "1") == "1"
+        # ... and in the transposed-convolution dgrads, for dec2b / dec3b / dec4b (botb sits behind a dropout backward): UB_FUSE_RED_DECONV
+        self.fuse_bn_reduce_deconv = os.environ.get("UB_FUSE_RED_DECONV", "0") == "1"
+        # 2: also the dgrad of dec1a (64 -> 64 + 64, the pair kernel), which carries the sums of up1
+        self.fuse_bn_reduce_64 = int(os.environ.get("UB_FUSE_RED64", "1"))
         # bf16 folded path, optional (UB_BN_ALGEBRA=1): dbeta / dgamma of a BatchNorm whose only consumer is a folded convolution come from that
         # convolution's weight gradient and border sums (ub_bn_bwd_sums_wgrad) instead of a reduction pass over the gradient tensor.  Parity
         # green and 4.3 GB less HBM traffic per step, but the BatchNorm backward of layer L then has to wait for the weight gradient of layer
@@ -868,7 +871,7 @@ class UNet:
                 wgrad()
             # worth it where the K loop is long enough to hide the longer epilogue: layers with >= 128 output channels, and (optional,
             # UB_FUSE_RED64) the 64 -> 64 layers through the row-streaming kernel
-            wide = L.cout >= 128 or (self.fuse_bn_reduce_64 and L.cout == 64 and L.cin == 64)
+            wide = L.cout >= 128 or (L.cout == 64 and (self.fuse_bn_reduce_64 >= 2 or (self.fuse_bn_reduce_64 == 1 and L.cin == 64)))
             if dx0 is not None and red is not None and self.fuse_bn_reduce and wide and not any(p is red for p, _ in algebra):
                 rm, rr = self._bn_vectors(red, True)
                 self._call("ub_conv3x3_dgrad_bnred", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w, self._b("a:" + red.name), rm, rr,
@@ -951,7 +954,13 @@ class UNet:
                 ws = self._b("wgrad_ws")
                 if not self.overlap_wgrad:
                     self._call("ub_deconv2x2_wgrad", xin, Lu.cin, dz, Lu.cout, dw, ws, ws.numel(), N, hi, wi)
-                self._call("ub_deconv2x2_dgrad", dz, Lu.cout, self.WT[Lu.name], self._b("g:" + prev.name), Lu.cin, N, hi, wi)
+                if self.fuse_bn_reduce and self.fuse_bn_reduce_deconv and lvl < 4 and not infer:
+                    rm, rr = self._bn_vectors(prev, True)
+                    self._call("ub_deconv2x2_dgrad_bnred", dz, Lu.cout, self.WT[Lu.name], self._b("g:" + prev.name), Lu.cin, N, hi, wi,
+                               self._b("a:" + prev.name), rm, rr, self.partial_red)
+                    self._red_ready = prev.name
+                else:
+                    self._call("ub_deconv2x2_dgrad", dz, Lu.cout, self.WT[Lu.name], self._b("g:" + prev.name), Lu.cin, N, hi, wi)
                 if self.overlap_wgrad:
                     with torch.cuda.stream(self._fork_side()):
                         self._call("ub_deconv2x2_wgrad", xin, Lu.cin, dz, Lu.cout, dw, ws, ws.numel(), N, hi, wi)

@@ -25,6 +25,89 @@ import time
 import numpy as np
 
 
+class StepPipeline:
+    """Training steps fed from PINNED HOST batches without stalling the device: the upload of batch i + 1 runs on a copy stream while
+    step i computes, and the loss of step i is read back while step i + 1 runs (the reference hides both behind
+    `dataset.prefetch` and TensorFlow's asynchronous metrics, UNet/train.py:85, :140-146).  Every batch is still copied host -> device
+    and every step's loss still reaches the host; only their latency leaves the critical path.  One batch of look-ahead, two device
+    slots (a slot is rewritten only after the step that consumed it has finished).
+
+        pipe = StepPipeline(unet)
+        for images, labels in batches:            # pinned float32 [B, C, H, W] images, uint8 [B, H, W] (or one-hot int32) labels
+            loss = pipe.feed(images, labels)      # python float of the step BEFORE the one just launched, None at the start
+        losses_tail = pipe.flush()                # runs the last uploaded batch; returns the losses not yet handed out
+    """
+
+    def __init__(self, unet):
+        import torch
+        self.torch = torch
+        self.m = unet
+        self.dev = unet.device
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.slots = [None, None]
+        self.step_done = [None, None]
+        self.k = 0
+        self.ready = None           # (x, labels, upload-done event, slot) of the batch waiting for its step
+        self.pending = None         # (pinned loss, event) of the last launched step
+
+    def _upload(self, images, labels):
+        torch = self.torch
+        k = self.k
+        self.k ^= 1
+        slot = self.slots[k]
+        if slot is None or slot[0].shape != images.shape or slot[0].dtype != images.dtype or slot[1].shape != labels.shape \
+                or slot[1].dtype != labels.dtype:
+            slot = (torch.empty(images.shape, dtype=images.dtype, device=self.dev), torch.empty(labels.shape, dtype=labels.dtype, device=self.dev))
+            self.slots[k] = slot
+        if self.step_done[k] is not None:
+            self.copy_stream.wait_event(self.step_done[k])
+        with torch.cuda.stream(self.copy_stream):
+            slot[0].copy_(images, non_blocking=True)
+            slot[1].copy_(labels, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return slot[0], slot[1], ev, k
+
+    def _run(self, item):
+        torch = self.torch
+        x, lab, ev, k = item
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        self.m.train_step(x, lab)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self.step_done[k] = done
+        prev = self.pending
+        vals = torch.empty(2, dtype=torch.float32, pin_memory=True)
+        vals.copy_(self.m.metrics[:2], non_blocking=True)          # ordered on the step's stream, before the next step overwrites it
+        got = torch.cuda.Event()
+        got.record(cur)
+        self.pending = (vals, got)
+        if prev is None:
+            return None
+        prev[1].synchronize()                                      # the host runs at most one step ahead of the device
+        return float(prev[0][0])
+
+    def feed(self, images, labels):
+        nxt = self._upload(images, labels)
+        out = self._run(self.ready) if self.ready is not None else None
+        self.ready = nxt
+        return out
+
+    def flush(self):
+        out = []
+        if self.ready is not None:
+            v = self._run(self.ready)
+            self.ready = None
+            if v is not None:
+                out.append(v)
+        if self.pending is not None:
+            self.pending[1].synchronize()
+            out.append(float(self.pending[0][0]))
+            self.pending = None
+        return out
+
+
 class _Mean:
     """stand-in for tf.keras.metrics.Mean / CategoricalAccuracy as UNet/train.py:104-107 uses them: the step hands it
     a 0-d device tensor; values are accumulated on the device and read only by result()"""

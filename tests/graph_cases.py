@@ -704,6 +704,37 @@ def case_graph_two_shapes():
     return r
 
 
+def case_step_pipeline(steps=6):
+    """unetb200.train.StepPipeline (pinned host batches, upload one batch ahead on a copy stream, loss read one step behind) gives the
+    losses of the same steps run one by one with blocking copies -- same kernels, same order, bit for bit -- and hands out exactly one
+    loss per batch"""
+    import torch
+    from unetb200.model import UNet
+    from unetb200.train import StepPipeline
+    rng = np.random.default_rng(5)
+    xs = [torch.from_numpy(rng.normal(size=(2, 1, 64, 64)).astype(np.float32)).pin_memory() for _ in range(3)]
+    ls = [torch.from_numpy(rng.integers(0, 2, size=(2, 64, 64)).astype(np.uint8)).pin_memory() for _ in range(3)]
+    out = {}
+    for mode in ("plain", "pipe"):
+        m = UNet(2, 2, 1, learning_rate=1e-3, precision="bf16", seed=7)
+        if mode == "plain":
+            out[mode] = [float(m.train_step(xs[i % 3].cuda(), ls[i % 3].cuda()).item()) for i in range(steps)]
+        else:
+            pipe = StepPipeline(m)
+            got = []
+            for i in range(steps):
+                v = pipe.feed(xs[i % 3], ls[i % 3])
+                if v is not None:
+                    got.append(v)
+            got += pipe.flush()
+            out[mode] = got
+        out[mode + "_p"] = m.P.clone()
+    r = dict(n_plain=len(out["plain"]), n_pipe=len(out["pipe"]), losses_equal=out["plain"] == out["pipe"],
+             params_bit_identical=bool(torch.equal(out["plain_p"], out["pipe_p"])), finite=bool(np.isfinite(out["pipe"]).all()))
+    r["ok"] = bool(r["n_pipe"] == steps and r["losses_equal"] and r["params_bit_identical"] and r["finite"])
+    return r
+
+
 def _with_env(fn, **env):
     """run a graph case with environment switches of unetb200.model.UNet set (e.g. UB_BN_ALGEBRA="1")"""
     def run():
@@ -806,6 +837,8 @@ CASES = {
     "algebra_wellcond_bf16_n2_256": _with_env(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256), UB_BN_ALGEBRA="1"),
     "algebra_curve_bf16": _with_env(lambda: case_curve("bf16", steps=100), UB_BN_ALGEBRA="1"),
     "nofold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=100)),
+    "step_pipeline": case_step_pipeline,
+    "reddeconv_wellcond_bf16_n2_256": _with_env(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256), UB_FUSE_RED_DECONV="1", UB_FUSE_RED64="2"),
     # BatchNorm-backward sums of enc1a / dec1a inside the 64 -> 64 row-streaming dgrads (csrc/conv3_rows.cuh, RED = 2) are the default;
     # the separate reduction pass stays covered
     "nored64_wellcond_bf16_n2_256": _with_env(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256), UB_FUSE_RED64="0"),

@@ -203,6 +203,36 @@ def case_deconv_bwd(Cin=128, Cout=64, N=2, h=12, w=20, seed=4):
     return dict(err_dx=e1, err_dw=e2, ok=bool(e1 < 1e-2 and e2 < 1e-3))
 
 
+def case_deconv_dgrad_bnred(Cin=128, Cout=64, N=2, h=12, w=20, seed=14):
+    """ub_deconv2x2_dgrad_bnred: the dgrad of the plain entry point plus the BatchNorm-backward sums of the tensor it writes"""
+    C = _C()
+    rng = np.random.default_rng(seed)
+    wt = bf16_round(rng.normal(size=(2, 2, Cout, Cin)) / np.sqrt(Cout))
+    dz = bf16_round(rng.normal(size=(N, 2 * h, 2 * w, Cout)))
+    a = bf16_round(np.maximum(rng.normal(0.3, 1.0, size=(N, h, w, Cin)), 0))
+    mean = a.mean((0, 1, 2)).astype(np.float32)
+    rstd = (1.0 / np.sqrt(a.var((0, 1, 2)) + 1e-3)).astype(np.float32)
+    dx_ref, _, _ = ON.deconv_bwd(a, dz, wt)
+    wp = dev(pack_deconv(wt), torch.float32)
+    w_t = torch.empty(Cin * 4 * Cout, dtype=torch.bfloat16, device="cuda")
+    C.call("ub_transpose_pack", wp, w_t, Cout, 4, Cin, 0, 1, C.UB_BF16, stream())
+    dzd = dev(dz, torch.bfloat16)
+    dx = torch.full((N, h, w, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dx_plain = torch.full((N, h, w, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    partial = torch.full((C.UB_STATS_ROWS * 2 * Cin,), float("nan"), dtype=torch.float32, device="cuda")
+    C.call("ub_deconv2x2_dgrad_bnred", dzd, Cout, w_t, dx, Cin, N, h, w, dev(a, torch.bfloat16), dev(mean, torch.float32), dev(rstd, torch.float32),
+           partial, stream())
+    C.call("ub_deconv2x2_dgrad", dzd, Cout, w_t, dx_plain, Cin, N, h, w, stream())
+    torch.cuda.synchronize()
+    got = dx.double().cpu().numpy()
+    e = rel_err(got, dx_ref)
+    same = bool(torch.equal(dx, dx_plain))
+    s, q = stats_from_partial(partial, Cin)
+    es = rel_err(s, got.sum((0, 1, 2)))
+    eq = rel_err(q, (got * (a - mean.astype(np.float64))).sum((0, 1, 2)) * rstd.astype(np.float64))
+    return dict(err=e, same_as_plain=same, err_sum=es, err_q=eq, ok=bool(e < 1e-2 and same and es < 1e-4 and eq < 1e-4 and np.isfinite(got).all()))
+
+
 def case_bn_pool(C_=128, N=2, H=16, W=24, dtype="bf16", seed=5, dropout=True):
     C = _C()
     rng = np.random.default_rng(seed)
@@ -867,7 +897,9 @@ def case_conv3x3_layer(C0, C1, Cout, N, H, W, seed=30, n_ci=6):
     C.call("ub_transpose_pack", dev(pack_conv(wd), torch.float32), wt, Cout, 9, Cin, 1, 0, C.UB_BF16, stream())
     dx0 = torch.full((N, H, W, C0), float("nan"), dtype=torch.bfloat16, device="cuda")
     dx1 = torch.full((N, H, W, C1), float("nan"), dtype=torch.bfloat16, device="cuda") if C1 else None
-    fused = Cout >= 128                               # unetb200.model.UNet._conv_bwd: where the step fuses the BatchNorm-backward sums
+    # unetb200.model.UNet._conv_bwd: where the step fuses the BatchNorm-backward sums (UB_FUSE_RED64: 1 = 64 -> 64 layers, 2 = dec1a too)
+    red64 = int(os.environ.get("UB_FUSE_RED64", "1"))
+    fused = Cout >= 128 or (Cout == 64 and (red64 >= 2 or (red64 == 1 and C0 == 64 and C1 == 0)))
     if fused:
         Cr = C1 if C1 else C0
         a = x1 if C1 else x0                          # stands in for the saved activation of the tensor being differentiated
@@ -1239,6 +1271,10 @@ CASES = {
     "rows_fwd_bn_cases_ragged": lambda: case_conv_fwd_bn(64, 0, 64, N=2, H=10, W=360, cases=True, seed=100),
     "rows_fwd_cat_ragged": lambda: case_conv3x3_fwd(64, 64, 64, N=1, H=5, W=1000, seed=101),
     "rows_dgrad_ragged": lambda: case_conv3x3_dgrad(64, 64, 0, N=1, H=17, W=360, seed=102),
+    "deconv_dgrad_bnred_128_64": case_deconv_dgrad_bnred,
+    "deconv_dgrad_bnred_256_128": lambda: case_deconv_dgrad_bnred(256, 128, N=3, h=17, w=9, seed=15),
+    "deconv_dgrad_bnred_512_256": lambda: case_deconv_dgrad_bnred(512, 256, N=1, h=8, w=16, seed=16),
+    "deconv_dgrad_bnred_64_64": lambda: case_deconv_dgrad_bnred(64, 64, N=1, h=5, w=33, seed=17),
     "rows_dgrad_bnred_64_64": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=2, H=13, W=256, seed=103),
     "rows_dgrad_bnred_tall": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=1, H=150, W=128, seed=104),
     "rows_dgrad_bnred_ragged": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=1, H=9, W=360, seed=105),

@@ -124,6 +124,14 @@ def test_optional_schedules():
     m2 = DryUNet(2, 1, 1, precision="bf16", seed=0)          # the default
     c2 = _count(_step(m2))
     assert "ub_bn_bwd_sums_wgrad" not in c2 and c2.get("ub_bn_bwd_reduce", 0) + c2.get("ub_conv3x3_dgrad_bnred", 0) == 22
+    # the 64 -> 64 dgrads (enc1b, dec1b) carry the sums of enc1a / dec1a by default
+    assert c2["ub_conv3x3_dgrad_bnred"] == 12 and c2["ub_bn_bwd_reduce"] == 10 and c2["ub_deconv2x2_dgrad"] == 4
+    m3 = DryUNet(2, 1, 1, precision="bf16", seed=0)
+    m3.fuse_bn_reduce_deconv = True         # UB_FUSE_RED_DECONV=1: dec2b / dec3b / dec4b get theirs from the transposed-convolution dgrads
+    m3.fuse_bn_reduce_64 = 2                # UB_FUSE_RED64=2: up1 gets its sums from the dgrad of dec1a
+    c3 = _count(_step(m3))
+    assert c3["ub_deconv2x2_dgrad_bnred"] == 3 and c3["ub_deconv2x2_dgrad"] == 1 and c3["ub_conv3x3_dgrad_bnred"] == 13
+    assert c3["ub_bn_bwd_reduce"] == 6      # the four encoder skips (pool backward), dec1b (head backward), botb (dropout backward)
     folded = {l for (n, l), a in zip(m.calls, m.args) if n == "ub_conv3x3_fwd_bn" and a[6] == 1}
     assert folded == {"enc1b", "enc2b", "enc3b", "enc4b", "botb", "dec4a", "dec4b", "dec3a", "dec3b", "dec2a", "dec2b", "dec1a", "dec1b"}
     # back to the default schedule on the same object
