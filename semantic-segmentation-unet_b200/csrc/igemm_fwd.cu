@@ -477,7 +477,9 @@ static int deconv_dgrad_impl(const void* dz, int Cout, const void* w_t, void* dx
     p.cblk[ab] = Cout / 64;
   }
   p.nsrc = 4;
-  if ((rc = ub_tmap_mat2d(&p.b_map, w_t, Cin, 4ll * Cout, Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64)))) return rc;
+  // the weight box must match the column tile launch() picks: 256 / 128 / 64, and never 256 with the fused reduction
+  const int bn = (Cin % 256 == 0 && !red_partial) ? 256 : (Cin % 128 == 0 ? 128 : 64);
+  if ((rc = ub_tmap_mat2d(&p.b_map, w_t, Cin, 4ll * Cout, bn))) return rc;
   if ((rc = dense_map(&p.o_map[0], dx, Cin, wd, h, N))) return rc;
   p.ntaps = 1;
   p.H = h;

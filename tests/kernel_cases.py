@@ -1275,6 +1275,8 @@ CASES = {
     "deconv_dgrad_bnred_256_128": lambda: case_deconv_dgrad_bnred(256, 128, N=3, h=17, w=9, seed=15),
     "deconv_dgrad_bnred_512_256": lambda: case_deconv_dgrad_bnred(512, 256, N=1, h=8, w=16, seed=16),
     "deconv_dgrad_bnred_64_64": lambda: case_deconv_dgrad_bnred(64, 64, N=1, h=5, w=33, seed=17),
+    "rows_dgrad_cat_64+64": lambda: case_conv3x3_dgrad(64, 64, 64, N=2, H=13, W=256, seed=106),
+    "rows_dgrad_bnred_cat_64+64": lambda: case_conv3x3_dgrad_bnred(64, 64, 64, N=1, H=21, W=128, seed=107),
     "rows_dgrad_bnred_64_64": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=2, H=13, W=256, seed=103),
     "rows_dgrad_bnred_tall": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=1, H=150, W=128, seed=104),
     "rows_dgrad_bnred_ragged": lambda: case_conv3x3_dgrad_bnred(64, 64, 0, N=1, H=9, W=360, seed=105),
