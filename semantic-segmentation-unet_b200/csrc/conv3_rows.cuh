@@ -282,14 +282,15 @@ int launch_c3_rows(Conv3Params& p, const void* const* a_base, const int* a_ch, i
 // the last strip of a row may be ragged; worth it while the padding stays under 1/8 of the row
 static bool rows_width_ok(int W) { return W >= RW && ((W + RW - 1) / RW * RW - W) * 8 <= W; }
 
-// UB_CONV3_ROWS: 0 = off (the halo-patch kernels of igemm_conv3.cu), 1 = 64 -> 64 layers only, 2 (default) = also 128 -> 64 (dec1a forward,
-// enc2a dgrad), 3 = also the 64 -> 64 + 64 dgrad of dec1a as two launches (igemm_conv3.cu: launch()).  Measured on B200 (profiles/r02_ab_runs.md, block N): enc1b dgrad 796 -> 1042 TFLOP/s sustained, dec1a forward 908 -> 1054,
-// enc2a dgrad 905 -> 1136; the step 22.69 -> 22.36 ms.
+// UB_CONV3_ROWS: 0 = off (the halo-patch kernels of igemm_conv3.cu), 1 = 64 -> 64 layers only, 2 = also 128 -> 64 (dec1a forward, enc2a
+// dgrad), 3 (default) = also the 64 -> 64 + 64 dgrad of dec1a as two launches (igemm_conv3.cu: launch()).  Measured on B200
+// (profiles/r02_ab_runs.md, blocks N-R), sustained at the 1000 W cap: enc1b forward 707 -> 968 TFLOP/s, enc1b dgrad 796 -> 1021, dec1a
+// forward 908 -> 1158, dec1a dgrad 930 -> 1084, enc2a dgrad 905 -> 1137; the step 22.7 -> 20.9 ms together with the epilogue changes.
 static int use_rows() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("UB_CONV3_ROWS");
-    v = e ? atoi(e) : 2;
+    v = e ? atoi(e) : 3;
   }
   return v;
 }

@@ -85,8 +85,9 @@ class UNet:
         # (on by default: 21.81 -> 21.59 ms per step, profiles/r02_ab_runs.md block P; UB_FUSE_RED64=0 restores the separate reduction pass)
         # ... and in the transposed-convolution dgrads, for dec2b / dec3b / dec4b (botb sits behind a dropout backward): UB_FUSE_RED_DECONV
         self.fuse_bn_reduce_deconv = os.environ.get("UB_FUSE_RED_DECONV", "0") == "1"
-        # 2: also the dgrad of dec1a (64 -> 64 + 64, the pair kernel), which carries the sums of up1
-        self.fuse_bn_reduce_64 = int(os.environ.get("UB_FUSE_RED64", "1"))
+        # 2 (default): also the dgrad of dec1a (64 -> 64 + 64), which carries the sums of up1 -- where the image width lets the row-streaming
+        # kernel take it (two launches, igemm_conv3.cu); elsewhere the 128-column pair kernel would fetch the `a` tile without look-ahead
+        self.fuse_bn_reduce_64 = int(os.environ.get("UB_FUSE_RED64", "2"))
         # bf16 folded path, optional (UB_BN_ALGEBRA=1): dbeta / dgamma of a BatchNorm whose only consumer is a folded convolution come from that
         # convolution's weight gradient and border sums (ub_bn_bwd_sums_wgrad) instead of a reduction pass over the gradient tensor.  Parity
         # green and 4.3 GB less HBM traffic per step, but the BatchNorm backward of layer L then has to wait for the weight gradient of layer
@@ -871,7 +872,8 @@ class UNet:
                 wgrad()
             # worth it where the K loop is long enough to hide the longer epilogue: layers with >= 128 output channels, and (optional,
             # UB_FUSE_RED64) the 64 -> 64 layers through the row-streaming kernel
-            wide = L.cout >= 128 or (L.cout == 64 and (self.fuse_bn_reduce_64 >= 2 or (self.fuse_bn_reduce_64 == 1 and L.cin == 64)))
+            rows_ok = w >= 128 and ((w + 127) // 128 * 128 - w) * 8 <= w          # csrc/conv3_rows.cuh: rows_width_ok
+            wide = L.cout >= 128 or (L.cout == 64 and ((self.fuse_bn_reduce_64 >= 2 and rows_ok) or (self.fuse_bn_reduce_64 >= 1 and L.cin == 64)))
             if dx0 is not None and red is not None and self.fuse_bn_reduce and wide and not any(p is red for p, _ in algebra):
                 rm, rr = self._bn_vectors(red, True)
                 self._call("ub_conv3x3_dgrad_bnred", dz, L.cout, self.WT[L.name], dx0, c0, dx1, c1, N, h, w, self._b("a:" + red.name), rm, rr,

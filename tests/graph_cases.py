@@ -838,7 +838,7 @@ CASES = {
     "algebra_curve_bf16": _with_env(lambda: case_curve("bf16", steps=100), UB_BN_ALGEBRA="1"),
     "nofold_curve_bf16": _with_fold(lambda: case_curve("bf16", steps=100)),
     "step_pipeline": case_step_pipeline,
-    "reddeconv_wellcond_bf16_n2_256": _with_env(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256), UB_FUSE_RED_DECONV="1", UB_FUSE_RED64="2"),
+    "reddeconv_wellcond_bf16_n2_256": _with_env(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256), UB_FUSE_RED_DECONV="1"),
     # BatchNorm-backward sums of enc1a / dec1a inside the 64 -> 64 row-streaming dgrads (csrc/conv3_rows.cuh, RED = 2) are the default;
     # the separate reduction pass stays covered
     "nored64_wellcond_bf16_n2_256": _with_env(lambda: case_live("bf16", N=2, C=1, H=256, W=256, K=2, seed=3, absolute=BF16_BOUNDS_256), UB_FUSE_RED64="0"),

@@ -898,7 +898,7 @@ def case_conv3x3_layer(C0, C1, Cout, N, H, W, seed=30, n_ci=6):
     dx0 = torch.full((N, H, W, C0), float("nan"), dtype=torch.bfloat16, device="cuda")
     dx1 = torch.full((N, H, W, C1), float("nan"), dtype=torch.bfloat16, device="cuda") if C1 else None
     # unetb200.model.UNet._conv_bwd: where the step fuses the BatchNorm-backward sums (UB_FUSE_RED64: 1 = 64 -> 64 layers, 2 = dec1a too)
-    red64 = int(os.environ.get("UB_FUSE_RED64", "1"))
+    red64 = int(os.environ.get("UB_FUSE_RED64", "2"))
     fused = Cout >= 128 or (Cout == 64 and (red64 >= 2 or (red64 == 1 and C0 == 64 and C1 == 0)))
     if fused:
         Cr = C1 if C1 else C0

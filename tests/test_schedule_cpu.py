@@ -128,10 +128,12 @@ def test_optional_schedules():
     assert c2["ub_conv3x3_dgrad_bnred"] == 12 and c2["ub_bn_bwd_reduce"] == 10 and c2["ub_deconv2x2_dgrad"] == 4
     m3 = DryUNet(2, 1, 1, precision="bf16", seed=0)
     m3.fuse_bn_reduce_deconv = True         # UB_FUSE_RED_DECONV=1: dec2b / dec3b / dec4b get theirs from the transposed-convolution dgrads
-    m3.fuse_bn_reduce_64 = 2                # UB_FUSE_RED64=2: up1 gets its sums from the dgrad of dec1a
-    c3 = _count(_step(m3))
+    assert m3.fuse_bn_reduce_64 == 2        # default: up1 gets its sums from the dgrad of dec1a where the row-streaming kernel takes it
+    c3 = _count(_step(m3, H=16, W=128))
     assert c3["ub_deconv2x2_dgrad_bnred"] == 3 and c3["ub_deconv2x2_dgrad"] == 1 and c3["ub_conv3x3_dgrad_bnred"] == 13
     assert c3["ub_bn_bwd_reduce"] == 6      # the four encoder skips (pool backward), dec1b (head backward), botb (dropout backward)
+    c3 = _count(_step(m3, H=32, W=48))      # a width the row-streaming kernel leaves to the pair kernel: dec1a's dgrad stays plain
+    assert c3["ub_conv3x3_dgrad_bnred"] == 12 and c3["ub_bn_bwd_reduce"] == 7
     folded = {l for (n, l), a in zip(m.calls, m.args) if n == "ub_conv3x3_fwd_bn" and a[6] == 1}
     assert folded == {"enc1b", "enc2b", "enc3b", "enc4b", "botb", "dec4a", "dec4b", "dec3a", "dec3b", "dec2a", "dec2b", "dec1a", "dec1b"}
     # back to the default schedule on the same object
