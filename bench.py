@@ -473,7 +473,7 @@ def run_cuda(args):
                 "serial_ms_per_step": ms_serial},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "conv3_pair_kernel / conv3_kernel (the 17 conv3x3 forward launches)", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
+        "roofline": {"bound": "tensor", "kernel": "conv3_pair_kernel / conv3_rows_kernel (the 17 conv3x3 forward launches)", "achieved": achieved, "peak": peaks["bf16"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["bf16"]) if achieved else None, "traffic": traffic, "peak_source": peaks["src"],
                      "launches_per_step": 17, "algorithmic_tflop_per_step": fam_fl[top] / 1e12,
                      "family_ms_per_step": fam_ms, "family_tflop_per_step": {k: v / 1e12 for k, v in fam_fl.items()},
