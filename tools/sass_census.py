@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "semantic-segmentation-unet_b200", "libunetb200.so")
-PAT = ["UTCHMMA", "2CTA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCATOMSWS", "UTCBAR", "SYNCS", "HMMA", "LDG", "STG", "LDS", "STS", "REDG", "ATOM"]
+PAT = ["UTCHMMA", "2CTA", "UTCQMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "UTCATOMSWS", "UTCBAR", "SYNCS", "HMMA", "LDG", "STG", "LDS", "STS", "REDG", "ATOM"]
 
 
 def main():
