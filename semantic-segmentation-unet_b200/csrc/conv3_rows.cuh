@@ -15,8 +15,15 @@
 // (1.5); activation rows enter shared memory exactly once ({64 ch, 130 px} TMA boxes, no vertical halo re-read).
 //
 // Work = "row units" (image, 128-pixel column strip, row), split evenly over the CTAs in that order; a CTA walks its range as
-// SEGMENTS of consecutive rows of one strip and loads one halo row above and below each segment.
-// Warp roles as in igemm_conv3.cu: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-9 epilogue (epilogue.cuh).
+// SEGMENTS of consecutive rows of one strip and loads one halo row above and below each segment.  The last strip of a row may be
+// ragged (TMA loads zero-fill, TMA stores clip, the statistics mask): rows_width_ok().
+// Warp roles as in igemm_conv3.cu: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2-9 epilogue (epilogue.cuh: bias / 9-case
+// border bias, ReLU, optional inference affine, bf16 staging + TMA store, forward statistics with the last-CTA BatchNorm finalise).
+// RED = 2 (64 -> 64 dgrads): the epilogue also accumulates the BatchNorm-backward sums of the tensor it writes from the matching row of
+// the saved activation, TMA-loaded one row ahead (ub_conv3x3_dgrad_bnred).
+// Barriers: afull / aempty per activation-row stage, wfull (weights, once), rfull[8] (tcgen05.commit: output row complete),
+// rempty[8] (8 warp arrivals: slot drained and zeroed; armed once at start after the initial zero fill of all 512 columns).
+// The index arithmetic is replayed in numpy against a direct convolution in tests/test_rows_schedule_cpu.py.
 #pragma once
 
 constexpr int RW = 128;                      // output pixels per row unit = MMA M
